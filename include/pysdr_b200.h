@@ -1,0 +1,166 @@
+/* pysdr_b200.h — C ABI of the B200-native receive-DSP path (libpysdr_b200.so).
+ *
+ * The reference (aa2il/pySDR) has no FFI: its seam is the Python object protocol of the external
+ * module `sig_proc` (reference receiver.py:45 `import sig_proc as dsp`).  Each entry point below names
+ * the reference call it stands behind.  All functions return 0 on success, <0 on error
+ * (message via pysdr_last_error()); nothing throws across the boundary.  Device buffers are owned by
+ * the caller (PyTorch); the library owns only handles, coefficient tables and scratch.  One handle is
+ * single-threaded; different handles are independent.  `stream` is a cudaStream_t passed as void*.
+ */
+#ifndef PYSDR_B200_H
+#define PYSDR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYSDR_MAX_RX 8          /* reference MAX_RX = 6 (params.py:33) */
+#define PYSDR_AGC_NB 8
+
+/* demodulator kinds: reference Tables.py:34 MODES */
+enum {
+    PYSDR_MODE_AM = 0,          /* also AM-Synch (envelope)             */
+    PYSDR_MODE_USB = 1,         /* also SSB                              */
+    PYSDR_MODE_LSB = 2,
+    PYSDR_MODE_CW = 3,
+    PYSDR_MODE_IQ = 4,          /* also RTTY (IQ feed, receiver.py:286-290) */
+    PYSDR_MODE_NFM = 5
+};
+
+enum {
+    PYSDR_OK = 0,
+    PYSDR_ERR_ARG = -1,
+    PYSDR_ERR_CUDA = -2,
+    PYSDR_ERR_CAPACITY = -3,
+    PYSDR_ERR_ALIGN = -4,       /* process() must start on an IN_CHUNK_SIZE boundary of the stream */
+    PYSDR_ERR_STATE = -5
+};
+
+const char *pysdr_last_error(void);
+int pysdr_version(void);
+
+/* ---- a3: NCO helpers (dsp.signal_generator; reference receiver.py:822,552-553; gui.py:1928) ---- */
+uint64_t pysdr_freq_to_phase_inc(double f_hz, double fs_hz);
+double pysdr_phase_inc_to_freq(uint64_t inc, double fs_hz);
+/* x[i] *= exp(-j*2*pi*(acc0 + i*inc)/2^64), in place or out of place; complex64 device pointers. */
+int pysdr_quad_mixer(const void *d_x, void *d_y, int64_t n, uint64_t acc0, uint64_t inc, void *stream);
+
+/* rx.auto_mute(x) building block (reference receiver.py:238-245): *d_out = mean(|x|^2), float32 device. */
+int pysdr_mean_power(const void *d_x, int64_t n, float *d_out, void *stream);
+
+/* dsp.convolver(h).convolve_fast(x) building block (reference receiver.py:862,216): valid FIR,
+ * out[i] = sum_j taps[j]*src[i+(L-1)-j]; src = L-1 history samples then n new; float32 or complex64. */
+int pysdr_fir_valid(const void *d_src, int src_is_complex, const float *taps_host, int L, int64_t n,
+                    void *d_out, void *stream);
+
+/* ---- a4..a7: receiver bank = all dsp.Receiver objects fed by one IQ stream -------------------- */
+typedef struct pysdr_bank pysdr_bank;
+
+typedef struct {
+    double srate;               /* P.SRATE                                   params.py:222-231 */
+    int32_t up, down;           /* P.UP, P.DOWN = up_dn(SRATE,FS_OUT)        params.py:405     */
+    int64_t in_chunk;           /* P.IN_CHUNK_SIZE (AGC / DC-removal block)  params.py:444     */
+    int32_t n_rx;               /* P.NUM_RX                                                    */
+    int32_t filt_len;           /* P.FILT_LEN, resampler prototype length    params.py:345     */
+    int32_t af_len;             /* demodulator FIR length                                     */
+    int64_t max_in;             /* largest n_in one process() call may carry                  */
+} pysdr_bank_config;
+
+int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out);
+int pysdr_bank_destroy(pysdr_bank *b);
+/* stream reset: histories, AGC, absolute indices (new Receiver objects) */
+int pysdr_bank_reset(pysdr_bank *b);
+
+/* rx.lo.change_freq(f)           reference gui.py:1938, receiver.py:112 */
+int pysdr_bank_set_lo(pysdr_bank *b, int rx, uint64_t phase_inc);
+/* rx.dec.h = rx.dec.filter_bank[idx]   reference gui.py:1713, receiver.py:127 ; h: host float32[n] */
+int pysdr_bank_set_dec_taps(pysdr_bank *b, int rx, const float *h, int n);
+/* P.MODE / P.AF_BW / P.AF_FILTER_NUM / P.BFO as read by demod_data at call time
+ * (reference receiver.py:115,130-131; gui.py:1698,1756-1757).  taps: host float32, n real taps, or n
+ * interleaved (re,im) pairs when is_complex. */
+int pysdr_bank_set_demod(pysdr_bank *b, int rx, int mode, const float *taps, int n, int is_complex,
+                         uint64_t bfo_phase_inc);
+/* rx.agc.reset()                 reference receiver.py:648 */
+int pysdr_bank_agc_reset(pysdr_bank *b, int rx);
+int pysdr_bank_agc_config(pysdr_bank *b, int rx, double ref, double beta);
+/* rx.agc.{agc,gain,maxbuf,ref,err}   reference watchdog.py:298-302 ; synchronises the stream */
+int pysdr_bank_agc_get(pysdr_bank *b, int rx, double out5[5], void *stream);
+
+/* # of audio samples the next process(n_in) will emit per receiver (index arithmetic only). */
+int64_t pysdr_bank_n_out(const pysdr_bank *b, int64_t n_in);
+int64_t pysdr_bank_position(const pysdr_bank *b);          /* absolute input index n0 */
+int64_t pysdr_bank_n_blocks(const pysdr_bank *b, int64_t n_in);
+
+/* rx.demod_data(x) for every receiver of the bank on one shared read of x
+ * (reference receiver.py:235 via :724-725).
+ *   d_iq      complex64[n_in] device; n_in may span many IN_CHUNK_SIZE blocks
+ *   halo_in_place  !=0: d_iq[-(lp-1)..-1] are valid preceding samples and replace the internal filter
+ *                  memory (time-sharded captures); 0: use the memory carried from the previous call
+ *   d_iq_bb   complex64[n_rx][out_stride]  -> rx.iq        (may be NULL)
+ *   d_am      float32  [n_rx][2*out_stride] -> rx.am  (real modes fill the first n_out floats of a row;
+ *             IQ mode fills n_out interleaved complex)
+ *   d_am_dc   like d_am: `am - mean(am)` per block for AM/USB (reference receiver.py:250-252), NULL to skip
+ *   n_out     host, receives the # of audio samples per receiver
+ */
+int pysdr_bank_process(pysdr_bank *b, const void *d_iq, int64_t n_in, int halo_in_place,
+                       void *d_iq_bb, float *d_am, float *d_am_dc, int64_t out_stride,
+                       int64_t *n_out, void *stream);
+
+/* Split form for time-sharded multi-GPU runs: front = everything up to the per-block AGC peaks
+ * (no cross-block dependency), back = AGC recursion + gain/DC application.  Between the two the
+ * caller may all-gather d_peaks across ranks (NCCL) and pass the peaks of ALL earlier blocks.
+ *   d_peaks: float32[n_rx][n_blocks(n_in)] written by front (device).
+ *   back:  d_prev_peaks float32[n_rx][n_prev] = peaks of the n_prev blocks preceding this call's
+ *          first block (NULL/0: continue from the carried AGC state). */
+int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t n_in, int halo_in_place,
+                             void *d_iq_bb, int64_t out_stride, float *d_peaks, int64_t *n_out,
+                             void *stream);
+int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev,
+                            float *d_am, float *d_am_dc, int64_t out_stride, void *stream);
+/* Move the stream position without processing (time shards): n0 must be a multiple of in_chunk.
+ * LO/BFO accumulators follow; filter memories are cleared. */
+int pysdr_bank_seek(pysdr_bank *b, int64_t n0_abs);
+
+/* Checkpoint = carry state (filter memories, AGC, indices) as a flat byte blob. */
+int64_t pysdr_bank_state_size(const pysdr_bank *b);
+int pysdr_bank_get_state(pysdr_bank *b, void *host_blob, int64_t size, void *stream);
+int pysdr_bank_set_state(pysdr_bank *b, const void *host_blob, int64_t size, void *stream);
+
+/* Which K1 variant the next process() will use: 0 generic, 1 tap-stationary fast path. */
+int pysdr_bank_k1_variant(const pysdr_bank *b);
+int pysdr_bank_force_generic(pysdr_bank *b, int on);
+/* # of kernels launched by this handle so far (bench.py's gpu_launches). */
+int64_t pysdr_bank_launch_count(const pysdr_bank *b);
+
+/* ---- a13: scipy.signal.lfilter(b,a,x,zi) with carried state (reference sigs/iir.py:90-105) ----
+ * float64 direct-form-II-transposed, evaluated as a block-parallel linear scan.
+ *   b,a: host float64[nb],[na]; d_x,d_y: device float32[n] (n_ch rows of `stride`);
+ *   d_zi: device float64[n_ch][order] in/out (order = max(na,nb)-1). */
+int pysdr_lfilter(const double *b, int nb, const double *a, int na, const float *d_x, float *d_y,
+                  int64_t n, int n_ch, int64_t stride, double *d_zi, void *stream);
+
+/* ---- a11: dsp.spectrum(fs,chunk,NFFT,overlap) (reference Plotting.py:376-377,462) --------------- */
+typedef struct pysdr_psd pysdr_psd;
+int pysdr_psd_create(int32_t chunk_size, int32_t nfft, int32_t hop, const float *window_host,
+                     pysdr_psd **out);
+int pysdr_psd_destroy(pysdr_psd *p);
+/* Frames k = 0..n_frames-1 start at k*hop, length chunk_size, zero-padded to nfft; every `navg`
+ * consecutive frames are averaged into one output line: d_out float32[n_lines][nfft], fftshifted,
+ * 10*log10 when dB.  complex64 input when is_complex else float32.  Returns # lines via n_lines. */
+int pysdr_psd_lines(pysdr_psd *p, const void *d_x, int64_t n, int is_complex, int32_t navg, int dB,
+                    float *d_out, int64_t *n_lines, void *stream);
+int64_t pysdr_psd_launch_count(const pysdr_psd *p);
+
+/* ---- a12: three_box_plot waterfall compute (reference Plotting.py:536-548,583-587,618-626,689-695)
+ * d_wf float32[nfft][ncols] state; shift-in one line, optional roll by nbins, background =
+ * median(mean(wf[:, -cnt:],1)) -> *d_bkgnd, image = max(wf-bkgnd, max(wf-bkgnd)-pan_dr) -> d_img. */
+int pysdr_waterfall_push(float *d_wf, int32_t nfft, int32_t ncols, int32_t cnt, const float *d_line,
+                         int32_t npsd, int32_t roll_bins, float pan_dr, float *d_img, float *d_bkgnd,
+                         float *d_scratch, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

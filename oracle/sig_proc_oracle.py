@@ -147,7 +147,7 @@ def phase_inc_to_freq(inc, fs):
 
 def nco_phase_cycles(acc0, inc, n):
     """phase (in cycles, in [-0.5,0.5)) of samples acc0 + inc*k for k in n (int array); exact mod-2^64."""
-    k = np.asarray(n).astype(np.uint64)
+    k = np.asarray(n).astype(np.int64).astype(np.uint64)     # negative indices wrap mod 2^64
     with np.errstate(over='ignore'):
         ph = np.uint64(acc0 & MASK64) + np.uint64(inc & MASK64) * k          # wraps mod 2^64
     # OPEN CHOICE: only the top 32 bits feed sin/cos (2^-32 cycle = 1.5e-9 rad resolution).
@@ -171,10 +171,13 @@ class signal_generator:
         self.fo = phase_inc_to_freq(self.inc, self.fs)
         return self.fo
 
+    def advance(self, n):
+        self.acc = (self.acc + self.inc * int(n)) & MASK64
+
     def lo(self, n):
         """n LO samples exp(+j*2*pi*phase) from the current accumulator; advances it."""
         ph = nco_phase_cycles(self.acc, self.inc, np.arange(n))
-        self.acc = (self.acc + self.inc * n) & MASK64
+        self.advance(n)
         z = np.exp(2j * np.pi * ph)
         return z if self.complex else z.real
 
@@ -222,7 +225,11 @@ def n_out_total(n_in, up, down):
 
 class decimator:
     """Streaming polyphase resampler; ``.h`` is assignable from ``.filter_bank[idx]``
-    (reference gui.py:1713, receiver.py:127)."""
+    (reference gui.py:1713, receiver.py:127).
+
+    OPEN CHOICE: the filter memory holds RAW input samples and the LO is applied at filter time
+    (``resamp(x, lo)``): with a fixed LO this is identical to mix-then-filter; after ``change_freq``
+    the new LO is also applied to the (lp-1)-sample memory, phase-continuous at the chunk boundary."""
 
     def __init__(self, srate, up, down, filt_len, video_bws=VIDEO_BWs, video_bw_other=10e3,
                  dtype=np.complex128):
@@ -234,26 +241,37 @@ class decimator:
 
     def reset(self):
         self.n0 = 0                                  # absolute index of the next input sample
-        self.hist = np.zeros(0, self.dtype)
+        self.hist = np.zeros(0, self.dtype)          # raw (un-mixed) input memory
 
     def _lp(self):
         return -(-len(self.h) // self.up)            # taps per polyphase branch (ceil)
 
-    def resamp(self, x):
-        """Definition-level evaluation (gather + dot per phase)."""
-        up, down = self.up, self.down
-        h = np.asarray(self.h, np.float64 if self.dtype == np.complex128 else np.float32)
-        lp = self._lp()
-        hp = np.zeros(lp * up, h.dtype)
-        hp[:len(h)] = h
+    def _extended(self, x, lo, H):
+        """[H raw history samples ; x], mixed with the LO whose accumulator sits at sample n0."""
         x = np.asarray(x).astype(self.dtype)
+        hist = self.hist
+        if len(hist) < H:
+            hist = np.concatenate((np.zeros(H - len(hist), self.dtype), hist))
+        raw = np.concatenate((hist[len(hist) - H:], x))
+        if lo is None:
+            return raw, raw
+        k = np.arange(-H, len(x), dtype=np.int64)
+        ph = nco_phase_cycles(lo.acc, lo.inc, k)      # negative k wraps mod 2^64 = phase run backwards
+        z = np.exp(-2j * np.pi * ph)
+        return raw, (raw * z).astype(self.dtype)
+
+    def resamp(self, x, lo=None):
+        """Definition-level evaluation (gather + dot per phase). Advances lo by len(x)."""
+        up, down = self.up, self.down
+        wide = np.float64 if self.dtype == np.complex128 else np.float32
+        h = np.asarray(self.h, wide)
+        lp = self._lp()
+        hp = np.zeros(lp * up, wide)
+        hp[:len(h)] = h
         n0, n1 = self.n0, self.n0 + len(x)
         m0, m1 = n_out_total(n0, up, down), n_out_total(n1, up, down)
         need = lp - 1
-        hist = self.hist[-need:] if need > 0 else self.hist[:0]
-        if len(hist) < need:
-            hist = np.concatenate((np.zeros(need - len(hist), self.dtype), hist))
-        xx = np.concatenate((hist, x))               # xx[k] <-> absolute index n0 - need + k
+        raw, xx = self._extended(x, lo, need)        # xx[k] <-> absolute index n0 - need + k
         m = np.arange(m0, m1, dtype=np.int64)
         t = m * down
         nm = t // up
@@ -266,32 +284,32 @@ class decimator:
                 continue
             idx = (nm[sel] - (n0 - need))[:, None] - j[None, :]
             y[sel] = xx[idx] @ hp[p::up].astype(self.dtype)
-        self.hist = xx[len(xx) - need:] if need > 0 else xx[:0]
+        self.hist = raw[max(0, len(raw) - (need + down)):]
         self.n0 = n1
+        if lo is not None:
+            lo.advance(len(x))
         return y
 
-    def resamp_fast(self, x):
+    def resamp_fast(self, x, lo=None):
         """Same numbers through scipy.signal.upfirdn (used for CPU-baseline timing)."""
         up, down = self.up, self.down
-        h = np.asarray(self.h, np.float64 if self.dtype == np.complex128 else np.float32)
+        wide = np.float64 if self.dtype == np.complex128 else np.float32
+        h = np.asarray(self.h, wide)
         lp = self._lp()
-        x = np.asarray(x).astype(self.dtype)
         n0, n1 = self.n0, self.n0 + len(x)
         m0, m1 = n_out_total(n0, up, down), n_out_total(n1, up, down)
-        keep = lp - 1 + down                          # history long enough to re-align to DOWN
-        hist = self.hist
-        if len(hist) < keep:
-            hist = np.concatenate((np.zeros(keep - len(hist), self.dtype), hist))
         H = (n0 % down)
         while H < lp - 1:
-            H += down
-        xx = np.concatenate((hist[len(hist) - H:], x))   # xx[0] <-> absolute n0-H, (n0-H)%DOWN==0
+            H += down                                 # (n0-H) % DOWN == 0: upfirdn's grid == ours
+        raw, xx = self._extended(x, lo, H)
         y = signal.upfirdn(h, xx, up, down)
-        q0 = m0 - ((n0 - H) // down) * up                # local index of absolute output m0
+        q0 = m0 - ((n0 - H) // down) * up             # local index of absolute output m0
         y = y[q0:q0 + (m1 - m0)]
-        allx = np.concatenate((hist, x))
-        self.hist = allx[len(allx) - keep:]
+        keep = lp - 1 + down
+        self.hist = raw[max(0, len(raw) - keep):]
         self.n0 = n1
+        if lo is not None:
+            lo.advance(len(x))
         return y.astype(self.dtype)
 
 
@@ -365,8 +383,13 @@ class _holder:
 
 
 class demodulator:
+    """All modes share ONE carried memory: the last L+1 complex baseband samples (L-1 for the FIR,
+    +2 for the 3-point NFM discriminator).  Detection (|.| or discriminator) is recomputed over that
+    memory each call, so a mode change re-interprets the memory under the new mode."""
+
     def __init__(self, fs_out, filt_len, af_bws=AF_BWs, dtype=np.complex128, exact=True):
         self.fs = float(fs_out)
+        self.L = int(filt_len)
         self.filter_bank_real = design_af_bank_real(fs_out, filt_len, af_bws)
         self.filter_bank_cmpx = design_af_bank_cmpx(fs_out, filt_len, af_bws)
         self.filter_bank_lp = design_af_bank_cw(fs_out, filt_len, af_bws)
@@ -380,59 +403,46 @@ class demodulator:
         self.reset()
 
     def reset(self):
-        self.hist_c = np.zeros(0, self.dtype)          # complex pre-detection history (IQ samples)
-        self.hist_r = np.zeros(0, self.rdtype)         # real post-detection history
-        self.prev2 = np.zeros(2, self.dtype)           # NFM: y[n-2], y[n-1]
+        self.hist_c = np.zeros(self.L + 1, self.dtype)
         self.m0 = 0                                    # absolute output index (BFO phase)
 
-    def _fir(self, g, x, which):
-        L = len(g)
-        hist = self.hist_c if which == 'c' else self.hist_r
-        dt = self.dtype if which == 'c' else self.rdtype
-        need = L - 1
-        hist = hist[len(hist) - need:] if len(hist) >= need else \
-            np.concatenate((np.zeros(need - len(hist), dt), hist))
-        xx = np.concatenate((hist, np.asarray(x).astype(dt)))
-        gw = np.asarray(g).astype(self.dtype if np.iscomplexobj(g) else self.rdtype)
-        if self.exact or len(x) < 256:
-            y = np.convolve(xx, gw, mode='valid')
-        else:
-            y = signal.fftconvolve(xx, gw, mode='valid')
-        new_hist = xx[len(xx) - need:] if need > 0 else xx[:0]
-        if which == 'c':
-            self.hist_c = new_hist
-        else:
-            self.hist_r = new_hist
-        return y
+    def _fir(self, g, src, n):
+        """valid convolution: src has len(g)-1+n samples -> n outputs."""
+        g = np.asarray(g)
+        gw = g.astype(self.dtype if np.iscomplexobj(g) else self.rdtype)
+        src = src[len(src) - (len(g) - 1 + n):]
+        if self.exact or n < 256:
+            return np.convolve(src, gw, mode='valid')
+        return signal.fftconvolve(src, gw, mode='valid')
 
     def demod(self, iq, mode, af_idx, bfo_hz):
         """iq: complex baseband chunk @FS_OUT -> pre-AGC audio (real; complex for IQ/RTTY)."""
         iq = np.asarray(iq).astype(self.dtype)
         n = len(iq)
         m = self.m0 + np.arange(n)
+        xx = np.concatenate((self.hist_c, iq))           # xx[k] <-> output index m0-(L+1)+k
         if mode in ('AM', 'AM-Synch'):
-            a = self._fir(self.filter_bank_real[af_idx], np.abs(iq), 'r')
+            a = self._fir(self.filter_bank_real[af_idx], np.abs(xx[2:]), n)
         elif mode in ('USB', 'SSB', 'LSB'):
             g = self.filter_bank_cmpx[af_idx]
             if mode == 'LSB':
                 g = np.conj(g)
-            a = self._fir(g, iq, 'c').real
+            a = self._fir(g, xx[2:], n).real
         elif mode == 'CW':
-            z = self._fir(self.filter_bank_lp[af_idx], iq, 'c')
+            z = self._fir(self.filter_bank_lp[af_idx], xx[2:], n)
             inc = freq_to_phase_inc(bfo_hz, self.fs)
             ph = nco_phase_cycles(0, inc, m)
             a = (z * np.exp(2j * np.pi * ph)).real
         elif mode in ('IQ', 'RTTY'):
-            a = self._fir(self.filter_bank_lp[af_idx], iq, 'c')
+            a = self._fir(self.filter_bank_lp[af_idx], xx[2:], n)
         elif mode == 'NFM':
-            y = np.concatenate((self.prev2, iq))         # y[k] <-> output index m0-2+k
-            d = y[2:] - y[:-2]                           # nfm.m:124  d = IQ - y(1:end-2)
-            y1 = y[1:-1]                                 # nfm.m:125
-            fm = y1.real * d.imag - y1.imag * d.real     # nfm.m:126
-            self.prev2 = y[len(y) - 2:]
-            a = self._fir(self.filter_bank_real[af_idx], fm, 'r')
+            d = xx[2:] - xx[:-2]                         # nfm.m:124  d = IQ - y(1:end-2)
+            y1 = xx[1:-1]                                # nfm.m:125
+            fm = y1.real * d.imag - y1.imag * d.real     # nfm.m:126  (one sample of latency)
+            a = self._fir(self.filter_bank_real[af_idx], fm, n)
         else:
             raise ValueError('mode %s not supported by the oracle' % mode)
+        self.hist_c = xx[len(xx) - (self.L + 1):]
         self.m0 += n
         return a
 
@@ -550,9 +560,7 @@ class Receiver:
     def demod_data(self, x):
         P = self.P
         x = np.asarray(x)
-        z = self.lo.lo(len(x))
-        xm = x.astype(self.dtype) * np.conj(z).astype(self.dtype)
-        iq = self.dec.resamp_fast(xm) if self.fast else self.dec.resamp(xm)
+        iq = self.dec.resamp_fast(x, self.lo) if self.fast else self.dec.resamp(x, self.lo)
         mode = self._mode()
         a = self.demod.demod(iq, mode, _af_index(P, self.irx), per_rx(getattr(P, 'BFO', 0), self.irx))
         if mode not in ('IQ', 'RTTY'):

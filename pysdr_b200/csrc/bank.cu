@@ -1,0 +1,823 @@
+// bank.cu — receiver bank: K2 audio-rate stages + the C ABI of pysdr_bank_* (include/pysdr_b200.h).
+//
+// Stage order of one process() (mirrors dsp.Receiver.demod_data, reference receiver.py:235):
+//   K1  fused mix + polyphase decimate            -> C[rx] = [hc history | n_out new]   (k1_*.cu)
+//   K2a detect (AM |.| , NFM discriminator nfm.m:123-127) -> R[rx]
+//   K2b AF FIR (real / complex->real / complex), CW BFO re-insertion -> a[rx] (pre-AGC audio)
+//   K2c per-block peak of |a|                      -> peaks[rx][block]
+//   K2d AGC recursion over blocks (agc.m loop filter)   -> gains[rx][block]
+//   K2e gain + per-block DC removal (receiver.py:250-252) -> am, am_dc
+//   K2f roll the complex memory
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void pysdr_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *pysdr_last_error(void) { return g_err; }
+extern "C" int pysdr_version(void) { return 100; }
+
+extern "C" uint64_t pysdr_freq_to_phase_inc(double f, double fs) {
+    double r = f / fs;
+    r = r - floor(r);
+    return (uint64_t)(r * 18446744073709551616.0);
+}
+extern "C" double pysdr_phase_inc_to_freq(uint64_t inc, double fs) {
+    return (double)(int64_t)inc / 18446744073709551616.0 * fs;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void quad_mixer_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, i64 n, u64 acc0,
+                                  u64 inc) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const float2 cs = nco_cs(acc0 + inc * (u64)i);
+        const float2 v = x[i];
+        y[i] = make_float2(v.x * cs.x + v.y * cs.y, v.y * cs.x - v.x * cs.y);
+    }
+}
+
+extern "C" int pysdr_quad_mixer(const void *d_x, void *d_y, int64_t n, uint64_t acc0, uint64_t inc,
+                                void *stream) {
+    if (n <= 0) return PYSDR_OK;
+    i64 blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    quad_mixer_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float2 *)d_x, (float2 *)d_y,
+                                                                        n, acc0, inc);
+    LAUNCH_CHECK();
+    return PYSDR_OK;
+}
+
+// mean |x|^2 of a chunk (auto-mute detector); single CTA, deterministic tree
+__global__ void __launch_bounds__(1024) mean_power_kernel(const float2 *__restrict__ x, i64 n, float *__restrict__ out) {
+    __shared__ double sm[32];
+    double acc = 0.0;
+    for (i64 i = threadIdx.x; i < n; i += blockDim.x) {
+        const float2 v = x[i];
+        acc += (double)v.x * v.x + (double)v.y * v.y;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 32; ++w) t += sm[w];
+        out[0] = (float)(t / (double)n);
+    }
+}
+
+extern "C" int pysdr_mean_power(const void *d_x, int64_t n, float *d_out, void *stream) {
+    if (!d_x || !d_out || n < 1) { pysdr_set_error("mean_power: bad arguments"); return PYSDR_ERR_ARG; }
+    mean_power_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((const float2 *)d_x, n, d_out);
+    LAUNCH_CHECK();
+    return PYSDR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2a: detection over the whole complex memory + new samples.  R[k] for k in [0, L-1+n_out):
+//   AM : |C[k+2]|          NFM: Re(C[k+1])*Im(d) - Im(C[k+1])*Re(d), d = C[k+2]-C[k]   (nfm.m:124-126)
+__global__ void detect_kernel(const float2 *__restrict__ C, float *__restrict__ R, i64 n, int nfm) {
+    i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (; k < n; k += stride) {
+        const float2 c2 = C[k + 2];
+        float v;
+        if (nfm) {
+            const float2 c0 = C[k], c1 = C[k + 1];
+            const float dr = c2.x - c0.x, di = c2.y - c0.y;
+            v = c1.x * di - c1.y * dr;
+        } else {
+            v = sqrtf(c2.x * c2.x + c2.y * c2.y);
+        }
+        R[k] = v;
+    }
+}
+
+// K2b: AF FIR.  out[i] = sum_j g[j] * src[i + (L-1) - j],  i in [0, n_out).
+// KIND 0: real src, real taps -> real.  KIND 1: complex src, complex taps -> real part.
+// KIND 2: complex src, real taps -> complex, then optional BFO rotation -> real (CW) or complex (IQ).
+#define FIR_THREADS 256
+#define FIR_PER_THREAD 4
+#define FIR_TILE (FIR_THREADS * FIR_PER_THREAD)
+
+template <int KIND>
+__global__ void __launch_bounds__(FIR_THREADS)
+af_fir_kernel(const void *__restrict__ src_v, const float2 *__restrict__ taps, int L, i64 n_out,
+              float *__restrict__ out, int cw, u64 bfo_inc, i64 m0) {
+    extern __shared__ float4 smem_raw[];
+    typedef typename std::conditional<KIND == 0, float, float2>::type src_t;
+    typedef typename std::conditional<KIND == 1, float2, float>::type tap_t;
+    src_t *s_src = (src_t *)smem_raw;
+    tap_t *s_tap = (tap_t *)(s_src + FIR_TILE + L - 1 + 1);
+    const src_t *src = (const src_t *)src_v;
+    const i64 o0 = (i64)blockIdx.x * FIR_TILE;
+    const int tid = threadIdx.x;
+    const i64 avail = (L - 1) + n_out;                   // valid src elements
+    for (int e = tid; e < FIR_TILE + L - 1; e += FIR_THREADS) {
+        const i64 g = o0 + e;
+        src_t v;
+        if (g < avail) v = src[g];
+        else memset(&v, 0, sizeof(v));
+        s_src[e] = v;
+    }
+    for (int j = tid; j < L; j += FIR_THREADS) {
+        if (KIND == 1) ((float2 *)s_tap)[j] = taps[j];
+        else ((float *)s_tap)[j] = taps[j].x;
+    }
+    __syncthreads();
+
+    float ar[FIR_PER_THREAD], ai[FIR_PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < FIR_PER_THREAD; ++i) { ar[i] = 0.f; ai[i] = 0.f; }
+    const int base = tid + (L - 1);
+#pragma unroll 4
+    for (int j = 0; j < L; ++j) {
+        if (KIND == 0) {
+            const float g = ((const float *)s_tap)[j];
+#pragma unroll
+            for (int i = 0; i < FIR_PER_THREAD; ++i)
+                ar[i] = fmaf(g, ((const float *)s_src)[base + i * FIR_THREADS - j], ar[i]);
+        } else if (KIND == 1) {
+            const float2 g = ((const float2 *)s_tap)[j];
+#pragma unroll
+            for (int i = 0; i < FIR_PER_THREAD; ++i) {
+                const float2 v = ((const float2 *)s_src)[base + i * FIR_THREADS - j];
+                ar[i] = fmaf(g.x, v.x, ar[i]);
+                ar[i] = fmaf(-g.y, v.y, ar[i]);
+            }
+        } else {
+            const float g = ((const float *)s_tap)[j];
+#pragma unroll
+            for (int i = 0; i < FIR_PER_THREAD; ++i) {
+                const float2 v = ((const float2 *)s_src)[base + i * FIR_THREADS - j];
+                ar[i] = fmaf(g, v.x, ar[i]);
+                ai[i] = fmaf(g, v.y, ai[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < FIR_PER_THREAD; ++i) {
+        const i64 o = o0 + tid + i * FIR_THREADS;
+        if (o >= n_out) continue;
+        if (KIND == 2) {
+            if (cw) {
+                const float2 cs = nco_cs(bfo_inc * (u64)(m0 + o));
+                out[o] = ar[i] * cs.x - ai[i] * cs.y;     // Re{ z * e^{+j th} }
+            } else {
+                ((float2 *)out)[o] = make_float2(ar[i], ai[i]);
+            }
+        } else {
+            out[o] = ar[i];
+        }
+    }
+}
+
+// Output index range [lo,hi) (relative to this call) of AGC/DC block b (relative to this call).
+__device__ __forceinline__ void block_range(i64 b, i64 B0, i64 in_chunk, int up, int down, i64 m0, i64 n_out,
+                                            i64 &lo, i64 &hi) {
+    const i64 s = ((i64)up * (B0 + b) * in_chunk + down - 1) / down - m0;
+    const i64 e = ((i64)up * (B0 + b + 1) * in_chunk + down - 1) / down - m0;
+    lo = s < 0 ? 0 : s;
+    hi = e > n_out ? n_out : e;
+}
+
+// K2c: peak of |a| per block.  grid (n_blocks), one launch per receiver.
+__global__ void __launch_bounds__(256)
+block_peak_kernel(const float *__restrict__ a, float *__restrict__ peaks, i64 B0, i64 in_chunk, int up, int down,
+                  i64 m0, i64 n_out) {
+    i64 lo, hi;
+    block_range(blockIdx.x, B0, in_chunk, up, down, m0, n_out, lo, hi);
+    float mx = 0.f;
+    for (i64 i = lo + threadIdx.x; i < hi; i += blockDim.x) mx = fmaxf(mx, fabsf(a[i]));
+    __shared__ float sm[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sm[w]);
+        peaks[blockIdx.x] = mx;
+    }
+}
+
+// K2d: AGC recursion, one thread per receiver.  Law documented in oracle/sig_proc_oracle.py (class agc);
+// loop filter = reference sigs/agc.m:6-12.
+__device__ __forceinline__ float agc_update(AgcState &s, double pk) {
+    s.ring[s.k % PYSDR_AGC_NB] = pk;
+    s.k += 1;
+    double mb = 0.0;
+#pragma unroll
+    for (int i = 0; i < PYSDR_AGC_NB; ++i) mb = fmax(mb, s.ring[i]);
+    s.maxbuf = mb;
+    double want = s.ref / fmax(mb, 1.0e-9);
+    want = fmin(want, 1.0e4);
+    s.err = want - s.gain;
+    if (want < s.gain) s.gain = want;
+    else s.gain = s.beta * want + (1.0 - s.beta) * s.gain;
+    return (float)s.gain;
+}
+
+struct AgcScanArgs {
+    AgcState *state;                 // [n_rx]
+    const float *peaks;              // [n_rx][peaks_stride]
+    i64 peaks_stride;
+    const float *prev_peaks;         // [n_rx][n_prev] or null
+    i64 n_prev;
+    float *gains;                    // [n_rx][gains_stride]
+    i64 gains_stride;
+    i64 n_blocks;
+    int n_rx;
+    int enabled[PYSDR_MAX_RX];
+};
+
+__global__ void agc_scan_kernel(AgcScanArgs p) {
+    const int rx = threadIdx.x;
+    if (rx >= p.n_rx) return;
+    AgcState s = p.state[rx];
+    if (p.prev_peaks) {                 // time shard: replay all earlier blocks from the reset state
+        for (int i = 0; i < PYSDR_AGC_NB; ++i) s.ring[i] = 0.0;
+        s.k = 0; s.gain = 1.0; s.maxbuf = 0.0; s.err = 0.0;
+        for (i64 b = 0; b < p.n_prev; ++b) agc_update(s, (double)p.prev_peaks[(size_t)rx * p.n_prev + b]);
+    }
+    for (i64 b = 0; b < p.n_blocks; ++b) {
+        float g = 1.f;
+        if (p.enabled[rx]) g = agc_update(s, (double)p.peaks[(size_t)rx * p.peaks_stride + b]);
+        p.gains[(size_t)rx * p.gains_stride + b] = g;
+    }
+    p.state[rx] = s;
+}
+
+// K2e: am = a*gain ; am_dc = am - mean_block(am) for AM/USB.  grid (n_blocks), launch per receiver.
+__global__ void __launch_bounds__(256)
+agc_apply_kernel(const float *__restrict__ a, const float *__restrict__ gains, float *__restrict__ am,
+                 float *__restrict__ am_dc, int dc_remove, i64 B0, i64 in_chunk, int up, int down, i64 m0,
+                 i64 n_out) {
+    i64 lo, hi;
+    block_range(blockIdx.x, B0, in_chunk, up, down, m0, n_out, lo, hi);
+    const float g = gains[blockIdx.x];
+    float sum = 0.f;
+    for (i64 i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const float v = a[i] * g;
+        am[i] = v;
+        sum += v;
+    }
+    if (!am_dc) return;
+    __shared__ float sm[8];
+    __shared__ float mean_s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += sm[w];
+        mean_s = (hi > lo && dc_remove) ? t / (float)(hi - lo) : 0.f;
+    }
+    __syncthreads();
+    const float mean = mean_s;
+    for (i64 i = lo + threadIdx.x; i < hi; i += blockDim.x) am_dc[i] = a[i] * g - mean;
+}
+
+__global__ void copy_f32_kernel(const float *__restrict__ s, float *__restrict__ d, i64 n) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) d[i] = s[i];
+}
+
+// K2f / input memory roll: dst[0..len) = src[0..len) where the ranges may overlap (single CTA per row).
+__global__ void __launch_bounds__(1024) roll_kernel(float2 *base, i64 row_stride, i64 src_off, int len) {
+    float2 *row = base + (size_t)blockIdx.x * row_stride;
+    float2 tmp[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = threadIdx.x + k * 1024;
+        if (e < len) tmp[k] = row[src_off + e];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = threadIdx.x + k * 1024;
+        if (e < len) row[e] = tmp[k];
+    }
+}
+
+// new input memory: hist'[k] = sample (n_in - need + k) of the stream [hist | x]
+__global__ void hist_update_kernel(float2 *hist, const float2 *__restrict__ hist_src, const float2 *__restrict__ x,
+                                   int need, i64 n_in) {
+    // single CTA; read everything first (hist may alias hist_src)
+    float2 tmp[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = threadIdx.x + k * 1024;
+        if (e < need) {
+            const i64 idx = n_in - need + e;                 // relative to x[0]
+            tmp[k] = idx >= 0 ? x[idx] : hist_src[need + idx];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = threadIdx.x + k * 1024;
+        if (e < need) hist[e] = tmp[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct pysdr_bank {
+    pysdr_bank_config cfg;
+    int lp, lp_pad, need, hc;
+    i64 max_out, max_blocks, c_stride, r_stride, a_stride;
+    i64 n0;                                  // absolute input index of the next sample
+    u64 inc[PYSDR_MAX_RX], acc0[PYSDR_MAX_RX];   // LO: phase(n) = acc0 + inc*n
+    std::vector<float> dec_h[PYSDR_MAX_RX];
+    bool g_dirty;
+    int mode[PYSDR_MAX_RX];
+    int af_cplx[PYSDR_MAX_RX];
+    u64 bfo_inc[PYSDR_MAX_RX];
+    bool demod_set[PYSDR_MAX_RX];
+    // device
+    float2 *d_hist, *d_g, *d_C, *d_af;
+    float *d_R, *d_a, *d_peaks, *d_gains;
+    AgcState *d_agc;
+    // pending front->back
+    i64 pend_n_out, pend_m0, pend_B0, pend_blocks;
+    const float *pend_peaks;
+    bool pending;
+    bool force_generic;
+    i64 launches;
+};
+
+static int bank_alloc(pysdr_bank *b) {
+    const pysdr_bank_config &c = b->cfg;
+    CUDA_TRY(cudaMalloc(&b->d_hist, sizeof(float2) * (size_t)(b->need + 8)));
+    CUDA_TRY(cudaMalloc(&b->d_g, sizeof(float2) * (size_t)c.n_rx * c.up * b->lp_pad));
+    CUDA_TRY(cudaMalloc(&b->d_C, sizeof(float2) * (size_t)c.n_rx * b->c_stride));
+    CUDA_TRY(cudaMalloc(&b->d_af, sizeof(float2) * (size_t)c.n_rx * c.af_len));
+    CUDA_TRY(cudaMalloc(&b->d_R, sizeof(float) * (size_t)c.n_rx * b->r_stride));
+    CUDA_TRY(cudaMalloc(&b->d_a, sizeof(float2) * (size_t)c.n_rx * b->a_stride));
+    CUDA_TRY(cudaMalloc(&b->d_peaks, sizeof(float) * (size_t)c.n_rx * b->max_blocks));
+    CUDA_TRY(cudaMalloc(&b->d_gains, sizeof(float) * (size_t)c.n_rx * b->max_blocks));
+    CUDA_TRY(cudaMalloc(&b->d_agc, sizeof(AgcState) * PYSDR_MAX_RX));
+    return PYSDR_OK;
+}
+
+static void agc_host_reset(AgcState &s, double ref, double beta) {
+    memset(&s, 0, sizeof(s));
+    s.gain = 1.0;
+    s.ref = ref;
+    s.beta = beta;
+}
+
+extern "C" int pysdr_bank_reset(pysdr_bank *b) {
+    if (!b) { pysdr_set_error("null bank"); return PYSDR_ERR_ARG; }
+    b->n0 = 0;
+    b->pending = false;
+    CUDA_TRY(cudaMemset(b->d_hist, 0, sizeof(float2) * (size_t)(b->need + 8)));
+    CUDA_TRY(cudaMemset(b->d_C, 0, sizeof(float2) * (size_t)b->cfg.n_rx * b->c_stride));
+    AgcState st[PYSDR_MAX_RX];
+    AgcState cur[PYSDR_MAX_RX];
+    CUDA_TRY(cudaMemcpy(cur, b->d_agc, sizeof(cur), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < PYSDR_MAX_RX; ++r) agc_host_reset(st[r], cur[r].ref, cur[r].beta);
+    CUDA_TRY(cudaMemcpy(b->d_agc, st, sizeof(st), cudaMemcpyHostToDevice));
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out) {
+    if (!cfg || !out) { pysdr_set_error("null argument"); return PYSDR_ERR_ARG; }
+    if (cfg->n_rx < 1 || cfg->n_rx > PYSDR_MAX_RX || cfg->up < 1 || cfg->down < 1 || cfg->filt_len < 1 ||
+        cfg->af_len < 1 || cfg->in_chunk < 1 || cfg->max_in < 1) {
+        pysdr_set_error("bad bank config (n_rx=%d up=%d down=%d filt_len=%d af_len=%d)", cfg->n_rx, cfg->up,
+                        cfg->down, cfg->filt_len, cfg->af_len);
+        return PYSDR_ERR_ARG;
+    }
+    pysdr_bank *b = new pysdr_bank();
+    b->cfg = *cfg;
+    b->lp = (cfg->filt_len + cfg->up - 1) / cfg->up;
+    b->lp_pad = k1_fast_lp_pad(b->lp);
+    b->need = b->lp - 1;
+    b->hc = cfg->af_len + 1;
+    if (b->need > 4096 || b->hc > 4096) {
+        pysdr_set_error("filter memories above 4096 samples are not supported (need=%d hc=%d)", b->need, b->hc);
+        delete b;
+        return PYSDR_ERR_ARG;
+    }
+    b->max_out = ((i64)cfg->up * cfg->max_in) / cfg->down + 2;
+    b->max_blocks = (cfg->max_in + cfg->in_chunk - 1) / cfg->in_chunk + 1;
+    b->c_stride = (b->hc + b->max_out + 3) / 2 * 2;
+    b->r_stride = (cfg->af_len - 1 + b->max_out + 3) / 4 * 4;
+    b->a_stride = (b->max_out + 1) / 2 * 2;
+    b->g_dirty = true;
+    b->force_generic = false;
+    b->launches = 0;
+    b->pending = false;
+    for (int r = 0; r < PYSDR_MAX_RX; ++r) {
+        b->inc[r] = 0; b->acc0[r] = 0; b->mode[r] = PYSDR_MODE_IQ; b->af_cplx[r] = 0; b->bfo_inc[r] = 0;
+        b->demod_set[r] = false;
+    }
+    int rc = bank_alloc(b);
+    if (rc) { delete b; return rc; }
+    AgcState st[PYSDR_MAX_RX];
+    for (int r = 0; r < PYSDR_MAX_RX; ++r) agc_host_reset(st[r], 0.25, 0.1);
+    if (cudaMemcpy(b->d_agc, st, sizeof(st), cudaMemcpyHostToDevice) != cudaSuccess) {
+        pysdr_set_error("agc init copy failed");
+        delete b;
+        return PYSDR_ERR_CUDA;
+    }
+    rc = pysdr_bank_reset(b);
+    if (rc) { delete b; return rc; }
+    *out = b;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_destroy(pysdr_bank *b) {
+    if (!b) return PYSDR_OK;
+    cudaFree(b->d_hist); cudaFree(b->d_g); cudaFree(b->d_C); cudaFree(b->d_af); cudaFree(b->d_R);
+    cudaFree(b->d_a); cudaFree(b->d_peaks); cudaFree(b->d_gains); cudaFree(b->d_agc);
+    delete b;
+    return PYSDR_OK;
+}
+
+#define CHECK_RX(b, rx)                                                                    \
+    if (!(b) || (rx) < 0 || (rx) >= (b)->cfg.n_rx) {                                       \
+        pysdr_set_error("bad bank/receiver index %d", (int)(rx));                          \
+        return PYSDR_ERR_ARG;                                                              \
+    }
+
+extern "C" int pysdr_bank_set_lo(pysdr_bank *b, int rx, uint64_t inc) {
+    CHECK_RX(b, rx);
+    // phase-continuous at the current position: acc0' + inc'*n0 == acc0 + inc*n0
+    b->acc0[rx] = b->acc0[rx] + (b->inc[rx] - (u64)inc) * (u64)b->n0;
+    b->inc[rx] = inc;
+    b->g_dirty = true;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_set_dec_taps(pysdr_bank *b, int rx, const float *h, int n) {
+    CHECK_RX(b, rx);
+    if (!h || n < 1 || n > b->cfg.filt_len) {
+        pysdr_set_error("dec taps: n=%d exceeds FILT_LEN=%d", n, b->cfg.filt_len);
+        return PYSDR_ERR_ARG;
+    }
+    b->dec_h[rx].assign(h, h + n);
+    b->g_dirty = true;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_set_demod(pysdr_bank *b, int rx, int mode, const float *taps, int n, int is_complex,
+                                    uint64_t bfo_inc) {
+    CHECK_RX(b, rx);
+    if (mode < PYSDR_MODE_AM || mode > PYSDR_MODE_NFM || !taps || n != b->cfg.af_len) {
+        pysdr_set_error("set_demod: mode=%d n=%d (af_len=%d)", mode, n, b->cfg.af_len);
+        return PYSDR_ERR_ARG;
+    }
+    const bool want_cplx = (mode == PYSDR_MODE_USB || mode == PYSDR_MODE_LSB);
+    if (want_cplx != (is_complex != 0)) {
+        pysdr_set_error("set_demod: mode %d needs %s taps", mode, want_cplx ? "complex" : "real");
+        return PYSDR_ERR_ARG;
+    }
+    std::vector<float2> t(n);
+    for (int j = 0; j < n; ++j) {
+        if (is_complex) t[j] = make_float2(taps[2 * j], taps[2 * j + 1]);   // LSB: host passes conj(g)
+        else t[j] = make_float2(taps[j], 0.f);
+    }
+    CUDA_TRY(cudaMemcpy(b->d_af + (size_t)rx * b->cfg.af_len, t.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    b->mode[rx] = mode;
+    b->af_cplx[rx] = is_complex;
+    b->bfo_inc[rx] = bfo_inc;
+    b->demod_set[rx] = true;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_agc_reset(pysdr_bank *b, int rx) {
+    CHECK_RX(b, rx);
+    AgcState s;
+    CUDA_TRY(cudaMemcpy(&s, b->d_agc + rx, sizeof(s), cudaMemcpyDeviceToHost));
+    agc_host_reset(s, s.ref, s.beta);
+    CUDA_TRY(cudaMemcpy(b->d_agc + rx, &s, sizeof(s), cudaMemcpyHostToDevice));
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_agc_config(pysdr_bank *b, int rx, double ref, double beta) {
+    CHECK_RX(b, rx);
+    AgcState s;
+    CUDA_TRY(cudaMemcpy(&s, b->d_agc + rx, sizeof(s), cudaMemcpyDeviceToHost));
+    s.ref = ref;
+    s.beta = beta;
+    CUDA_TRY(cudaMemcpy(b->d_agc + rx, &s, sizeof(s), cudaMemcpyHostToDevice));
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_agc_get(pysdr_bank *b, int rx, double out5[5], void *stream) {
+    CHECK_RX(b, rx);
+    AgcState s;
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    CUDA_TRY(cudaMemcpy(&s, b->d_agc + rx, sizeof(s), cudaMemcpyDeviceToHost));
+    out5[0] = s.gain; out5[1] = s.gain; out5[2] = s.maxbuf; out5[3] = s.ref; out5[4] = s.err;
+    return PYSDR_OK;
+}
+
+extern "C" int64_t pysdr_bank_n_out(const pysdr_bank *b, int64_t n_in) {
+    if (!b) return -1;
+    return n_out_total(b->n0 + n_in, b->cfg.up, b->cfg.down) - n_out_total(b->n0, b->cfg.up, b->cfg.down);
+}
+extern "C" int64_t pysdr_bank_position(const pysdr_bank *b) { return b ? b->n0 : -1; }
+extern "C" int64_t pysdr_bank_n_blocks(const pysdr_bank *b, int64_t n_in) {
+    if (!b) return -1;
+    return (n_in + b->cfg.in_chunk - 1) / b->cfg.in_chunk;
+}
+extern "C" int pysdr_bank_force_generic(pysdr_bank *b, int on) {
+    if (!b) return PYSDR_ERR_ARG;
+    b->force_generic = on != 0;
+    return PYSDR_OK;
+}
+extern "C" int pysdr_bank_k1_variant(const pysdr_bank *b) {
+    if (!b) return -1;
+    return (!b->force_generic && k1_fast_supported(b->cfg.up, b->cfg.down, b->lp, b->cfg.n_rx)) ? 1 : 0;
+}
+extern "C" int64_t pysdr_bank_launch_count(const pysdr_bank *b) { return b ? b->launches : -1; }
+
+// folded taps: G[rx][p][j] = h[p + j*up] * exp(+j*2*pi*frac(inc*j / 2^64)), zero padded to lp_pad
+static int upload_folded_taps(pysdr_bank *b, cudaStream_t st) {
+    const pysdr_bank_config &c = b->cfg;
+    std::vector<float2> g((size_t)c.n_rx * c.up * b->lp_pad, make_float2(0.f, 0.f));
+    for (int r = 0; r < c.n_rx; ++r) {
+        const std::vector<float> &h = b->dec_h[r];
+        if (h.empty()) { pysdr_set_error("receiver %d has no resampler taps (set_dec_taps)", r); return PYSDR_ERR_STATE; }
+        for (int p = 0; p < c.up; ++p)
+            for (int j = 0; j < b->lp; ++j) {
+                const size_t k = (size_t)p + (size_t)j * c.up;
+                if (k >= h.size()) continue;
+                const u64 ph = b->inc[r] * (u64)j;
+                const double cyc = (double)(int64_t)ph / 18446744073709551616.0;
+                const double ang = 2.0 * M_PI * cyc;
+                g[((size_t)r * c.up + p) * b->lp_pad + j] = make_float2((float)(h[k] * cos(ang)), (float)(h[k] * sin(ang)));
+            }
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->d_g, g.data(), sizeof(float2) * g.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));      // g is a stack-owned staging vector
+    b->g_dirty = false;
+    return PYSDR_OK;
+}
+
+template <int KIND>
+static int launch_fir(pysdr_bank *b, int rx, const void *src, i64 n_out, float *out, int cw, i64 m0, cudaStream_t st) {
+    const int L = b->cfg.af_len;
+    const size_t src_sz = (KIND == 0 ? sizeof(float) : sizeof(float2)) * (size_t)(FIR_TILE + L);
+    const size_t tap_sz = (KIND == 1 ? sizeof(float2) : sizeof(float)) * (size_t)L;
+    const size_t smem = src_sz + tap_sz + 16;
+    if (smem > 48 * 1024) {
+        CUDA_TRY(cudaFuncSetAttribute(af_fir_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    const unsigned grid = (unsigned)((n_out + FIR_TILE - 1) / FIR_TILE);
+    af_fir_kernel<KIND><<<grid, FIR_THREADS, smem, st>>>(src, b->d_af + (size_t)rx * L, L, n_out, out, cw,
+                                                         b->bfo_inc[rx], m0);
+    LAUNCH_CHECK();
+    b->launches++;
+    return PYSDR_OK;
+}
+
+// Standalone streaming-FIR building block (dsp.convolver.convolve_fast, reference receiver.py:862,216):
+// out[i] = sum_j taps[j] * src[i + (L-1) - j], src holds L-1 history samples followed by n new ones.
+extern "C" int pysdr_fir_valid(const void *d_src, int src_is_complex, const float *taps_host, int L, int64_t n,
+                               void *d_out, void *stream) {
+    if (!d_src || !taps_host || !d_out || L < 1 || L > 8192 || n < 0) { pysdr_set_error("fir_valid: bad arguments"); return PYSDR_ERR_ARG; }
+    if (n == 0) return PYSDR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<float2> t(L);
+    for (int j = 0; j < L; ++j) t[j] = make_float2(taps_host[j], 0.f);
+    float2 *d_t = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_t, sizeof(float2) * L, st));
+    CUDA_TRY(cudaMemcpyAsync(d_t, t.data(), sizeof(float2) * L, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const size_t smem = (src_is_complex ? sizeof(float2) : sizeof(float)) * (size_t)(FIR_TILE + L) + sizeof(float) * (size_t)L + 16;
+    const unsigned grid = (unsigned)((n + FIR_TILE - 1) / FIR_TILE);
+    if (src_is_complex) {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(af_fir_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        af_fir_kernel<2><<<grid, FIR_THREADS, smem, st>>>(d_src, d_t, L, n, (float *)d_out, 0, 0ull, 0);
+    } else {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(af_fir_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        af_fir_kernel<0><<<grid, FIR_THREADS, smem, st>>>(d_src, d_t, L, n, (float *)d_out, 0, 0ull, 0);
+    }
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaFreeAsync(d_t, st));
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t n_in, int halo_in_place,
+                                        void *d_iq_bb, int64_t out_stride, float *d_peaks, int64_t *n_out_p,
+                                        void *stream) {
+    if (!b || !d_iq || n_in < 1 || !d_peaks) { pysdr_set_error("process: bad arguments"); return PYSDR_ERR_ARG; }
+    const pysdr_bank_config &c = b->cfg;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_in > c.max_in) { pysdr_set_error("process: n_in=%lld exceeds max_in=%lld", (i64)n_in, (i64)c.max_in); return PYSDR_ERR_CAPACITY; }
+    if (b->n0 % c.in_chunk != 0) {
+        pysdr_set_error("process: stream position %lld is not on an IN_CHUNK_SIZE=%lld boundary", b->n0, (i64)c.in_chunk);
+        return PYSDR_ERR_ALIGN;
+    }
+    for (int r = 0; r < c.n_rx; ++r)
+        if (!b->demod_set[r]) { pysdr_set_error("receiver %d has no demodulator (set_demod)", r); return PYSDR_ERR_STATE; }
+    if (b->g_dirty) { int rc = upload_folded_taps(b, st); if (rc) return rc; }
+
+    const i64 m0 = n_out_total(b->n0, c.up, c.down);
+    const i64 n_out = n_out_total(b->n0 + n_in, c.up, c.down) - m0;
+    if (n_out > b->max_out || (d_iq_bb && n_out > out_stride)) {
+        pysdr_set_error("process: n_out=%lld exceeds capacity/out_stride", n_out);
+        return PYSDR_ERR_CAPACITY;
+    }
+    const i64 B0 = b->n0 / c.in_chunk;
+    const i64 n_blocks = (n_in + c.in_chunk - 1) / c.in_chunk;
+
+    K1Args a;
+    a.x = (const float2 *)d_iq;
+    a.hist = halo_in_place ? a.x - b->need : b->d_hist;
+    a.need = b->need;
+    a.n0 = b->n0; a.n_in = n_in; a.m0 = m0; a.n_out = n_out;
+    a.up = c.up; a.down = c.down; a.lp = b->lp; a.lp_pad = b->lp_pad; a.n_rx = c.n_rx;
+    a.g = b->d_g;
+    for (int r = 0; r < PYSDR_MAX_RX; ++r) { a.acc[r] = b->acc0[r] + b->inc[r] * (u64)b->n0; a.inc[r] = b->inc[r]; }
+    a.c_out = b->d_C; a.c_stride = b->c_stride; a.hc = b->hc;
+    a.bb_out = (float2 *)d_iq_bb; a.bb_stride = out_stride;
+    int rc;
+    if (!b->force_generic && k1_fast_supported(c.up, c.down, b->lp, c.n_rx)) rc = k1_launch_fast(a, st);
+    else rc = k1_launch_generic(a, st);
+    if (rc) return rc;
+    b->launches++;
+
+    // input memory for the next call
+    if (b->need > 0) {
+        hist_update_kernel<<<1, 1024, 0, st>>>(b->d_hist, a.hist, a.x, b->need, n_in);
+        LAUNCH_CHECK();
+        b->launches++;
+    }
+
+    const int L = c.af_len;
+    for (int r = 0; r < c.n_rx; ++r) {
+        float2 *C = b->d_C + (size_t)r * b->c_stride;
+        float *R = b->d_R + (size_t)r * b->r_stride;
+        float *aout = (float *)(b->d_a + (size_t)r * b->a_stride);
+        const int mode = b->mode[r];
+        if (mode == PYSDR_MODE_AM || mode == PYSDR_MODE_NFM) {
+            const i64 nr = (L - 1) + n_out;
+            i64 blocks = (nr + 255) / 256;
+            if (blocks > 148 * 8) blocks = 148 * 8;
+            detect_kernel<<<(unsigned)blocks, 256, 0, st>>>(C, R, nr, mode == PYSDR_MODE_NFM);
+            LAUNCH_CHECK();
+            b->launches++;
+            rc = launch_fir<0>(b, r, R, n_out, aout, 0, m0, st);
+        } else if (mode == PYSDR_MODE_USB || mode == PYSDR_MODE_LSB) {
+            rc = launch_fir<1>(b, r, C + 2, n_out, aout, 0, m0, st);
+        } else {
+            rc = launch_fir<2>(b, r, C + 2, n_out, aout, mode == PYSDR_MODE_CW, m0, st);
+        }
+        if (rc) return rc;
+        if (mode != PYSDR_MODE_IQ) {
+            block_peak_kernel<<<(unsigned)n_blocks, 256, 0, st>>>(aout, d_peaks + (size_t)r * n_blocks, B0, c.in_chunk,
+                                                                 c.up, c.down, m0, n_out);
+            LAUNCH_CHECK();
+            b->launches++;
+        }
+    }
+    // roll the complex memory: C[0..hc) <- C[n_out .. n_out+hc)
+    roll_kernel<<<c.n_rx, 1024, 0, st>>>(b->d_C, b->c_stride, n_out, b->hc);
+    LAUNCH_CHECK();
+    b->launches++;
+
+    b->pend_n_out = n_out; b->pend_m0 = m0; b->pend_B0 = B0; b->pend_blocks = n_blocks;
+    b->pend_peaks = d_peaks;
+    b->pending = true;
+    b->n0 += n_in;
+    if (n_out_p) *n_out_p = n_out;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, float *d_am,
+                                       float *d_am_dc, int64_t out_stride, void *stream) {
+    if (!b || !b->pending) { pysdr_set_error("process_back without process_front"); return PYSDR_ERR_STATE; }
+    if (!d_am) { pysdr_set_error("process_back: d_am is null"); return PYSDR_ERR_ARG; }
+    const pysdr_bank_config &c = b->cfg;
+    cudaStream_t st = (cudaStream_t)stream;
+    const i64 n_out = b->pend_n_out, n_blocks = b->pend_blocks;
+    if (n_out > out_stride) { pysdr_set_error("process_back: out_stride too small"); return PYSDR_ERR_CAPACITY; }
+    AgcScanArgs s;
+    s.state = b->d_agc;
+    s.peaks = b->pend_peaks; s.peaks_stride = n_blocks;
+    s.prev_peaks = (n_prev > 0) ? d_prev_peaks : nullptr; s.n_prev = n_prev;
+    s.gains = b->d_gains; s.gains_stride = b->max_blocks;
+    s.n_blocks = n_blocks; s.n_rx = c.n_rx;
+    for (int r = 0; r < PYSDR_MAX_RX; ++r) s.enabled[r] = (r < c.n_rx && b->mode[r] != PYSDR_MODE_IQ) ? 1 : 0;
+    agc_scan_kernel<<<1, 32, 0, st>>>(s);
+    LAUNCH_CHECK();
+    b->launches++;
+    for (int r = 0; r < c.n_rx; ++r) {
+        const float *aout = (const float *)(b->d_a + (size_t)r * b->a_stride);
+        float *am = d_am + (size_t)r * 2 * out_stride;
+        float *amdc = d_am_dc ? d_am_dc + (size_t)r * 2 * out_stride : nullptr;
+        if (b->mode[r] == PYSDR_MODE_IQ) {
+            i64 n = 2 * n_out, blocks = (n + 255) / 256;
+            if (blocks > 148 * 8) blocks = 148 * 8;
+            copy_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(aout, am, n);
+            LAUNCH_CHECK();
+            b->launches++;
+            if (amdc) {
+                copy_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(aout, amdc, n);
+                LAUNCH_CHECK();
+                b->launches++;
+            }
+        } else {
+            const int dc = (b->mode[r] == PYSDR_MODE_AM || b->mode[r] == PYSDR_MODE_USB) ? 1 : 0;
+            agc_apply_kernel<<<(unsigned)n_blocks, 256, 0, st>>>(aout, b->d_gains + (size_t)r * b->max_blocks, am, amdc, dc,
+                                                                b->pend_B0, c.in_chunk, c.up, c.down, b->pend_m0, n_out);
+            LAUNCH_CHECK();
+            b->launches++;
+        }
+    }
+    b->pending = false;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_process(pysdr_bank *b, const void *d_iq, int64_t n_in, int halo_in_place, void *d_iq_bb,
+                                  float *d_am, float *d_am_dc, int64_t out_stride, int64_t *n_out, void *stream) {
+    if (!b) { pysdr_set_error("null bank"); return PYSDR_ERR_ARG; }
+    int rc = pysdr_bank_process_front(b, d_iq, n_in, halo_in_place, d_iq_bb, out_stride, b->d_peaks, n_out, stream);
+    if (rc) return rc;
+    return pysdr_bank_process_back(b, nullptr, 0, d_am, d_am_dc, out_stride, stream);
+}
+
+extern "C" int pysdr_bank_seek(pysdr_bank *b, int64_t n0_abs) {
+    if (!b || n0_abs < 0 || n0_abs % b->cfg.in_chunk != 0) {
+        pysdr_set_error("seek: position must be a non-negative multiple of IN_CHUNK_SIZE");
+        return PYSDR_ERR_ALIGN;
+    }
+    b->n0 = n0_abs;
+    b->pending = false;
+    CUDA_TRY(cudaMemset(b->d_hist, 0, sizeof(float2) * (size_t)(b->need + 8)));
+    CUDA_TRY(cudaMemset(b->d_C, 0, sizeof(float2) * (size_t)b->cfg.n_rx * b->c_stride));
+    return PYSDR_OK;
+}
+
+// ---- checkpoint ------------------------------------------------------------------------------------
+struct StateHeader {
+    uint32_t magic, version;
+    int32_t n_rx, need, hc, pad;
+    i64 n0;
+    u64 inc[PYSDR_MAX_RX], acc0[PYSDR_MAX_RX];
+};
+
+extern "C" int64_t pysdr_bank_state_size(const pysdr_bank *b) {
+    if (!b) return -1;
+    return (int64_t)(sizeof(StateHeader) + sizeof(AgcState) * PYSDR_MAX_RX + sizeof(float2) * (size_t)b->need +
+                     sizeof(float2) * (size_t)b->cfg.n_rx * b->hc);
+}
+
+extern "C" int pysdr_bank_get_state(pysdr_bank *b, void *blob, int64_t size, void *stream) {
+    if (!b || !blob || size < pysdr_bank_state_size(b)) { pysdr_set_error("get_state: bad blob"); return PYSDR_ERR_ARG; }
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    char *p = (char *)blob;
+    StateHeader h;
+    memset(&h, 0, sizeof(h));
+    h.magic = 0x50534452u; h.version = 1; h.n_rx = b->cfg.n_rx; h.need = b->need; h.hc = b->hc; h.n0 = b->n0;
+    memcpy(h.inc, b->inc, sizeof(h.inc));
+    memcpy(h.acc0, b->acc0, sizeof(h.acc0));
+    memcpy(p, &h, sizeof(h)); p += sizeof(h);
+    CUDA_TRY(cudaMemcpy(p, b->d_agc, sizeof(AgcState) * PYSDR_MAX_RX, cudaMemcpyDeviceToHost)); p += sizeof(AgcState) * PYSDR_MAX_RX;
+    if (b->need) CUDA_TRY(cudaMemcpy(p, b->d_hist, sizeof(float2) * (size_t)b->need, cudaMemcpyDeviceToHost));
+    p += sizeof(float2) * (size_t)b->need;
+    for (int r = 0; r < b->cfg.n_rx; ++r) {
+        CUDA_TRY(cudaMemcpy(p, b->d_C + (size_t)r * b->c_stride, sizeof(float2) * (size_t)b->hc, cudaMemcpyDeviceToHost));
+        p += sizeof(float2) * (size_t)b->hc;
+    }
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_set_state(pysdr_bank *b, const void *blob, int64_t size, void *stream) {
+    if (!b || !blob || size < pysdr_bank_state_size(b)) { pysdr_set_error("set_state: bad blob"); return PYSDR_ERR_ARG; }
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    const char *p = (const char *)blob;
+    StateHeader h;
+    memcpy(&h, p, sizeof(h)); p += sizeof(h);
+    if (h.magic != 0x50534452u || h.version != 1 || h.n_rx != b->cfg.n_rx || h.need != b->need || h.hc != b->hc) {
+        pysdr_set_error("set_state: blob does not match this bank's geometry");
+        return PYSDR_ERR_STATE;
+    }
+    b->n0 = h.n0;
+    memcpy(b->inc, h.inc, sizeof(h.inc));
+    memcpy(b->acc0, h.acc0, sizeof(h.acc0));
+    b->g_dirty = true;
+    b->pending = false;
+    CUDA_TRY(cudaMemcpy(b->d_agc, p, sizeof(AgcState) * PYSDR_MAX_RX, cudaMemcpyHostToDevice)); p += sizeof(AgcState) * PYSDR_MAX_RX;
+    if (b->need) CUDA_TRY(cudaMemcpy(b->d_hist, p, sizeof(float2) * (size_t)b->need, cudaMemcpyHostToDevice));
+    p += sizeof(float2) * (size_t)b->need;
+    for (int r = 0; r < b->cfg.n_rx; ++r) {
+        CUDA_TRY(cudaMemcpy(b->d_C + (size_t)r * b->c_stride, p, sizeof(float2) * (size_t)b->hc, cudaMemcpyHostToDevice));
+        p += sizeof(float2) * (size_t)b->hc;
+    }
+    return PYSDR_OK;
+}

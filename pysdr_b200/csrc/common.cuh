@@ -1,0 +1,77 @@
+// common.cuh — shared declarations for libpysdr_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/pysdr_b200.h"
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+void pysdr_set_error(const char *fmt, ...);
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            pysdr_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return PYSDR_ERR_CUDA;                                                             \
+        }                                                                                      \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) {                                                               \
+            pysdr_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return PYSDR_ERR_CUDA;                                                             \
+        }                                                                                      \
+    } while (0)
+
+static inline i64 ceil_div_i64(i64 a, i64 b) { return -((-a) / b) ; }   // b>0, a>=0 in our uses
+static inline i64 n_out_total(i64 n_in, int up, int down) { return (up * n_in + down - 1) / down; }
+
+// NCO: phase accumulator is an exact u64 fraction of a cycle; only the top 32 bits feed sin/cos.
+// Returns (cos, sin) of 2*pi*phase.
+__device__ __forceinline__ float2 nco_cs(u64 phase) {
+    int top = (int)(phase >> 32);
+    float v = (float)top * 4.656612873077393e-10f;      // 2^-31: half-cycles in [-1,1)
+    float s, c;
+    sincospif(v, &s, &c);
+    return make_float2(c, s);
+}
+
+struct AgcState {
+    double ring[PYSDR_AGC_NB];
+    i64 k;
+    double gain, maxbuf, err, ref, beta;
+};
+
+// ---- K1 arguments (by value) ------------------------------------------------------------------
+struct K1Args {
+    const float2 *x;          // chunk, n_in samples (absolute index n0..)
+    const float2 *hist;       // `need` samples preceding x (absolute n0-need..n0-1)
+    int need;                 // lp-1
+    i64 n0, n_in, m0, n_out;
+    int up, down, lp, lp_pad, n_rx;
+    const float2 *g;          // folded taps [n_rx][up][lp_pad]
+    u64 acc[PYSDR_MAX_RX];    // LO phase at absolute sample n0
+    u64 inc[PYSDR_MAX_RX];
+    float2 *c_out;            // C[rx*c_stride + hc + i]
+    i64 c_stride;
+    int hc;
+    float2 *bb_out;           // optional rx.iq copy [rx*bb_stride + i]
+    i64 bb_stride;
+};
+
+int k1_launch_generic(const K1Args &a, cudaStream_t st);
+// returns 1 if the tap-stationary fast path supports this geometry
+int k1_fast_supported(int up, int down, int lp, int n_rx);
+int k1_launch_fast(const K1Args &a, cudaStream_t st);
+// taps-per-phase padding the fast path wants (multiple of 32)
+int k1_fast_lp_pad(int lp);

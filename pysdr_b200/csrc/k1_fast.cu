@@ -1,0 +1,333 @@
+// K1 (fast variant): fused NCO-mix + polyphase FIR decimate, tap-stationary, sm_100a.
+//
+// Same arithmetic and indexing contract as k1_generic.cu (reference: dsp.Receiver.demod_data's
+// lo/dec stages, receiver.py:235,822,866).  Design:
+//
+//  * persistent grid, one 384-thread CTA per SM; input streamed once from HBM into a 3-stage shared
+//    memory ring by 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) completing on mbarriers;
+//  * a tile = S "super-periods" (DOWN inputs -> UP outputs each); a warp-task = one output phase i,
+//    M consecutive super-periods, NRXP receivers.  The warp keeps the folded complex taps of its
+//    phase for all NRXP receivers in REGISTERS (lane l owns taps l, l+32, ...), so the inner loop is
+//    one LDS.64 of x per 4*NRXP FMAs;
+//  * the 32 lanes' partial dot products (32 accumulators per lane) are summed with a butterfly whose
+//    first steps need no selects: lane bit 4 swizzles which super-period a slot accumulates (half-warp
+//    granular -> conflict-free LDS), lane bits below it swizzle which receiver's taps a slot holds;
+//  * one sincospi per OUTPUT sample from the exact u64 phase accumulator de-rotates the result.
+#include "common.cuh"
+
+#define K1F_WARPS 12
+#define K1F_THREADS (K1F_WARPS * 32)
+#define K1F_STAGES 3
+#define K1F_STAGE_ELEMS 9216          /* float2 per stage: 72 KB */
+
+struct FastGeom {
+    int S;                 // super-periods per tile
+    i64 n_tiles;
+    i64 q_first;           // absolute super-period index of tile 0
+    int rx0;               // first receiver of this launch's group
+    int need_pad;          // lp_pad - 1
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <int NRXP>
+struct Bits {
+    static constexpr int RB = (NRXP == 4) ? 2 : (NRXP == 2 ? 1 : 0);
+    static constexpr int SB = 4 - RB;
+    static constexpr int M = 1 << SB;
+};
+
+template <int NRXP, int TPL>
+__global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a, const FastGeom g) {
+    constexpr int RB = Bits<NRXP>::RB;
+    constexpr int SB = Bits<NRXP>::SB;
+    constexpr int M = Bits<NRXP>::M;
+    constexpr int SLOW = 1 << (SB - 1);          // # values of the non-swizzled low s bits
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long *bars = (unsigned long long *)smem;          // K1F_STAGES mbarriers
+    float2 *stage0 = (float2 *)(smem + 64);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int up = a.up, down = a.down;
+    const int need_pad = g.need_pad;
+    const int par = (int)(((unsigned long long)a.x >> 3) & 1ull);
+    const int S = g.S;
+
+    if (tid == 0) {
+        for (int s = 0; s < K1F_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // tile geometry helpers ---------------------------------------------------------------------
+    auto tile_a2 = [&](i64 T, i64 &a2, int &cnt2) {
+        const i64 q0 = g.q_first + T * S;
+        const i64 ar = q0 * down - need_pad - a.n0;              // rel index of first needed element
+        a2 = ar - ((ar + par) & 1);                              // 16-byte aligned global address
+        const i64 br = (q0 + S) * down - a.n0;
+        int cnt = (int)(br - a2);
+        cnt2 = cnt + (cnt & 1);
+    };
+    auto tile_interior = [&](i64 a2, int cnt2) { return a2 >= 0 && a2 + cnt2 <= a.n_in; };
+
+    auto issue_tile = [&](i64 T, int st) {       // all threads call; after a __syncthreads that freed `st`
+        if (T >= g.n_tiles) return;
+        i64 a2; int cnt2;
+        tile_a2(T, a2, cnt2);
+        float2 *dst = stage0 + (size_t)st * K1F_STAGE_ELEMS;
+        if (tile_interior(a2, cnt2)) {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                const unsigned bytes = (unsigned)cnt2 * 8u;
+                mbar_expect_tx(smem_u32(&bars[st]), bytes);
+                bulk_g2s(smem_u32(dst), a.x + a2, bytes, smem_u32(&bars[st]));
+            }
+        } else {
+            for (int e = tid; e < cnt2; e += K1F_THREADS) {
+                const i64 rel = a2 + e;
+                float2 v = make_float2(0.f, 0.f);
+                if (rel >= 0) { if (rel < a.n_in) v = a.x[rel]; }
+                else if (rel >= -(i64)a.need) v = a.hist[a.need + rel];
+                dst[e] = v;
+            }
+        }
+    };
+
+    // per-lane swizzles ---------------------------------------------------------------------------
+    const int sw_s = (lane >> 4) & 1;                                   // flips the top s bit
+    const int sw_r = (NRXP > 1) ? ((lane >> (4 - RB)) & (NRXP - 1)) : 0;
+
+    float2 tap[NRXP][TPL];
+    int tap_phase_i = -1;
+
+    // prologue: fill the ring
+    const i64 T0 = blockIdx.x;
+    const i64 Tstep = gridDim.x;
+    for (int s = 0; s < K1F_STAGES; ++s) issue_tile(T0 + (i64)s * Tstep, s);
+    __syncthreads();
+
+    const int tasks_per_tile = up * (S / M);
+    unsigned phase_bits = 0;                 // per-stage mbarrier parity (only bulk tiles advance it)
+    i64 it = 0;
+    for (i64 T = T0; T < g.n_tiles; T += Tstep, ++it) {
+        const int st = (int)(it % K1F_STAGES);
+        i64 a2; int cnt2;
+        tile_a2(T, a2, cnt2);
+        if (tile_interior(a2, cnt2)) {
+            mbar_wait(smem_u32(&bars[st]), (phase_bits >> st) & 1u);
+            phase_bits ^= (1u << st);
+        }
+        const float2 *xs = stage0 + (size_t)st * K1F_STAGE_ELEMS;
+        const i64 q0 = g.q_first + T * S;
+        const int shift = (int)((q0 * down - need_pad - a.n0) - a2);     // 0 or 1
+
+        for (int t = warp; t < tasks_per_tile; t += K1F_WARPS) {
+            const int i = t % up;
+            const int sblk = t / up;
+            const int idn = i * down;
+            const int o_i = idn / up;
+            const int p_i = idn - o_i * up;
+            if (i != tap_phase_i) {                                     // (re)load this phase's taps
+#pragma unroll
+                for (int r = 0; r < NRXP; ++r) {
+                    const int rr = g.rx0 + (r ^ sw_r);
+                    const float2 *gp = a.g + ((size_t)rr * up + p_i) * a.lp_pad + lane;
+#pragma unroll
+                    for (int k = 0; k < TPL; ++k)
+                        tap[r][k] = (rr < a.n_rx) ? __ldg(gp + 32 * k) : make_float2(0.f, 0.f);
+                }
+                tap_phase_i = i;
+            }
+            float acc[32];
+#pragma unroll
+            for (int v = 0; v < 32; ++v) acc[v] = 0.f;
+
+#pragma unroll
+            for (int stop = 0; stop < 2; ++stop) {
+#pragma unroll
+                for (int sl = 0; sl < SLOW; ++sl) {
+                    const int s_eff = ((stop ^ sw_s) << (SB - 1)) | sl;
+                    const int e_m = (sblk * M + s_eff) * down + o_i + need_pad + shift - lane;
+                    float2 xv[TPL];
+#pragma unroll
+                    for (int k = 0; k < TPL; ++k) xv[k] = xs[e_m - 32 * k];
+#pragma unroll
+                    for (int k = 0; k < TPL; ++k) {
+#pragma unroll
+                        for (int r = 0; r < NRXP; ++r) {
+                            const int slot = (stop << 4) | (r << (4 - RB)) | (sl << 1);
+                            acc[slot] = fmaf(tap[r][k].x, xv[k].x, acc[slot]);
+                            acc[slot + 1] = fmaf(tap[r][k].x, xv[k].y, acc[slot + 1]);
+                        }
+#pragma unroll
+                        for (int r = 0; r < NRXP; ++r) {
+                            const int slot = (stop << 4) | (r << (4 - RB)) | (sl << 1);
+                            acc[slot] = fmaf(-tap[r][k].y, xv[k].y, acc[slot]);
+                            acc[slot + 1] = fmaf(tap[r][k].y, xv[k].x, acc[slot + 1]);
+                        }
+                    }
+                }
+            }
+
+            // butterfly: lane bit 4 and the RB bits below it are swizzled (no selects) ...
+#pragma unroll
+            for (int step = 0; step < 1 + RB; ++step) {
+                const int off = 16 >> step;
+                const int H = 16 >> step;                               // slots kept
+#pragma unroll
+                for (int v = 0; v < H; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[H + v], off);
+            }
+            // ... the remaining low s bits use selects
+#pragma unroll
+            for (int step = 1 + RB; step < 4; ++step) {
+                const int off = 16 >> step;
+                const int H = 16 >> step;
+                const bool upper = (lane & off) != 0;
+#pragma unroll
+                for (int v = 0; v < H; ++v) {
+                    const float send = upper ? acc[v] : acc[H + v];
+                    const float keep = upper ? acc[H + v] : acc[v];
+                    acc[v] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            const float sr = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 1);
+            const float si = acc[1] + __shfl_xor_sync(0xffffffffu, acc[1], 1);
+
+            // epilogue: lane -> (s, r)
+            const int s_log = (((lane >> 4) & 1) << (SB - 1)) | ((lane >> 1) & (SLOW - 1));
+            const int r_log = (NRXP > 1) ? ((lane >> (4 - RB)) & (NRXP - 1)) : 0;
+            const int rx = g.rx0 + r_log;
+            const i64 q = q0 + (i64)sblk * M + s_log;
+            const i64 m = q * up + i;
+            const i64 oi = m - a.m0;
+            if (rx < a.n_rx && oi >= 0 && oi < a.n_out) {
+                const i64 rel = q * down + o_i - a.n0;
+                const float2 cs = nco_cs(a.acc[rx] + a.inc[rx] * (u64)rel);
+                float2 y;
+                y.x = sr * cs.x + si * cs.y;
+                y.y = si * cs.x - sr * cs.y;
+                if ((lane & 1) == 0) a.c_out[(size_t)rx * a.c_stride + a.hc + oi] = y;
+                else if (a.bb_out) a.bb_out[(size_t)rx * a.bb_stride + oi] = y;
+            }
+        }
+        __syncthreads();                                                // stage `st` is free
+        issue_tile(T + (i64)K1F_STAGES * Tstep, st);
+        // edge tiles are written with plain stores: make them visible before they are consumed
+        // (the __syncthreads at the end of the next iteration orders them; K1F_STAGES >= 2).
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+static int pick_tpl(int lp) {
+    const int need = (lp + 31) / 32;
+    const int opts[] = {4, 8, 11, 16, 22, 32};
+    for (int o : opts) if (need <= o) return o;
+    return -1;
+}
+static int pick_nrxp(int tpl, int n_rx) {
+    int nr = 1;
+    while (nr * 2 <= 4 && nr < n_rx && tpl * nr * 2 <= 48) nr *= 2;
+    return nr;
+}
+int k1_fast_lp_pad(int lp) {
+    const int t = pick_tpl(lp);
+    return t > 0 ? 32 * t : (lp + 31) / 32 * 32;
+}
+static int pick_S(int down, int lp_pad, int M) {
+    i64 s = (K1F_STAGE_ELEMS - lp_pad - 4) / down;
+    s = s / M * M;
+    if (s > 4096) s = 4096 / M * M;
+    return (int)s;
+}
+
+int k1_fast_supported(int up, int down, int lp, int n_rx) {
+    const int tpl = pick_tpl(lp);
+    if (tpl < 0) return 0;
+    const int nrxp = pick_nrxp(tpl, n_rx);
+    const int M = 16 / nrxp;
+    if (pick_S(down, 32 * tpl, M) < M) return 0;
+    if ((i64)up * down > (1 << 30)) return 0;
+    return 1;
+}
+
+template <int NRXP, int TPL>
+static int launch_one(const K1Args &a, const FastGeom &g, int grid, cudaStream_t st) {
+    const size_t smem = 64 + sizeof(float2) * (size_t)K1F_STAGES * K1F_STAGE_ELEMS;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(k1_fast_kernel<NRXP, TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    k1_fast_kernel<NRXP, TPL><<<grid, K1F_THREADS, smem, st>>>(a, g);
+    LAUNCH_CHECK();
+    return PYSDR_OK;
+}
+
+template <int NRXP>
+static int launch_tpl(int tpl, const K1Args &a, const FastGeom &g, int grid, cudaStream_t st) {
+    switch (tpl) {
+        case 4: return launch_one<NRXP, 4>(a, g, grid, st);
+        case 8: return launch_one<NRXP, 8>(a, g, grid, st);
+        case 11: return launch_one<NRXP, 11>(a, g, grid, st);
+        case 16: if (NRXP <= 2) return launch_one<(NRXP <= 2 ? NRXP : 1), 16>(a, g, grid, st); break;
+        case 22: if (NRXP <= 2) return launch_one<(NRXP <= 2 ? NRXP : 1), 22>(a, g, grid, st); break;
+        case 32: if (NRXP == 1) return launch_one<1, 32>(a, g, grid, st); break;
+    }
+    pysdr_set_error("k1_fast: no instantiation for NRXP=%d TPL=%d", NRXP, tpl);
+    return PYSDR_ERR_ARG;
+}
+
+int k1_launch_fast(const K1Args &a, cudaStream_t st) {
+    if (a.n_out <= 0) return PYSDR_OK;
+    const int tpl = pick_tpl(a.lp);
+    if (tpl < 0 || a.lp_pad != 32 * tpl) {
+        pysdr_set_error("k1_fast: lp=%d lp_pad=%d not laid out for the fast path", a.lp, a.lp_pad);
+        return PYSDR_ERR_ARG;
+    }
+    const int nrxp = pick_nrxp(tpl, a.n_rx);
+    const int M = 16 / nrxp;
+    FastGeom g;
+    g.S = pick_S(a.down, a.lp_pad, M);
+    g.need_pad = a.lp_pad - 1;
+    g.q_first = a.m0 / a.up;
+    const i64 q_last = (a.m0 + a.n_out - 1) / a.up;
+    g.n_tiles = (q_last - g.q_first) / g.S + 1;
+    int sms = 148;
+    int grid = (int)(g.n_tiles < sms ? g.n_tiles : sms);
+    for (int rx0 = 0; rx0 < a.n_rx; rx0 += nrxp) {
+        g.rx0 = rx0;
+        int rc;
+        if (nrxp == 4) rc = launch_tpl<4>(tpl, a, g, grid, st);
+        else if (nrxp == 2) rc = launch_tpl<2>(tpl, a, g, grid, st);
+        else rc = launch_tpl<1>(tpl, a, g, grid, st);
+        if (rc) return rc;
+    }
+    return PYSDR_OK;
+}

@@ -1,0 +1,281 @@
+// psd.cu — K3: windowed, zero-padded FFT periodogram with segment averaging, dB mapping and fftshift
+// (dsp.spectrum.periodogram / psd_est; reference Plotting.py:376-377,462, sigs/iq.py:75-79; FFT idiom
+// rtty.py:839-841) and the three_box_plot waterfall compute (reference Plotting.py:536-548,583-587,
+// 618-626,689-695).
+//
+// One CTA owns one (line, split) work item: it loops over its frames, loading chunk_size samples times
+// the window into shared memory (zero padded to nfft), runs an in-place shared-memory FFT and
+// accumulates |X|^2 in registers.  cuFFT is not used anywhere (tests cross-check against numpy).
+#include "common.cuh"
+
+#define PSD_THREADS 512
+
+struct pysdr_psd {
+    int chunk, nfft, hop, log2n;
+    double wsum2;
+    float *d_win;
+    float2 *d_tw;          // nfft/2 twiddles e^{-j 2 pi k / nfft}
+    float *d_part;         // partial sums workspace
+    size_t part_cap;
+    i64 launches;
+};
+
+__device__ __forceinline__ unsigned bitrev(unsigned v, int bits) { return __brev(v) >> (32 - bits); }
+
+// in-place radix-2 decimation-in-frequency FFT; output in bit-reversed order
+__device__ void fft_smem_dif(float2 *s, const float2 *__restrict__ tw, int n, int log2n, int tid, int nthreads) {
+    for (int stage = 0; stage < log2n; ++stage) {
+        const int half = n >> (stage + 1);
+        const int tw_stride = 1 << stage;
+        for (int b = tid; b < (n >> 1); b += nthreads) {
+            const int grp = b / half;
+            const int pos = b - grp * half;
+            const int i0 = grp * 2 * half + pos;
+            const int i1 = i0 + half;
+            const float2 u = s[i0], v = s[i1];
+            const float2 w = __ldg(tw + pos * tw_stride);
+            const float dr = u.x - v.x, di = u.y - v.y;
+            s[i0] = make_float2(u.x + v.x, u.y + v.y);
+            s[i1] = make_float2(dr * w.x - di * w.y, dr * w.y + di * w.x);
+        }
+        __syncthreads();
+    }
+}
+
+// grid (n_split, n_lines). Frames of line l: [l*navg, (l+1)*navg); split s takes frames s, s+n_split, ...
+template <bool CPLX>
+__global__ void __launch_bounds__(PSD_THREADS)
+psd_frames_kernel(const void *__restrict__ xv, i64 n, const float *__restrict__ win, const float2 *__restrict__ tw, int chunk,
+                  int nfft, int log2n, int hop, int navg, int n_split, float *__restrict__ part /* [lines][split][nfft] */) {
+    extern __shared__ __align__(16) float2 s[];
+    const int tid = threadIdx.x;
+    const int line = blockIdx.y, split = blockIdx.x;
+    const int per = nfft / PSD_THREADS;          // nfft >= PSD_THREADS enforced by host (else per = 0 -> handled)
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int f = split; f < navg; f += n_split) {
+        const i64 start = ((i64)line * navg + f) * hop;
+        for (int e = tid; e < nfft; e += PSD_THREADS) {
+            float2 v = make_float2(0.f, 0.f);
+            if (e < chunk) {
+                const float w = win[e];
+                if (CPLX) {
+                    const float2 xx = ((const float2 *)xv)[start + e];
+                    v = make_float2(xx.x * w, xx.y * w);
+                } else {
+                    v = make_float2(((const float *)xv)[start + e] * w, 0.f);
+                }
+            }
+            s[e] = v;
+        }
+        __syncthreads();
+        fft_smem_dif(s, tw, nfft, log2n, tid, PSD_THREADS);
+        if (per >= 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (i < per) {
+                    const int k = tid + i * PSD_THREADS;
+                    const float2 X = s[bitrev((unsigned)k, log2n)];
+                    acc[i] += X.x * X.x + X.y * X.y;
+                }
+            }
+        } else if (tid < nfft) {
+            const float2 X = s[bitrev((unsigned)tid, log2n)];
+            acc[0] += X.x * X.x + X.y * X.y;
+        }
+        __syncthreads();
+    }
+    float *p = part + ((size_t)line * n_split + split) * nfft;
+    if (per >= 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < per) p[tid + i * PSD_THREADS] = acc[i];
+    } else if (tid < nfft) {
+        p[tid] = acc[0];
+    }
+}
+
+// out[line][fftshift(k)] = dB( sum_split part / (navg * wsum2) )
+__global__ void psd_finalize_kernel(const float *__restrict__ part, int nfft, int n_split, float scale, int dB,
+                                    float *__restrict__ out) {
+    const int line = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nfft) return;
+    const float *p = part + (size_t)line * n_split * nfft + k;
+    float sum = 0.f;
+    for (int sp = 0; sp < n_split; ++sp) sum += p[(size_t)sp * nfft];
+    float v = sum * scale;
+    if (dB) v = 10.f * log10f(fmaxf(v, 1.0e-30f));
+    const int ks = (k + nfft / 2) % nfft;        // fftshift
+    out[(size_t)line * nfft + ks] = v;
+}
+
+extern "C" int pysdr_psd_create(int32_t chunk, int32_t nfft, int32_t hop, const float *window, pysdr_psd **out) {
+    if (!out || !window || chunk < 1 || nfft < chunk || hop < 1 || (nfft & (nfft - 1)) != 0 || nfft > 16384 || nfft < 2) {
+        pysdr_set_error("psd_create: need 1 <= chunk <= nfft, nfft a power of two <= 16384 (got chunk=%d nfft=%d hop=%d)", chunk,
+                        nfft, hop);
+        return PYSDR_ERR_ARG;
+    }
+    if (nfft > PSD_THREADS * 32) { pysdr_set_error("psd_create: nfft too large"); return PYSDR_ERR_ARG; }
+    pysdr_psd *p = new pysdr_psd();
+    p->chunk = chunk; p->nfft = nfft; p->hop = hop;
+    p->log2n = 0;
+    while ((1 << p->log2n) < nfft) p->log2n++;
+    p->wsum2 = 0.0;
+    for (int i = 0; i < chunk; ++i) p->wsum2 += (double)window[i] * (double)window[i];
+    p->d_part = nullptr; p->part_cap = 0; p->launches = 0;
+    std::vector<float2> tw(nfft / 2 > 0 ? nfft / 2 : 1);
+    for (int k = 0; k < nfft / 2; ++k) {
+        const double ang = -2.0 * 3.14159265358979323846 * (double)k / (double)nfft;
+        tw[k] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    if (cudaMalloc(&p->d_win, sizeof(float) * chunk) != cudaSuccess || cudaMalloc(&p->d_tw, sizeof(float2) * tw.size()) != cudaSuccess) {
+        pysdr_set_error("psd_create: cudaMalloc failed");
+        delete p;
+        return PYSDR_ERR_CUDA;
+    }
+    CUDA_TRY(cudaMemcpy(p->d_win, window, sizeof(float) * chunk, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(p->d_tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
+    *out = p;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_psd_destroy(pysdr_psd *p) {
+    if (!p) return PYSDR_OK;
+    cudaFree(p->d_win); cudaFree(p->d_tw); cudaFree(p->d_part);
+    delete p;
+    return PYSDR_OK;
+}
+
+extern "C" int64_t pysdr_psd_launch_count(const pysdr_psd *p) { return p ? p->launches : -1; }
+
+extern "C" int pysdr_psd_lines(pysdr_psd *p, const void *d_x, int64_t n, int is_complex, int32_t navg, int dB, float *d_out,
+                               int64_t *n_lines_p, void *stream) {
+    if (!p || !d_x || !d_out || navg < 1) { pysdr_set_error("psd_lines: bad arguments"); return PYSDR_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const i64 n_frames = n < p->chunk ? 0 : 1 + (n - p->chunk) / p->hop;
+    const i64 n_lines = n_frames / navg;
+    if (n_lines_p) *n_lines_p = n_lines;
+    if (n_lines == 0) return PYSDR_OK;
+    int n_split = 1;
+    if (n_lines < 296) {
+        n_split = (int)((296 + n_lines - 1) / n_lines);
+        if (n_split > navg) n_split = navg;
+    }
+    const size_t need = (size_t)n_lines * n_split * p->nfft;
+    if (need > p->part_cap) {
+        if (p->d_part) CUDA_TRY(cudaFree(p->d_part));
+        CUDA_TRY(cudaMalloc(&p->d_part, sizeof(float) * need));
+        p->part_cap = need;
+    }
+    const size_t smem = sizeof(float2) * (size_t)p->nfft;
+    if (smem > 48 * 1024) {
+        CUDA_TRY(cudaFuncSetAttribute(psd_frames_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(psd_frames_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (n_lines > 65535) { pysdr_set_error("psd_lines: more than 65535 lines per call"); return PYSDR_ERR_CAPACITY; }
+    dim3 grid((unsigned)n_split, (unsigned)n_lines);
+    if (is_complex)
+        psd_frames_kernel<true><<<grid, PSD_THREADS, smem, st>>>(d_x, n, p->d_win, p->d_tw, p->chunk, p->nfft, p->log2n, p->hop, navg,
+                                                                n_split, p->d_part);
+    else
+        psd_frames_kernel<false><<<grid, PSD_THREADS, smem, st>>>(d_x, n, p->d_win, p->d_tw, p->chunk, p->nfft, p->log2n, p->hop, navg,
+                                                                 n_split, p->d_part);
+    LAUNCH_CHECK();
+    const float scale = (float)(1.0 / ((double)navg * p->wsum2));
+    dim3 g2((unsigned)((p->nfft + 255) / 256), (unsigned)n_lines);
+    psd_finalize_kernel<<<g2, 256, 0, st>>>(p->d_part, p->nfft, n_split, scale, dB, d_out);
+    LAUNCH_CHECK();
+    p->launches += 2;
+    return PYSDR_OK;
+}
+
+// ---- waterfall (reference Plotting.py) ---------------------------------------------------------------
+// wf is [nfft][ncols] row-major like the reference's numpy array.
+__global__ void wf_shift_kernel(const float *__restrict__ wf_in, float *__restrict__ wf_out, int nfft, int ncols,
+                                const float *__restrict__ line, int npsd, int roll) {
+    // out[r][c] = c < ncols-1 ? in[(r+roll) mod nfft][c+1] : (r<npsd ? line[r] : -1e38)
+    const int r = blockIdx.x;
+    int src = (r + roll) % nfft;
+    if (src < 0) src += nfft;
+    for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+        float v;
+        if (c < ncols - 1) v = wf_in[(size_t)src * ncols + c + 1];
+        else v = (r < npsd) ? line[r] : -1e38f;
+        wf_out[(size_t)r * ncols + c] = v;
+    }
+}
+
+__global__ void wf_rowmean_kernel(const float *__restrict__ wf, int nfft, int ncols, int cnt, float *__restrict__ mean) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nfft) return;
+    double sum = 0.0;
+    for (int c = ncols - cnt; c < ncols; ++c) sum += (double)wf[(size_t)r * ncols + c];
+    mean[r] = (float)(sum / cnt);
+}
+
+// median by rank counting (nfft <= 16384: O(n^2/threads) is fine at display rate); also max of wf[0:npsd]
+__global__ void wf_median_kernel(const float *__restrict__ mean, int nfft, float *__restrict__ bk) {
+    // np.median: average of the two middle order statistics for even n
+    __shared__ float lo_s, hi_s;
+    const int k_lo = (nfft - 1) / 2, k_hi = nfft / 2;
+    for (int i = threadIdx.x; i < nfft; i += blockDim.x) {
+        const float v = mean[i];
+        int less = 0, eq = 0;
+        for (int j = 0; j < nfft; ++j) {
+            const float u = mean[j];
+            less += (u < v);
+            eq += (u == v);
+        }
+        if (less <= k_lo && k_lo < less + eq) lo_s = v;
+        if (less <= k_hi && k_hi < less + eq) hi_s = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) bk[0] = 0.5f * (lo_s + hi_s);
+}
+
+__global__ void wf_max_kernel(const float *__restrict__ wf, i64 n, float *__restrict__ mx) {
+    __shared__ float sm[32];
+    float m = -3.0e38f;
+    for (i64 i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, wf[i]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, sm[w]);
+        mx[0] = m;
+    }
+}
+
+__global__ void wf_image_kernel(const float *__restrict__ wf, i64 n, const float *__restrict__ bk, const float *__restrict__ mx,
+                                float pan_dr, float *__restrict__ img) {
+    const float b = bk[0];
+    const float floor_v = (mx[0] - b) - pan_dr;
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) img[i] = fmaxf(wf[i] - b, floor_v);
+}
+
+extern "C" int pysdr_waterfall_push(float *d_wf, int32_t nfft, int32_t ncols, int32_t cnt, const float *d_line, int32_t npsd,
+                                    int32_t roll_bins, float pan_dr, float *d_img, float *d_bkgnd, float *d_scratch, void *stream) {
+    // d_scratch: nfft*ncols (shifted copy) + nfft (row means) + 2 floats
+    if (!d_wf || !d_line || !d_img || !d_bkgnd || !d_scratch || nfft < 1 || ncols < 2 || cnt < 1 || cnt > ncols || npsd > nfft) {
+        pysdr_set_error("waterfall_push: bad arguments");
+        return PYSDR_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float *tmp = d_scratch, *mean = d_scratch + (size_t)nfft * ncols, *mx = mean + nfft;
+    wf_shift_kernel<<<nfft, 128, 0, st>>>(d_wf, tmp, nfft, ncols, d_line, npsd, roll_bins);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(d_wf, tmp, sizeof(float) * (size_t)nfft * ncols, cudaMemcpyDeviceToDevice, st));
+    wf_rowmean_kernel<<<(nfft + 255) / 256, 256, 0, st>>>(d_wf, nfft, ncols, cnt, mean);
+    LAUNCH_CHECK();
+    wf_median_kernel<<<1, 1024, 0, st>>>(mean, nfft, d_bkgnd);
+    LAUNCH_CHECK();
+    wf_max_kernel<<<1, 1024, 0, st>>>(d_wf, (i64)npsd * ncols, mx);
+    LAUNCH_CHECK();
+    wf_image_kernel<<<148, 256, 0, st>>>(d_wf, (i64)npsd * ncols, d_bkgnd, mx, pan_dr, d_img);
+    LAUNCH_CHECK();
+    return PYSDR_OK;
+}

@@ -1,0 +1,355 @@
+"""Drop-in for the L1 surface pySDR imports as ``import sig_proc as dsp`` (reference receiver.py:45,
+Plotting.py:31, params.py, srates.py:26) — same names, argument meaning and error behaviour, with the
+arithmetic done by hand-written sm_100a kernels behind the C ABI (libpysdr_b200.so).
+
+Surface:  up_dn, signal_generator, Receiver, spectrum, ring_buffer2, ring_buffer3, bpf, convolver.
+Host numpy arrays in / out, exactly like the reference's callers expect; device-resident batch processing
+lives in bank.ReceiverBank / receiver.py.
+"""
+import ctypes
+import queue
+
+import numpy as np
+import torch
+
+from . import _lib, design
+from ._lib import PysdrError, check
+from .bank import ReceiverBank, _stream_ptr
+from .design import up_dn, bpf                      # noqa: F401  (re-exported reference names)
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise PysdrError("pysdr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda:%d" % torch.cuda.current_device())
+
+
+# ---------------------------------------------------------------------------------------------------
+class signal_generator:
+    """NCO (reference receiver.py:822 ``dsp.signal_generator(f, N, fs, True)``; ``.quad_mixer(x)``
+    receiver.py:552-553; ``.change_freq(f)`` returns the applied frequency, gui.py:1928)."""
+
+    def __init__(self, f, N, fs, cmplx=True):
+        self.lib = _lib.load()
+        self.N = int(N)
+        self.fs = float(fs)
+        self.complex = bool(cmplx)
+        self.acc = 0
+        self.change_freq(f)
+
+    def change_freq(self, f):
+        self.inc = design.freq_to_phase_inc(f, self.fs)
+        self.fo = design.phase_inc_to_freq(self.inc, self.fs)
+        return self.fo
+
+    def quad_mixer(self, x):
+        dev = _dev()
+        host = not isinstance(x, torch.Tensor)
+        xd = torch.from_numpy(np.ascontiguousarray(x, np.complex64)).to(dev) if host else x.contiguous()
+        y = torch.empty_like(xd)
+        n = xd.numel()
+        check(self.lib.pysdr_quad_mixer(ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(y.data_ptr()), n,
+                                        ctypes.c_uint64(self.acc), ctypes.c_uint64(self.inc), _stream_ptr()))
+        self.acc = (self.acc + self.inc * n) & ((1 << 64) - 1)
+        return y.cpu().numpy() if host else y
+
+
+# ---------------------------------------------------------------------------------------------------
+class _Lo:
+    def __init__(self, rx):
+        self._rx = rx
+
+    @property
+    def fo(self):
+        return self._rx._bank.fo[0]
+
+    def change_freq(self, f):
+        return self._rx._bank.set_freq(0, f)
+
+
+class _Dec:
+    """``rx.dec.h`` is assignable from ``rx.dec.filter_bank[idx]`` (reference gui.py:1713, receiver.py:127)."""
+
+    def __init__(self, rx):
+        self._rx = rx
+        self.filter_bank = rx._bank.filter_bank
+        self._h = self.filter_bank[design.video_index(rx.P, rx._bank.video_bws)]
+
+    @property
+    def h(self):
+        return self._h
+
+    @h.setter
+    def h(self, taps):
+        self._rx._bank.set_dec_taps(0, taps)          # takes effect at the next chunk boundary
+        self._h = np.asarray(taps, np.float32)
+
+
+class _Pll:
+    def reset(self):                                     # reference receiver.py:649
+        pass
+
+
+class _Holder:
+    pass
+
+
+class _Demod:
+    def __init__(self, rx):
+        b = rx._bank
+        self.filter_bank_real = b.filter_bank_real      # reference receiver.py:873
+        self.filter_bank_cmpx = b.filter_bank_cmpx      # reference receiver.py:874
+        self.am_pll = _Pll()
+        self.wfm_video = _Holder()
+        self.wfm_video.h = None
+        self.wfm_filter_bank = []
+
+
+class _Agc:
+    """``rx.agc.reset()`` (reference receiver.py:648) and the read-outs of reference watchdog.py:298-302."""
+
+    def __init__(self, rx):
+        self._rx = rx
+
+    def reset(self):
+        self._rx._bank.agc_reset(0)
+
+    def _get(self, k):
+        return self._rx._bank.agc_get(0)[k]
+
+    agc = property(lambda s: s._get('agc'))
+    gain = property(lambda s: s._get('gain'))
+    maxbuf = property(lambda s: s._get('maxbuf'))
+    ref = property(lambda s: s._get('ref'))
+    err = property(lambda s: s._get('err'))
+
+
+class Receiver:
+    """``dsp.Receiver(P, frq, irx, name, VIDEO_BWs, AF_BWs)`` (reference receiver.py:65,835).
+
+    ``demod_data(x)`` takes the caller-owned complex64 chunk (copied to the device before returning, the
+    caller may reuse it — reference receiver.py:445,588) and returns ``am``; side effects ``.am``, ``.iq``
+    stay valid until the next call."""
+
+    AUTO_MUTE_THRESH = 0.25
+
+    def __init__(self, P, frq, irx, name, video_bws=design.VIDEO_BWs, af_bws=design.AF_BWs):
+        self.P = P
+        self.irx = irx
+        self.name = name
+        self.sub = 0
+        self._view = _PView(P, irx)
+        self._bank = ReceiverBank(self._view, [frq], max_in=int(P.IN_CHUNK_SIZE), video_bws=video_bws, af_bws=af_bws)
+        self.lo = _Lo(self)
+        self.dec = _Dec(self)
+        self.demod = _Demod(self)
+        self.agc = _Agc(self)
+        self.am = np.zeros(0, np.float32)
+        self.iq = np.zeros(0, np.complex64)
+        self.am_dc = np.zeros(0, np.float32)
+        self.mute_cnt = 0
+        self._pw = torch.zeros(1, dtype=torch.float32, device=self._bank.device)
+
+    def demod_data(self, x):
+        am, iq, dc = self._bank.process_host(x)
+        self.am, self.iq, self.am_dc = am[0], iq[0], dc[0]
+        return self.am
+
+    def auto_mute(self, x):
+        """Mute while mean|x|^2 exceeds the threshold, held for MUTE_CHUNKS calls (reference receiver.py:238-245,
+        params.py:447-450)."""
+        xd = torch.from_numpy(np.ascontiguousarray(x, np.complex64)).to(self._bank.device)
+        check(self._bank.lib.pysdr_mean_power(ctypes.c_void_p(xd.data_ptr()), xd.numel(),
+                                              ctypes.c_void_p(self._pw.data_ptr()), _stream_ptr()))
+        if float(self._pw.item()) > self.AUTO_MUTE_THRESH:
+            self.mute_cnt = int(self.P.MUTE_CHUNKS)
+        elif self.mute_cnt > 0:
+            self.mute_cnt -= 1
+        return self.mute_cnt > 0
+
+
+class _PView:
+    """What a single Receiver sees of P: per-RX entries of list-valued MODE/AF_BW/... are projected to its
+    own index; everything is read through to P at call time."""
+
+    def __init__(self, P, irx):
+        object.__setattr__(self, '_P', P)
+        object.__setattr__(self, '_irx', irx)
+
+    def __getattr__(self, k):
+        v = getattr(object.__getattribute__(self, '_P'), k)
+        if k in ('MODE', 'AF_BW', 'AF_FILTER_NUM', 'BFO'):
+            return design.per_rx(v, object.__getattribute__(self, '_irx'))
+        return v
+
+
+# ---------------------------------------------------------------------------------------------------
+class spectrum:
+    """``dsp.spectrum(fs, chunk_size, NFFT, overlap, TAG=)`` (reference Plotting.py:376-377); attributes
+    ``NFFT frq frq2 df fs chunk_size new_samps`` (Plotting.py:467,594,690; gui.py:1259,1289-1290,1369)."""
+
+    def __init__(self, fs, chunk_size, NFFT, overlap, TAG=''):
+        self.lib = _lib.load()
+        self.fs = fs
+        self.chunk_size = int(chunk_size)
+        self.NFFT = int(NFFT)
+        self.overlap = overlap
+        self.TAG = TAG
+        self.new_samps = int(self.chunk_size * (1 - overlap))
+        from scipy import signal as _sig
+        self.win = _sig.get_window('hann', self.chunk_size, fftbins=True).astype(np.float32)
+        self.df = fs / float(self.NFFT)
+        self.frq = (np.arange(self.NFFT) - self.NFFT // 2) * self.df
+        self.frq2 = self.frq
+        self.device = _dev()
+        if self.NFFT & (self.NFFT - 1):
+            raise PysdrError("spectrum: NFFT=%d is not a power of two (the reference's 65636-point RF panel, "
+                             "Plotting.py:370-375, is not served yet)" % self.NFFT)
+        h = ctypes.c_void_p()
+        check(self.lib.pysdr_psd_create(self.chunk_size, self.NFFT, max(1, self.new_samps),
+                                        self.win.ctypes.data_as(ctypes.c_void_p), ctypes.byref(h)))
+        self.h = h
+        self.buf = torch.zeros(self.chunk_size, dtype=torch.complex64, device=self.device)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.pysdr_psd_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _to_dev(self, y):
+        if isinstance(y, torch.Tensor):
+            return y.to(self.device).to(torch.complex64).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(y).astype(np.complex64))).to(self.device)
+
+    def _lines(self, x, navg, dB):
+        n = x.numel()
+        nfr = 0 if n < self.chunk_size else 1 + (n - self.chunk_size) // max(1, self.new_samps)
+        nl = nfr // navg
+        out = torch.empty((max(nl, 1), self.NFFT), dtype=torch.float32, device=self.device)
+        got = ctypes.c_int64(0)
+        check(self.lib.pysdr_psd_lines(self.h, ctypes.c_void_p(x.data_ptr()), n, 1, int(navg), 1 if dB else 0,
+                                       ctypes.c_void_p(out.data_ptr()), ctypes.byref(got), _stream_ptr()))
+        return out[:got.value]
+
+    def periodogram(self, y, dB=True):
+        """One frame; the newest len(y) samples are shifted into the chunk_size window.  Returns [] on
+        error like the reference (Plotting.py:463-465)."""
+        n = len(y)
+        if n == 0 or n > self.chunk_size:
+            return []
+        yd = self._to_dev(y)
+        self.buf = torch.cat((self.buf[n:], yd))
+        return self._lines(self.buf, 1, dB)[0].cpu().numpy()
+
+    def psd_est(self, x, dB=True):
+        """Welch average over all full frames (reference sigs/iq.py:75-79)."""
+        xd = self._to_dev(x)
+        n = xd.numel()
+        if n < self.chunk_size:
+            return []
+        nfr = 1 + (n - self.chunk_size) // max(1, self.new_samps)
+        return self._lines(xd, nfr, dB)[0].cpu().numpy()
+
+    def waterfall(self, x, navg, dB=True, to_host=True):
+        out = self._lines(self._to_dev(x), navg, dB)
+        return out.cpu().numpy() if to_host else out
+
+
+# ---------------------------------------------------------------------------------------------------
+class convolver:
+    """``dsp.convolver(h, dtype).convolve_fast(x)`` (reference receiver.py:862,216): streaming FIR with
+    carried history on the device (pysdr_fir_valid)."""
+
+    def __init__(self, h, dtype=np.float32):
+        self.lib = _lib.load()
+        self.h = np.ascontiguousarray(h, np.float32)
+        self.dtype = dtype
+        self.device = _dev()
+        self.hist = None
+
+    def convolve_fast(self, x):
+        x = np.asarray(x)
+        cplx = np.iscomplexobj(x)
+        tdt = torch.complex64 if cplx else torch.float32
+        xd = torch.from_numpy(np.ascontiguousarray(x.astype(np.complex64 if cplx else np.float32))).to(self.device)
+        L = len(self.h)
+        if self.hist is None or self.hist.dtype != tdt:
+            self.hist = torch.zeros(L - 1, dtype=tdt, device=self.device)
+        src = torch.cat((self.hist, xd)).contiguous()
+        out = torch.empty(xd.numel(), dtype=tdt, device=self.device)
+        check(self.lib.pysdr_fir_valid(ctypes.c_void_p(src.data_ptr()), 1 if cplx else 0,
+                                       self.h.ctypes.data_as(ctypes.c_void_p), L, xd.numel(),
+                                       ctypes.c_void_p(out.data_ptr()), _stream_ptr()))
+        self.hist = src[src.numel() - (L - 1):].clone()
+        y = out.cpu().numpy()
+        return y if cplx else y.astype(self.dtype)
+
+
+# ---------------------------------------------------------------------------------------------------
+class ring_buffer2:
+    """Host-side sample FIFO (reference pySDR.py:103-112, watchdog.py:153-156,190,197, gui.py:1264-1266).
+    Plumbing only — stays in Python like the reference."""
+
+    def __init__(self, tag, size, PREVENT_OVERFLOW=False, BLOCK=False):
+        self.tag = tag
+        self.size = int(size)
+        self.prevent_overflow = PREVENT_OVERFLOW
+        self.buf = queue.Queue()
+        self.data = None
+        self.nsamps = 0
+
+    def clear(self):
+        self.data = None
+        self.nsamps = 0
+
+    def push(self, x):
+        x = np.asarray(x)
+        if self.data is None or self.nsamps == 0:
+            self.data = x.copy()
+        else:
+            self.data = np.concatenate((self.data[-self.nsamps:], x))
+        if len(self.data) > self.size:                  # overflow: keep the newest `size` samples
+            if self.prevent_overflow:
+                self.data = self.data[:self.size]
+            else:
+                self.data = self.data[len(self.data) - self.size:]
+        self.nsamps = len(self.data)
+        return self.nsamps
+
+    def push_zeros(self, n):
+        dt = self.data.dtype if self.data is not None else np.float32
+        return self.push(np.zeros(int(n), dt))
+
+    def ready(self, n):
+        return self.nsamps >= n
+
+    def pull(self, n, flush=False):
+        """Oldest n samples; flush=True discards everything older than the newest n first (gui.py:1264)."""
+        n = int(n)
+        if self.nsamps < n:
+            return np.zeros(0, np.float32)
+        d = self.data[-self.nsamps:]
+        if flush:
+            out = d[len(d) - n:]
+            self.data = None
+            self.nsamps = 0
+            return out
+        out = d[:n]
+        self.data = d[n:]
+        self.nsamps = len(self.data)
+        return out
+
+
+class ring_buffer3(ring_buffer2):
+    """Queue-backed variant used by mp.py (reference mp.py:90-95: ``*_psd_Q = rb.buf``)."""
+
+    def __init__(self, tag, size):
+        super().__init__(tag, size)
+
+    def pull(self, n, flush=False):
+        while not self.buf.empty():
+            self.push(self.buf.get())
+        return super().pull(n, flush)

@@ -1,0 +1,139 @@
+"""CPU tests: host-side control plane equals the oracle's restatement; the C-ABI library loads and exports
+every symbol include/pysdr_b200.h declares (no compute calls — there is no GPU here)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import receiver_oracle as rxo
+from oracle import sig_proc_oracle as odsp
+from pysdr_b200 import design
+from tests.util import make_both
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from pysdr_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "pysdr_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(pysdr_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 30
+    for n in sorted(names):
+        assert hasattr(lib, n), "symbol %s declared in the header is not exported" % n
+        assert n in _lib.SIGNATURES, "symbol %s has no ctypes signature" % n
+    assert lib.pysdr_version() >= 100
+
+
+def test_phase_inc_matches_oracle_and_c():
+    from pysdr_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for f, fs in [(99975.5859375, 8e6), (-1.5e6, 8e6), (700.0, 48000.0), (0.0, 1e6), (1e6 - 1e-3, 2.048e6)] + \
+            [(float(rng.uniform(-4e6, 4e6)), 8e6) for _ in range(50)]:
+        a = design.freq_to_phase_inc(f, fs)
+        assert a == odsp.freq_to_phase_inc(f, fs) == lib.pysdr_freq_to_phase_inc(f, fs)
+        assert design.phase_inc_to_freq(a, fs) == odsp.phase_inc_to_freq(a, fs) == lib.pysdr_phase_inc_to_freq(a, fs)
+
+
+def test_params_match_oracle_derivations():
+    for args in [dict(srate_mhz=8, fcs_khz=[-500, 700, 1400, 3100], modes=['AM', 'NFM', 'USB', 'CW'], af_bw_khz=[5, 10, 2, .5]),
+                 dict(srate_mhz=2.048, fcs_khz=[1000], modes=['USB'], af_bw_khz=[2]),
+                 dict(srate_mhz=10, fcs_khz=[7000, 7100], modes=['CW'], foffset_khz=0)]:
+        P, Po = make_both(**args)
+        for k in ('SRATE', 'UP', 'DOWN', 'FS_OUT', 'IN_CHUNK_SIZE', 'OUT_CHUNK_SIZE', 'RB_SIZE', 'FOFFSET', 'MUTE_CHUNKS',
+                  'VIDEO_BW', 'FILT_LEN', 'NUM_RX', 'AF_GAIN'):
+            assert getattr(P, k) == getattr(Po, k), k
+        assert list(np.atleast_1d(P.BFO)) == list(np.atleast_1d(Po.BFO))
+        assert list(np.atleast_1d(P.AF_BW)) == list(np.atleast_1d(Po.AF_BW))
+        np.testing.assert_array_equal(P.FC, Po.FC)
+
+
+def test_filter_designs_bit_equal_oracle():
+    for srate, up, down, L in [(8e6, 3, 500, 1001), (2.048e6, 3, 128, 1001), (2.4e6, 1, 50, 301)]:
+        a = design.resampler_bank(srate, up, down, L)
+        b = odsp.design_resampler_bank(srate, up, down, L)
+        assert len(a) == len(b) == 16                       # Tables.py:41-42 incl. 'Max' and 'Other'
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+    for fn_a, fn_b in [(design.af_bank_real, odsp.design_af_bank_real), (design.af_bank_cmpx, odsp.design_af_bank_cmpx),
+                       (design.af_bank_lp, odsp.design_af_bank_cw)]:
+        a, b = fn_a(48000, 1001), fn_b(48000, 1001)
+        assert len(a) == len(b) == 18
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+
+
+def test_index_selection_rules():
+    P, Po = make_both(8, [1000], ['USB'], af_bw_khz=[2])
+    assert design.af_index(P) == odsp._af_index(Po) == 5             # '2 KHz'
+    assert design.video_index(P) == odsp._video_index(Po) == 2       # default 10 kHz -> '10 KHz' (gui.py:1675-1685)
+    P.AF_BW = 1234.0
+    assert design.af_index(P) == 0                                   # lookup miss -> 'Max' (gui.py:1726-1731)
+    P.VIDEO_BW = 12345.0
+    assert design.video_index(P) == len(design.VIDEO_BWs) - 1        # -> 'Other'
+    assert design.find_filter(48000, design.VIDEO_BWs) == '45 KHz' == odsp.find_filter(48000, odsp.VIDEO_BWs)
+
+
+def test_receiver_offsets_rule():
+    from pysdr_b200.receiver import receiver_offsets
+    P, Po = make_both(8, [-500, 700, 1400, 3100], ['AM', 'NFM', 'USB', 'CW'])
+    off = receiver_offsets(P)
+    assert off[0] == P.FOFFSET == 99975.5859375
+    assert off[1] == P.FOFFSET + 1.2e6
+    P.SOURCE[2] = 0
+    assert receiver_offsets(P)[2] == 1.9e6                            # FC[irx]-FC[SOURCE] (receiver.py:829-830)
+
+
+def test_ring_buffer_protocol():
+    from pysdr_b200.sig_proc import ring_buffer2, ring_buffer3
+    rb = ring_buffer2('Audio1', 4096)
+    assert rb.tag == 'Audio1' and rb.size == 4096 and rb.nsamps == 0 and not rb.ready(1)
+    rb.push(np.arange(1000, dtype=np.float32))
+    rb.push(np.arange(1000, 2000, dtype=np.float32))
+    assert rb.nsamps == 2000 and rb.ready(2000)
+    np.testing.assert_array_equal(rb.pull(500), np.arange(500))
+    np.testing.assert_array_equal(rb.pull(100, True), np.arange(1900, 2000))     # flush to the newest n
+    assert rb.nsamps == 0
+    rb.push_zeros(10)
+    assert rb.nsamps == 10
+    rb.clear()
+    assert rb.nsamps == 0 and rb.buf.qsize() == 0
+    rb.push(np.zeros(5000, np.float32))
+    assert rb.nsamps == 4096                                                    # overflow keeps `size`
+    r3 = ring_buffer3('BB', 100)
+    r3.buf.put(np.ones(30, np.complex64))
+    assert len(r3.pull(30)) == 30
+
+
+def test_synth_is_shard_consistent():
+    import torch
+    from pysdr_b200.synth import synth_iq
+    a = synth_iq(3 << 12, 8e6, [1e5, -3e5], ['AM', 'CW'], block=1 << 12)
+    b = synth_iq(1 << 12, 8e6, [1e5, -3e5], ['AM', 'CW'], n0=2 << 12, block=1 << 12)
+    assert torch.equal(a[2 << 12:], b)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from pysdr_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libpysdr_b200.so")
+    with pytest.raises(_lib.PysdrError):
+        _lib.load()
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pysdr_b200.sig_proc import Receiver, spectrum
+    from pysdr_b200._lib import PysdrError
+    P, _ = make_both(2.048, [1000], ['USB'])
+    with pytest.raises(PysdrError):
+        Receiver(P, 1e5, 0, '1')
+    with pytest.raises(PysdrError):
+        spectrum(48., 4096, 8192, 0.5)

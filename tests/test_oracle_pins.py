@@ -148,7 +148,7 @@ def test_nfm_discriminator_is_nfm_m():
     d = IQ - y[:-2]
     y1 = y[1:-1]
     fm_ref = y1.real * d.imag - y1.imag * d.real
-    dm = dsp.demodulator(48000, 5)
+    dm = dsp.demodulator(48000, 1)
     dm.filter_bank_real = [np.array([1.0], np.float32)]      # no AF filtering: isolate the discriminator
     fm = np.concatenate([dm.demod(y[:100], 'NFM', 0, 0), dm.demod(y[100:], 'NFM', 0, 0)])
     # streaming version has one sample of latency and a zero-history start-up

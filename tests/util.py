@@ -1,0 +1,50 @@
+import numpy as np
+
+REL_TOL = 1e-4          # north_star: max-abs relative error <= 1e-4
+SNR_MIN_DB = 80.0       # north_star: difference SNR >= 80 dB
+
+
+def err_metrics(got, ref):
+    got = np.asarray(got)
+    ref = np.asarray(ref)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    d = got.astype(np.complex128) - ref.astype(np.complex128)
+    peak = np.max(np.abs(ref)) if ref.size else 1.0
+    rel = float(np.max(np.abs(d)) / max(peak, 1e-300)) if ref.size else 0.0
+    pr = float(np.sum(np.abs(ref.astype(np.complex128)) ** 2))
+    pd = float(np.sum(np.abs(d) ** 2))
+    snr = 10 * np.log10(pr / pd) if pd > 0 else np.inf
+    return rel, snr
+
+
+def assert_parity(got, ref, what="", rel_tol=REL_TOL, snr_min=SNR_MIN_DB):
+    rel, snr = err_metrics(got, ref)
+    assert rel <= rel_tol and snr >= snr_min, "%s: max-abs rel err %.3e (tol %.1e), diff SNR %.1f dB (min %.0f)" % (
+        what, rel, rel_tol, snr, snr_min)
+    return rel, snr
+
+
+def cfg_args(srate_mhz, fcs_khz, modes, foffset_khz=100, af_bw_khz=None, nfilt=1001, bfo=None):
+    a = ['-fs', str(srate_mhz), '-fc'] + [str(f) for f in fcs_khz] + ['-mode'] + list(modes) + \
+        ['-foffset', str(foffset_khz), '-nfilt', str(nfilt)]
+    if af_bw_khz is not None:
+        a += ['-af_bw'] + [str(b) for b in af_bw_khz]
+    if bfo is not None:
+        a += ['-bfo'] + [str(b) for b in bfo]
+    return a
+
+
+def make_both(srate_mhz, fcs_khz, modes, foffset_khz=100, af_bw_khz=None, nfilt=1001, bfo=None, srate_hz=None):
+    """(product P, oracle P) for the same configuration."""
+    from pysdr_b200.params import RUN_TIME_PARAMS
+    from oracle import receiver_oracle as rxo
+    kw = {}
+    if srate_hz:
+        kw['srate_hz'] = srate_hz
+    P = RUN_TIME_PARAMS(cfg_args(srate_mhz, fcs_khz, modes, foffset_khz, af_bw_khz, nfilt, bfo), **kw)
+    mode = list(modes) if len(modes) > 1 else modes[0]
+    af = 0.0 if af_bw_khz is None else ([b * 1e3 for b in af_bw_khz] if len(af_bw_khz) > 1 else af_bw_khz[0] * 1e3)
+    b = 0 if bfo is None else (list(bfo) if len(bfo) > 1 else bfo[0])
+    Po = rxo.make_P(srate_hz or P.SRATE, [f * 1e3 for f in fcs_khz], mode, foffset=foffset_khz * 1e3, af_bw=af,
+                    nfilt=nfilt, bfo=b)
+    return P, Po
