@@ -120,8 +120,9 @@ int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t n_in, int 
 int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev,
                             float *d_am, float *d_am_dc, int64_t out_stride, void *stream);
 /* Move the stream position without processing (time shards): n0 must be a multiple of in_chunk.
- * LO/BFO accumulators follow; filter memories are cleared. */
-int pysdr_bank_seek(pysdr_bank *b, int64_t n0_abs);
+ * LO/BFO accumulators follow; filter memories are cleared; n0 == 0 also resets the AGC (stream restart).
+ * Asynchronous on `stream`. */
+int pysdr_bank_seek(pysdr_bank *b, int64_t n0_abs, void *stream);
 
 /* Checkpoint = carry state (filter memories, AGC, indices) as a flat byte blob. */
 int64_t pysdr_bank_state_size(const pysdr_bank *b);
@@ -131,6 +132,10 @@ int pysdr_bank_set_state(pysdr_bank *b, const void *host_blob, int64_t size, voi
 /* Which K1 variant the next process() will use: 0 generic, 1 tap-stationary fast path. */
 int pysdr_bank_k1_variant(const pysdr_bank *b);
 int pysdr_bank_force_generic(pysdr_bank *b, int on);
+/* On-stream stage timing for bench.py's roofline: out4 = {sum K1 ms, sum rest-of-front ms, sum back ms,
+ * # process calls} since the last get; get synchronises `stream`. */
+int pysdr_bank_set_timing(pysdr_bank *b, int on);
+int pysdr_bank_get_timing(pysdr_bank *b, double out4[4], void *stream);
 /* # of kernels launched by this handle so far (bench.py's gpu_launches). */
 int64_t pysdr_bank_launch_count(const pysdr_bank *b);
 
@@ -138,6 +143,8 @@ int64_t pysdr_bank_launch_count(const pysdr_bank *b);
  * float64 direct-form-II-transposed, evaluated as a block-parallel linear scan.
  *   b,a: host float64[nb],[na]; d_x,d_y: device float32[n] (n_ch rows of `stride`);
  *   d_zi: device float64[n_ch][order] in/out (order = max(na,nb)-1). */
+/* 0 = auto (block scan unless chaining would be ill-conditioned: max|Phi^B| > 1e3), 1 = scan, 2 = sequential */
+int pysdr_lfilter_set_mode(int mode);
 int pysdr_lfilter(const double *b, int nb, const double *a, int na, const float *d_x, float *d_y,
                   int64_t n, int n_ch, int64_t stride, double *d_zi, void *stream);
 

@@ -50,13 +50,16 @@ SIGNATURES = {
     "pysdr_bank_process": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),
     "pysdr_bank_process_front": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, ctypes.POINTER(c_i64), c_vp]),
     "pysdr_bank_process_back": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
-    "pysdr_bank_seek": (c_int, [c_vp, c_i64]),
+    "pysdr_bank_seek": (c_int, [c_vp, c_i64, c_vp]),
+    "pysdr_bank_set_timing": (c_int, [c_vp, c_int]),
+    "pysdr_bank_get_timing": (c_int, [c_vp, ctypes.POINTER(c_dbl), c_vp]),
     "pysdr_bank_state_size": (c_i64, [c_vp]),
     "pysdr_bank_get_state": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "pysdr_bank_set_state": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "pysdr_bank_k1_variant": (c_int, [c_vp]),
     "pysdr_bank_force_generic": (c_int, [c_vp, c_int]),
     "pysdr_bank_launch_count": (c_i64, [c_vp]),
+    "pysdr_lfilter_set_mode": (c_int, [c_int]),
     "pysdr_lfilter": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
     "pysdr_psd_create": (c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_vp, ctypes.POINTER(c_vp)]),
     "pysdr_psd_destroy": (c_int, [c_vp]),

@@ -132,7 +132,15 @@ class ReceiverBank:
         check(self.lib.pysdr_bank_reset(self.h))
 
     def seek(self, n0):
-        check(self.lib.pysdr_bank_seek(self.h, int(n0)))
+        check(self.lib.pysdr_bank_seek(self.h, int(n0), _stream_ptr()))
+
+    def set_timing(self, on=True):
+        check(self.lib.pysdr_bank_set_timing(self.h, 1 if on else 0))
+
+    def get_timing(self):
+        out = (ctypes.c_double * 4)()
+        check(self.lib.pysdr_bank_get_timing(self.h, out, _stream_ptr()))
+        return dict(k1_ms=out[0], front_rest_ms=out[1], back_ms=out[2], calls=int(out[3]))
 
     def force_generic(self, on=True):
         check(self.lib.pysdr_bank_force_generic(self.h, 1 if on else 0))

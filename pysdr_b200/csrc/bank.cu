@@ -353,6 +353,9 @@ struct pysdr_bank {
     bool pending;
     bool force_generic;
     i64 launches;
+    // optional on-stream stage timing (bench.py roofline): events e0 |K1| e1 |rest of front| e2 ... e3 |back| e4
+    bool timing;
+    std::vector<cudaEvent_t> evs;
 };
 
 static int bank_alloc(pysdr_bank *b) {
@@ -416,6 +419,7 @@ extern "C" int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out)
     b->a_stride = (b->max_out + 1) / 2 * 2;
     b->g_dirty = true;
     b->force_generic = false;
+    b->timing = false;
     b->launches = 0;
     b->pending = false;
     for (int r = 0; r < PYSDR_MAX_RX; ++r) {
@@ -646,10 +650,24 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
     a.c_out = b->d_C; a.c_stride = b->c_stride; a.hc = b->hc;
     a.bb_out = (float2 *)d_iq_bb; a.bb_stride = out_stride;
     int rc;
-    if (!b->force_generic && k1_fast_supported(c.up, c.down, b->lp, c.n_rx)) rc = k1_launch_fast(a, st);
-    else rc = k1_launch_generic(a, st);
+    auto mark = [&](void) -> int {
+        if (!b->timing) return PYSDR_OK;
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        CUDA_TRY(cudaEventRecord(e, st));
+        b->evs.push_back(e);
+        return PYSDR_OK;
+    };
+    if ((rc = mark())) return rc;
+    if (!b->force_generic && k1_fast_supported(c.up, c.down, b->lp, c.n_rx)) {
+        rc = k1_launch_fast(a, st);
+        b->launches += k1_fast_groups(b->lp, c.n_rx);
+    } else {
+        rc = k1_launch_generic(a, st);
+        b->launches++;
+    }
     if (rc) return rc;
-    b->launches++;
+    if ((rc = mark())) return rc;
 
     // input memory for the next call
     if (b->need > 0) {
@@ -690,6 +708,7 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
     LAUNCH_CHECK();
     b->launches++;
 
+    if ((rc = mark())) return rc;
     b->pend_n_out = n_out; b->pend_m0 = m0; b->pend_B0 = B0; b->pend_blocks = n_blocks;
     b->pend_peaks = d_peaks;
     b->pending = true;
@@ -713,6 +732,12 @@ extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks,
     s.gains = b->d_gains; s.gains_stride = b->max_blocks;
     s.n_blocks = n_blocks; s.n_rx = c.n_rx;
     for (int r = 0; r < PYSDR_MAX_RX; ++r) s.enabled[r] = (r < c.n_rx && b->mode[r] != PYSDR_MODE_IQ) ? 1 : 0;
+    if (b->timing) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        CUDA_TRY(cudaEventRecord(e, st));
+        b->evs.push_back(e);
+    }
     agc_scan_kernel<<<1, 32, 0, st>>>(s);
     LAUNCH_CHECK();
     b->launches++;
@@ -739,7 +764,39 @@ extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks,
             b->launches++;
         }
     }
+    if (b->timing) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        CUDA_TRY(cudaEventRecord(e, st));
+        b->evs.push_back(e);
+    }
     b->pending = false;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_set_timing(pysdr_bank *b, int on) {
+    if (!b) return PYSDR_ERR_ARG;
+    for (cudaEvent_t e : b->evs) cudaEventDestroy(e);
+    b->evs.clear();
+    b->timing = on != 0;
+    return PYSDR_OK;
+}
+
+// out4 = { sum K1 ms, sum rest-of-front ms, sum back ms, # of process calls }; clears the record.
+extern "C" int pysdr_bank_get_timing(pysdr_bank *b, double out4[4], void *stream) {
+    if (!b || !out4) return PYSDR_ERR_ARG;
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    out4[0] = out4[1] = out4[2] = out4[3] = 0.0;
+    const size_t n = b->evs.size() / 5;
+    for (size_t i = 0; i < n; ++i) {
+        float k1 = 0.f, fr = 0.f, bk = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&k1, b->evs[5 * i], b->evs[5 * i + 1]));
+        CUDA_TRY(cudaEventElapsedTime(&fr, b->evs[5 * i + 1], b->evs[5 * i + 2]));
+        CUDA_TRY(cudaEventElapsedTime(&bk, b->evs[5 * i + 3], b->evs[5 * i + 4]));
+        out4[0] += k1; out4[1] += fr; out4[2] += bk; out4[3] += 1.0;
+    }
+    for (cudaEvent_t e : b->evs) cudaEventDestroy(e);
+    b->evs.clear();
     return PYSDR_OK;
 }
 
@@ -751,15 +808,29 @@ extern "C" int pysdr_bank_process(pysdr_bank *b, const void *d_iq, int64_t n_in,
     return pysdr_bank_process_back(b, nullptr, 0, d_am, d_am_dc, out_stride, stream);
 }
 
-extern "C" int pysdr_bank_seek(pysdr_bank *b, int64_t n0_abs) {
+__global__ void agc_reset_kernel(AgcState *s, int n) {
+    const int r = threadIdx.x;
+    if (r >= n) return;
+    for (int i = 0; i < PYSDR_AGC_NB; ++i) s[r].ring[i] = 0.0;
+    s[r].k = 0; s[r].gain = 1.0; s[r].maxbuf = 0.0; s[r].err = 0.0;
+}
+
+extern "C" int pysdr_bank_seek(pysdr_bank *b, int64_t n0_abs, void *stream) {
     if (!b || n0_abs < 0 || n0_abs % b->cfg.in_chunk != 0) {
         pysdr_set_error("seek: position must be a non-negative multiple of IN_CHUNK_SIZE");
         return PYSDR_ERR_ALIGN;
     }
+    cudaStream_t st = (cudaStream_t)stream;
     b->n0 = n0_abs;
     b->pending = false;
-    CUDA_TRY(cudaMemset(b->d_hist, 0, sizeof(float2) * (size_t)(b->need + 8)));
-    CUDA_TRY(cudaMemset(b->d_C, 0, sizeof(float2) * (size_t)b->cfg.n_rx * b->c_stride));
+    CUDA_TRY(cudaMemsetAsync(b->d_hist, 0, sizeof(float2) * (size_t)(b->need + 8), st));
+    CUDA_TRY(cudaMemset2DAsync(b->d_C, sizeof(float2) * (size_t)b->c_stride, 0, sizeof(float2) * (size_t)b->hc,
+                               (size_t)b->cfg.n_rx, st));
+    if (n0_abs == 0) {                       // back at the stream origin: a fresh set of receivers
+        agc_reset_kernel<<<1, 32, 0, st>>>(b->d_agc, PYSDR_MAX_RX);
+        LAUNCH_CHECK();
+        b->launches++;
+    }
     return PYSDR_OK;
 }
 

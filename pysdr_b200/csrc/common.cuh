@@ -75,3 +75,5 @@ int k1_fast_supported(int up, int down, int lp, int n_rx);
 int k1_launch_fast(const K1Args &a, cudaStream_t st);
 // taps-per-phase padding the fast path wants (multiple of 32)
 int k1_fast_lp_pad(int lp);
+// # of kernel launches the fast path needs for n_rx receivers (receiver groups of 1/2/4)
+int k1_fast_groups(int lp, int n_rx);

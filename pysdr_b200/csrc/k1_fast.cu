@@ -260,6 +260,12 @@ int k1_fast_lp_pad(int lp) {
     const int t = pick_tpl(lp);
     return t > 0 ? 32 * t : (lp + 31) / 32 * 32;
 }
+int k1_fast_groups(int lp, int n_rx) {
+    const int tpl = pick_tpl(lp);
+    if (tpl < 0) return 1;
+    const int nrxp = pick_nrxp(tpl, n_rx);
+    return (n_rx + nrxp - 1) / nrxp;
+}
 static int pick_S(int down, int lp_pad, int M) {
     i64 s = (K1F_STAGE_ELEMS - lp_pad - 4) / down;
     s = s / M * M;

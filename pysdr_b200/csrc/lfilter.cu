@@ -17,6 +17,18 @@
 #define LF_B 512            /* samples per scan block */
 #define LF_ROWS 32          /* blocks handled per CTA (one per thread) */
 
+// One DF2T step in scipy's own operation order without FMA contraction (scipy/signal/_lfilter.c.in:
+//   y = z0 + x*b0 ; z_i = (z_{i+1} + x*b_{i+1}) - y*a_{i+1} ; z_last = x*b_last - y*a_last).
+template <int K>
+__device__ __forceinline__ double lf_step(const double *b, const double *a, double *z, double xv) {
+    const double yv = __dadd_rn(z[0], __dmul_rn(xv, b[0]));
+#pragma unroll
+    for (int i = 0; i < K - 1; ++i)
+        z[i] = __dsub_rn(__dadd_rn(z[i + 1], __dmul_rn(xv, b[i + 1])), __dmul_rn(yv, a[i + 1]));
+    z[K - 1] = __dsub_rn(__dmul_rn(xv, b[K]), __dmul_rn(yv, a[K]));
+    return yv;
+}
+
 template <int K>
 struct LfCoef {
     double b[K + 1];
@@ -50,11 +62,7 @@ lf_block_kernel(LfCoef<K> c, const float *__restrict__ x, float *__restrict__ y,
         __syncwarp();
 #pragma unroll 4
         for (int j = 0; j < 32; ++j) {
-            const double xv = (double)tile[t][j];
-            const double yv = c.b[0] * xv + z[0];
-#pragma unroll
-            for (int i = 0; i < K - 1; ++i) z[i] = c.b[i + 1] * xv + z[i + 1] - c.a[i + 1] * yv;
-            z[K - 1] = c.b[K] * xv - c.a[K] * yv;
+            const double yv = lf_step<K>(c.b, c.a, z, (double)tile[t][j]);
             if (WRITE_Y) tile[t][j] = (float)yv;
         }
         __syncwarp();
@@ -110,52 +118,58 @@ __global__ void lf_tail_kernel(LfCoef<K> c, const float *__restrict__ x, i64 n, 
 #pragma unroll
     for (int i = 0; i < K; ++i) z[i] = z_entry[((size_t)ch * nblk + b) * K + i];
     const float *xc = x + (size_t)ch * stride;
-    for (i64 idx = b * LF_B; idx < n; ++idx) {
-        const double xv = (double)xc[idx];
-        const double yv = c.b[0] * xv + z[0];
-#pragma unroll
-        for (int i = 0; i < K - 1; ++i) z[i] = c.b[i + 1] * xv + z[i + 1] - c.a[i + 1] * yv;
-        z[K - 1] = c.b[K] * xv - c.a[K] * yv;
-    }
+    for (i64 idx = b * LF_B; idx < n; ++idx) lf_step<K>(c.b, c.a, z, (double)xc[idx]);
 #pragma unroll
     for (int i = 0; i < K; ++i) zi[(size_t)ch * K + i] = z[i];
 }
 
-static void matmul(const std::vector<long double> &A, const std::vector<long double> &B, std::vector<long double> &C, int K) {
-    std::vector<long double> T((size_t)K * K, 0.0L);
-    for (int i = 0; i < K; ++i)
-        for (int k = 0; k < K; ++k) {
-            const long double aik = A[(size_t)i * K + k];
-            if (aik == 0.0L) continue;
-            for (int j = 0; j < K; ++j) T[(size_t)i * K + j] += aik * B[(size_t)k * K + j];
-        }
-    C.swap(T);
+// Sequential evaluation (one thread per channel): used when chaining blocks would be ill-conditioned.
+// Same operation order as scipy, so it tracks scipy's own float64 rounding.
+template <int K>
+__global__ void lf_seq_kernel(LfCoef<K> c, const float *__restrict__ x, float *__restrict__ y, i64 n, i64 stride,
+                              double *__restrict__ zi) {
+    const int ch = blockIdx.x;
+    double z[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) z[i] = zi[(size_t)ch * K + i];
+    const float *xc = x + (size_t)ch * stride;
+    float *yc = y + (size_t)ch * stride;
+    for (i64 i = 0; i < n; ++i) yc[i] = (float)lf_step<K>(c.b, c.a, z, (double)xc[i]);
+#pragma unroll
+    for (int i = 0; i < K; ++i) zi[(size_t)ch * K + i] = z[i];
 }
 
 template <int K>
 static int lfilter_run(const double *bn, const double *an, const float *d_x, float *d_y, i64 n, int n_ch, i64 stride,
-                       double *d_zi, cudaStream_t st) {
+                       double *d_zi, cudaStream_t st, int force_mode) {
     LfCoef<K> c;
     for (int i = 0; i <= K; ++i) { c.b[i] = bn[i]; c.a[i] = an[i]; }
     const i64 nblk = (n + LF_B - 1) / LF_B;
-    // z -> Phi z for one step with x = 0:  y = z0;  z_i' = z_{i+1} - a_{i+1} z0
-    std::vector<long double> Phi((size_t)K * K, 0.0L), P((size_t)K * K, 0.0L);
-    for (int i = 0; i < K; ++i) {
-        Phi[(size_t)i * K + 0] -= (long double)an[i + 1];
-        if (i + 1 < K) Phi[(size_t)i * K + i + 1] += 1.0L;
-    }
-    for (int i = 0; i < K; ++i) P[(size_t)i * K + i] = 1.0L;
-    {
-        std::vector<long double> Q = Phi;
-        int e = LF_B;
-        while (e) {
-            if (e & 1) matmul(P, Q, P, K);
-            e >>= 1;
-            if (e) matmul(Q, Q, Q, K);
+    // Phi^B column j = state reached after B zero-input steps from the unit state e_j (the recursion itself is
+    // the numerically stable way to form it; powering the companion matrix is not).
+    std::vector<double> phiB((size_t)K * K);
+    double pmax = 0.0;
+    for (int j = 0; j < K; ++j) {
+        long double z[K];
+        for (int i = 0; i < K; ++i) z[i] = (i == j) ? 1.0L : 0.0L;
+        for (int stp = 0; stp < LF_B; ++stp) {
+            const long double yv = z[0];
+            for (int i = 0; i < K - 1; ++i) z[i] = z[i + 1] - (long double)an[i + 1] * yv;
+            z[K - 1] = -(long double)an[K] * yv;
+        }
+        for (int i = 0; i < K; ++i) {
+            phiB[(size_t)i * K + j] = (double)z[i];
+            const double m = fabs((double)z[i]);
+            if (!(m <= pmax)) pmax = m;             // also catches NaN
         }
     }
-    std::vector<double> phiB((size_t)K * K);
-    for (size_t i = 0; i < phiB.size(); ++i) phiB[i] = (double)P[i];
+    // Conditioning gate: chaining multiplies state round-off by |Phi^B|.  Narrow-band high-order direct forms
+    // (e.g. reference sigs/iir.py ellip-7 @200/8000 Hz, cheby2-15 band) exceed it and run sequentially.
+    if (force_mode == 2 || (force_mode == 0 && !(pmax <= 1.0e3))) {
+        lf_seq_kernel<K><<<n_ch, 1, 0, st>>>(c, d_x, d_y, n, stride, d_zi);
+        LAUNCH_CHECK();
+        return PYSDR_OK;
+    }
 
     double *d_ws = nullptr;      // [phiB K*K][s n_ch*nblk*K][z_entry n_ch*nblk*K]
     const size_t per = (size_t)n_ch * nblk * K;
@@ -177,6 +191,9 @@ static int lfilter_run(const double *bn, const double *an, const float *d_x, flo
     CUDA_TRY(cudaFreeAsync(d_ws, st));
     return PYSDR_OK;
 }
+
+static int g_lf_mode = 0;       // 0 auto, 1 force block scan, 2 force sequential
+extern "C" int pysdr_lfilter_set_mode(int mode) { g_lf_mode = mode; return PYSDR_OK; }
 
 extern "C" int pysdr_lfilter(const double *b, int nb, const double *a, int na, const float *d_x, float *d_y,
                              int64_t n, int n_ch, int64_t stride, double *d_zi, void *stream) {
@@ -205,12 +222,12 @@ extern "C" int pysdr_lfilter(const double *b, int nb, const double *a, int na, c
                                cudaMemcpyDeviceToDevice, st));
     int rc;
     switch (K) {
-        case 1: rc = lfilter_run<1>(bn, an, d_x, d_y, n, n_ch, stride, d_zp, st); break;
-        case 2: rc = lfilter_run<2>(bn, an, d_x, d_y, n, n_ch, stride, d_zp, st); break;
-        case 4: rc = lfilter_run<4>(bn, an, d_x, d_y, n, n_ch, stride, d_zp, st); break;
-        case 8: rc = lfilter_run<8>(bn, an, d_x, d_y, n, n_ch, stride, d_zp, st); break;
-        case 16: rc = lfilter_run<16>(bn, an, d_x, d_y, n, n_ch, stride, d_zp, st); break;
-        default: rc = lfilter_run<32>(bn, an, d_x, d_y, n, n_ch, stride, d_zp, st); break;
+        case 1: rc = lfilter_run<1>(bn, an, d_x, d_y, n, n_ch, stride, d_zp, st, g_lf_mode); break;
+        case 2: rc = lfilter_run<2>(bn, an, d_x, d_y, n, n_ch, stride, d_zp, st, g_lf_mode); break;
+        case 4: rc = lfilter_run<4>(bn, an, d_x, d_y, n, n_ch, stride, d_zp, st, g_lf_mode); break;
+        case 8: rc = lfilter_run<8>(bn, an, d_x, d_y, n, n_ch, stride, d_zp, st, g_lf_mode); break;
+        case 16: rc = lfilter_run<16>(bn, an, d_x, d_y, n, n_ch, stride, d_zp, st, g_lf_mode); break;
+        default: rc = lfilter_run<32>(bn, an, d_x, d_y, n, n_ch, stride, d_zp, st, g_lf_mode); break;
     }
     if (rc) return rc;
     CUDA_TRY(cudaMemcpy2DAsync(d_zi, sizeof(double) * order, d_zp, sizeof(double) * K, sizeof(double) * order, n_ch,
