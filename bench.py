@@ -230,37 +230,16 @@ def run_own(args):
     n_chunks = int(args.chunks)
     n = n_chunks * C                                   # samples per GPU per step
     offs = receiver_offsets(P)
-    warm = 1 if rank > 0 else 0                        # warm-up chunk before the shard (AF memories: 1002 outputs < 1 chunk)
-    need = (P.FILT_LEN + P.UP - 1) // P.UP - 1
-    start = rank * n                                   # absolute sample index of this rank's shard
-    lead = warm * C + (need + 1 if rank > 0 else 0)
-    lead += lead & 1                                   # keep the shard 16-byte aligned
-    xbuf = synth_iq(lead + n, P.SRATE, offs, MODES, seed=1234, device=dev, n0=start - lead)
-    x_main = xbuf[lead:]
-    x_warm = xbuf[lead - C:lead] if warm else None
+    from pysdr_b200.dist import ShardedCapture
     bank = ReceiverBank(P, offs, max_in=n, device=dev)
-    n_blocks = n_chunks
-    peaks = torch.zeros((4, n_blocks), dtype=torch.float32, device=dev)
-    warm_pk = torch.zeros((4, 1), dtype=torch.float32, device=dev)
-    all_pk = torch.zeros((world, 4, n_blocks), dtype=torch.float32, device=dev) if world > 1 else None
+    shard = ShardedCapture(bank, P, rank, world, n_chunks)          # plan: warm-up chunk + K1 halo for rank > 0
+    plan = shard.plan
+    warm = plan['warm_chunks']
+    xbuf = synth_iq(plan['lead'] + n, P.SRATE, offs, MODES, seed=1234, device=dev, n0=plan['first_sample'])
+    x_main = xbuf[plan['lead']:]
 
     def step():
-        if world == 1:
-            bank.seek(0)
-            bank.process_front(x_main, peaks)
-            bank.process_back(want_dc=False)
-            return
-        if warm:
-            bank.seek(start - C)
-            bank.process_front(x_warm, warm_pk, halo_in_place=True)
-            bank.process_back(want_dc=False)
-            bank.process_front(x_main, peaks, halo_in_place=True)
-        else:
-            bank.seek(0)
-            bank.process_front(x_main, peaks)
-        dist.all_gather_into_tensor(all_pk, peaks)                        # the one collective: AGC carry
-        prev = all_pk[:rank].permute(1, 0, 2).reshape(4, rank * n_blocks).contiguous() if rank > 0 else None
-        bank.process_back(prev_peaks=prev, want_dc=False)
+        shard.step(xbuf)                                            # front -> all-gather of AGC peaks -> back
 
     def barrier():
         if world > 1:

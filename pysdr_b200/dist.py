@@ -1,0 +1,77 @@
+"""Time-sharding of one long capture across ranks (one process per GPU, torch.distributed).
+
+The path shards naturally along time: K1 is stateless given the absolute sample index (LO phase
+= exact u64 function of n) and a halo of ceil(FILT_LEN/UP)-1 preceding raw samples; the audio-rate FIR memories
+(FILT_LEN+1 baseband samples) are rebuilt by processing the chunk(s) just before the shard; the only state
+that depends on the whole past is the block AGC — its inputs are the per-block peaks, so ONE all-gather of
+n_rx x n_blocks floats per rank lets every rank replay the (tiny, serial) AGC recursion over all earlier blocks.
+No IQ samples are ever exchanged.
+
+Host-side planning and the collective live here and are back-end agnostic (NCCL on GPUs, gloo in the CPU tests).
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+
+def shard_plan(P, rank, world, chunks_per_rank):
+    """Where rank's shard starts and what it must read before it.  All quantities in input samples."""
+    C = int(P.IN_CHUNK_SIZE)
+    need = (int(P.FILT_LEN) + int(P.UP) - 1) // int(P.UP) - 1           # K1 halo (raw samples)
+    hist_out = int(P.FILT_LEN) + 1                                      # AF memory (baseband samples)
+    start = rank * chunks_per_rank * C
+    if rank == 0:
+        warm_chunks, halo = 0, 0
+    else:
+        warm_in = math.ceil(hist_out * int(P.DOWN) / int(P.UP))         # inputs that produce >= hist_out outputs
+        warm_chunks = max(1, math.ceil(warm_in / C))
+        halo = need
+    lead = warm_chunks * C + halo                                       # samples to read before `start`
+    return dict(start=start, n=chunks_per_rank * C, warm_chunks=warm_chunks, halo=halo, lead=lead,
+                first_sample=start - lead, n_blocks=chunks_per_rank)
+
+
+def exchange_agc_peaks(peaks, rank, world, group=None):
+    """peaks: [n_rx, n_blocks] of this rank -> [n_rx, rank*n_blocks] peaks of all EARLIER blocks (None for rank 0).
+    The one collective of the path."""
+    if world == 1:
+        return None
+    n_rx, n_blocks = peaks.shape
+    if peaks.is_cuda:
+        allp = torch.empty((world, n_rx, n_blocks), dtype=peaks.dtype, device=peaks.device)
+        dist.all_gather_into_tensor(allp, peaks.contiguous(), group=group)
+    else:
+        parts = [torch.empty_like(peaks) for _ in range(world)]
+        dist.all_gather(parts, peaks.contiguous(), group=group)
+        allp = torch.stack(parts)
+    if rank == 0:
+        return None
+    return allp[:rank].permute(1, 0, 2).reshape(n_rx, rank * n_blocks).contiguous()
+
+
+class ShardedCapture:
+    """Per-rank driver of one time shard on the GPU bank (used by bench.py for N>1 and by receiver-level tools)."""
+
+    def __init__(self, bank, P, rank, world, chunks_per_rank):
+        self.bank, self.P, self.rank, self.world = bank, P, rank, world
+        self.plan = shard_plan(P, rank, world, chunks_per_rank)
+        dev = bank.device
+        self.peaks = torch.zeros((bank.n_rx, self.plan['n_blocks']), dtype=torch.float32, device=dev)
+        self.warm_pk = torch.zeros((bank.n_rx, max(1, self.plan['warm_chunks'])), dtype=torch.float32, device=dev)
+
+    def step(self, xbuf, want_dc=False):
+        """xbuf: device tensor holding samples [first_sample, start+n) of the capture."""
+        p, b = self.plan, self.bank
+        C = int(self.P.IN_CHUNK_SIZE)
+        main = xbuf[p['lead']:]
+        if p['warm_chunks']:
+            b.seek(p['start'] - p['warm_chunks'] * C)
+            b.process_front(xbuf[p['halo']:p['lead']], self.warm_pk, halo_in_place=True)
+            b.process_back(want_dc=False)                                # outputs discarded: memories are now exact
+            b.process_front(main, self.peaks, halo_in_place=True)
+        else:
+            b.seek(0)
+            b.process_front(main, self.peaks)
+        prev = exchange_agc_peaks(self.peaks, self.rank, self.world)
+        return b.process_back(prev_peaks=prev, want_dc=want_dc)

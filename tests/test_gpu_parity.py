@@ -396,7 +396,8 @@ def test_spectrum_parity(chunk, nfft, overlap):
     est, ref = sp.psd_est(x, False), so.psd_est(x, False)
     assert_parity(est, ref, "psd_est linear")
     est_db, ref_db = sp.psd_est(x, True), so.psd_est(x, True)
-    assert np.max(np.abs(est_db - ref_db)) < 1e-3
+    top = ref_db > ref_db.max() - 60                               # dB is a relative measure: gate it within 60 dB of the peak
+    assert np.max(np.abs(est_db - ref_db)[top]) < 1e-3
     wf, wref = sp.waterfall(x, 4, False), so.waterfall(x, 4, False)
     assert wf.shape == wref.shape
     assert_parity(wf, wref, "waterfall lines")
@@ -404,7 +405,9 @@ def test_spectrum_parity(chunk, nfft, overlap):
     ns = sp.new_samps
     for k in range(5):
         g, r = sp.periodogram(x[k * ns:(k + 1) * ns], True), so.periodogram(x[k * ns:(k + 1) * ns], True)
-    assert np.max(np.abs(g - r)) < 2e-3
+    top = r > r.max() - 60
+    assert np.max(np.abs(g - r)[top]) < 2e-3
+    assert_parity(10 ** (g / 10), 10 ** (r / 10), "streaming periodogram (linear)")
     assert len(sp.periodogram(np.zeros(0), True)) == 0
 
 

@@ -48,3 +48,25 @@ def make_both(srate_mhz, fcs_khz, modes, foffset_khz=100, af_bw_khz=None, nfilt=
     Po = rxo.make_P(srate_hz or P.SRATE, [f * 1e3 for f in fcs_khz], mode, foffset=foffset_khz * 1e3, af_bw=af,
                     nfilt=nfilt, bfo=b)
     return P, Po
+
+
+def lcg_iq(n, seed, scale=0.05):
+    """Portable deterministic complex64 noise (integer LCG, no library RNG) for golden fixtures."""
+    k = np.arange(n, dtype=np.uint64)
+    with np.errstate(over='ignore'):
+        h = (k + np.uint64(seed)) * np.uint64(6364136223846793005) + np.uint64(1442695040888963407)
+        h ^= h >> np.uint64(29)
+        h = h * np.uint64(0xBF58476D1CE4E5B9)
+        h ^= h >> np.uint64(32)
+    re = ((h & np.uint64(0xFFFF)).astype(np.float64) / 32768.0 - 1.0)
+    im = (((h >> np.uint64(16)) & np.uint64(0xFFFF)).astype(np.float64) / 32768.0 - 1.0)
+    return ((re + 1j * im) * scale).astype(np.complex64)
+
+
+def golden_input(n, srate, offsets_hz, seed):
+    """LCG noise + one AM-ish carrier per receiver offset (float64 phase, cast once)."""
+    x = lcg_iq(n, seed).astype(np.complex128)
+    t = np.arange(n, dtype=np.float64) / srate
+    for i, f in enumerate(offsets_hz):
+        x += 0.1 * (1 + 0.5 * np.sin(2 * np.pi * (700.0 + 300 * i) * t)) * np.exp(2j * np.pi * (f + 900.0) * t)
+    return x.astype(np.complex64)
