@@ -132,6 +132,8 @@ int pysdr_bank_set_state(pysdr_bank *b, const void *host_blob, int64_t size, voi
 /* Which K1 variant the next process() will use: 0 generic, 1 tap-stationary fast path. */
 int pysdr_bank_k1_variant(const pysdr_bank *b);
 int pysdr_bank_force_generic(pysdr_bank *b, int on);
+/* AF filter variant: default = overlap-save FFT convolution in shared memory; on != 0 forces the direct-form FIR. */
+int pysdr_bank_force_direct_fir(pysdr_bank *b, int on);
 /* On-stream stage timing for bench.py's roofline: out4 = {sum K1 ms, sum rest-of-front ms, sum back ms,
  * # process calls} since the last get; get synchronises `stream`. */
 int pysdr_bank_set_timing(pysdr_bank *b, int on);

@@ -142,6 +142,9 @@ class ReceiverBank:
         check(self.lib.pysdr_bank_get_timing(self.h, out, _stream_ptr()))
         return dict(k1_ms=out[0], front_rest_ms=out[1], back_ms=out[2], calls=int(out[3]))
 
+    def force_direct_fir(self, on=True):
+        check(self.lib.pysdr_bank_force_direct_fir(self.h, 1 if on else 0))
+
     def force_generic(self, on=True):
         check(self.lib.pysdr_bank_force_generic(self.h, 1 if on else 0))
 

@@ -189,10 +189,12 @@ __device__ __forceinline__ void block_range(i64 b, i64 B0, i64 in_chunk, int up,
     hi = e > n_out ? n_out : e;
 }
 
-// K2c: peak of |a| per block.  grid (n_blocks), one launch per receiver.
+// K2c: peak of |a| per block.  grid (n_blocks, n_rx).
 __global__ void __launch_bounds__(256)
-block_peak_kernel(const float *__restrict__ a, float *__restrict__ peaks, i64 B0, i64 in_chunk, int up, int down,
-                  i64 m0, i64 n_out) {
+block_peak_kernel(const float *__restrict__ a, i64 a_row, float *__restrict__ peaks, i64 peaks_row, i64 B0, i64 in_chunk,
+                  int up, int down, i64 m0, i64 n_out) {
+    a += (size_t)blockIdx.y * a_row;
+    peaks += (size_t)blockIdx.y * peaks_row;
     i64 lo, hi;
     block_range(blockIdx.x, B0, in_chunk, up, down, m0, n_out, lo, hi);
     float mx = 0.f;
@@ -238,21 +240,126 @@ struct AgcScanArgs {
     int enabled[PYSDR_MAX_RX];
 };
 
-__global__ void agc_scan_kernel(AgcScanArgs p) {
-    const int rx = threadIdx.x;
-    if (rx >= p.n_rx) return;
-    AgcState s = p.state[rx];
-    if (p.prev_peaks) {                 // time shard: replay all earlier blocks from the reset state
-        for (int i = 0; i < PYSDR_AGC_NB; ++i) s.ring[i] = 0.0;
-        s.k = 0; s.gain = 1.0; s.maxbuf = 0.0; s.err = 0.0;
-        for (i64 b = 0; b < p.n_prev; ++b) agc_update(s, (double)p.prev_peaks[(size_t)rx * p.n_prev + b]);
+// The per-block update is  gain <- f_b(gain) = min(w_b, beta*w_b + (1-beta)*gain)  (attack when w_b < gain,
+// agc.m loop filter otherwise), w_b = min(ref / max(maxbuf_b, 1e-9), 1e4), maxbuf_b = max of the last 8 peaks.
+// maxbuf/w are data-parallel.  f_b(g) = min(A, C + D*g) is closed under composition
+//     (f2 o f1)(g) = min( min(A2, C2 + D2*A1),  (C2 + D2*C1) + (D2*D1)*g )
+// so the replay of EARLIER shards' blocks (time-sharded runs) is an ordered parallel reduction; this call's own
+// blocks run the recurrence sequentially in one thread (1 DFMA + 1 DMNMX per block) so that chunk-at-a-time and
+// whole-capture processing produce bit-identical gains.  One CTA per receiver.
+#define AGC_TILE 2048
+#define AGC_THREADS 256
+
+struct AgcFn { double A, C, D; };
+__device__ __forceinline__ AgcFn agc_compose(const AgcFn &f1, const AgcFn &f2) {       // f2 after f1
+    AgcFn r;
+    r.A = fmin(f2.A, fma(f2.D, f1.A, f2.C));
+    r.C = fma(f2.D, f1.C, f2.C);
+    r.D = f2.D * f1.D;
+    return r;
+}
+
+__global__ void __launch_bounds__(AGC_THREADS) agc_scan_kernel(AgcScanArgs p) {
+    const int rx = blockIdx.x;
+    const int tid = threadIdx.x;
+    float *gains = p.gains + (size_t)rx * p.gains_stride;
+    if (!p.enabled[rx]) {
+        for (i64 b = tid; b < p.n_blocks; b += AGC_THREADS) gains[b] = 1.f;
+        return;
     }
-    for (i64 b = 0; b < p.n_blocks; ++b) {
-        float g = 1.f;
-        if (p.enabled[rx]) g = agc_update(s, (double)p.peaks[(size_t)rx * p.peaks_stride + b]);
-        p.gains[(size_t)rx * p.gains_stride + b] = g;
+    __shared__ double s_w[AGC_TILE];
+    __shared__ float s_pk[AGC_TILE + 8];
+    __shared__ AgcFn s_fn[AGC_THREADS / 32];
+    __shared__ AgcState st;
+    __shared__ double s_g, s_err, s_mb;
+    const float *prev = p.prev_peaks ? p.prev_peaks + (size_t)rx * p.n_prev : nullptr;
+    const float *own = p.peaks + (size_t)rx * p.peaks_stride;
+    const i64 n_prev = prev ? p.n_prev : 0;
+    if (tid == 0) {
+        st = p.state[rx];
+        if (prev) {                                  // time shard: replay from the reset state
+            for (int i = 0; i < PYSDR_AGC_NB; ++i) st.ring[i] = 0.0;
+            st.k = 0; st.gain = 1.0; st.maxbuf = 0.0; st.err = 0.0;
+        }
+        s_g = st.gain; s_err = st.err; s_mb = st.maxbuf;
     }
-    p.state[rx] = s;
+    __syncthreads();
+    const double ref = st.ref, beta = st.beta, D = 1.0 - st.beta;
+    const i64 k0 = st.k;
+    if (tid < 7) s_pk[6 - tid] = (float)st.ring[(int)(((k0 - 1 - tid) % 8 + 8) % 8)];   // 7 peaks before element 0
+    const i64 n_total = n_prev + p.n_blocks;
+    for (i64 t0 = 0; t0 < n_total;) {
+        // a tile never straddles the prev/own boundary
+        const bool in_prev = t0 < n_prev;
+        const i64 lim = in_prev ? n_prev : n_total;
+        const int len = (int)((lim - t0 < AGC_TILE) ? (lim - t0) : AGC_TILE);
+        __syncthreads();
+        for (int i = tid; i < len; i += AGC_THREADS) {
+            const i64 e = t0 + i;
+            s_pk[7 + i] = e < n_prev ? prev[e] : own[e - n_prev];
+        }
+        __syncthreads();
+        for (int i = tid; i < len; i += AGC_THREADS) {
+            float mb = s_pk[i];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) mb = fmaxf(mb, s_pk[i + j]);
+            s_w[i] = fmin(ref / fmax((double)mb, 1.0e-9), 1.0e4);
+            if (i == len - 1) s_mb = (double)mb;
+        }
+        __syncthreads();
+        if (in_prev) {
+            // ordered parallel composition of this tile's block functions
+            AgcFn f; f.A = 1.0e300; f.C = 0.0; f.D = 1.0;                  // identity
+            const int per = (len + AGC_THREADS - 1) / AGC_THREADS;
+            for (int j = 0; j < per; ++j) {
+                const int i = tid * per + j;
+                if (i < len) { AgcFn g; g.A = s_w[i]; g.C = beta * s_w[i]; g.D = D; f = agc_compose(f, g); }
+            }
+            for (int o = 1; o < 32; o <<= 1) {                             // inclusive ordered scan inside the warp
+                AgcFn lo;
+                lo.A = __shfl_up_sync(0xffffffffu, f.A, o);
+                lo.C = __shfl_up_sync(0xffffffffu, f.C, o);
+                lo.D = __shfl_up_sync(0xffffffffu, f.D, o);
+                if ((tid & 31) >= o) f = agc_compose(lo, f);
+            }
+            if ((tid & 31) == 31) s_fn[tid >> 5] = f;
+            __syncthreads();
+            if (tid == 0) {
+                AgcFn t = s_fn[0];
+                for (int w = 1; w < AGC_THREADS / 32; ++w) t = agc_compose(t, s_fn[w]);
+                // gain before the tile's last block (for err) is not tracked in the replay; err is refreshed below
+                s_g = fmin(t.A, fma(t.D, s_g, t.C));
+            }
+        } else if (tid == 0) {
+            double g = s_g, err = s_err;
+            const i64 b0 = t0 - n_prev;
+#pragma unroll 4
+            for (int i = 0; i < len; ++i) {
+                const double w = s_w[i];
+                err = w - g;
+                g = fmin(w, fma(D, g, beta * w));
+                gains[b0 + i] = (float)g;
+            }
+            s_g = g; s_err = err;
+        }
+        __syncthreads();
+        float ctxv = 0.f;                                                  // context for the next tile:
+        if (tid < 7) ctxv = s_pk[len + tid];                               // the last 7 entries of [ctx | tile]
+        __syncthreads();
+        if (tid < 7) s_pk[tid] = ctxv;
+        t0 += len;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        st.gain = s_g; st.err = s_err; st.maxbuf = s_mb;
+        for (int j = 0; j < 8; ++j) {                                      // ring <- the last 8 peaks seen
+            const i64 e = n_total - 1 - j;
+            if (e < 0) break;
+            st.ring[(int)((k0 + e) % 8)] = (double)(e < n_prev ? prev[e] : own[e - n_prev]);
+        }
+        st.k = k0 + n_total;
+        p.state[rx] = st;
+    }
 }
 
 // K2e: am = a*gain ; am_dc = am - mean_block(am) for AM/USB.  grid (n_blocks), launch per receiver.
@@ -344,6 +451,9 @@ struct pysdr_bank {
     u64 bfo_inc[PYSDR_MAX_RX];
     bool demod_set[PYSDR_MAX_RX];
     // device
+    bool h_dirty[PYSDR_MAX_RX];             // AF taps changed: their position-order FFT must be refreshed
+    bool force_direct_fir;                  // testing: use the direct-form AF FIR instead of the FFT path
+    float2 *d_H;                            // [n_rx][Nfft] FFT of AF taps (position order, 1/N folded in)
     float2 *d_hist, *d_g, *d_C, *d_af;
     float *d_R, *d_a, *d_peaks, *d_gains;
     AgcState *d_agc;
@@ -364,6 +474,9 @@ static int bank_alloc(pysdr_bank *b) {
     CUDA_TRY(cudaMalloc(&b->d_g, sizeof(float2) * (size_t)c.n_rx * c.up * b->lp_pad));
     CUDA_TRY(cudaMalloc(&b->d_C, sizeof(float2) * (size_t)c.n_rx * b->c_stride));
     CUDA_TRY(cudaMalloc(&b->d_af, sizeof(float2) * (size_t)c.n_rx * c.af_len));
+    b->d_H = nullptr;
+    if (fftconv_supported(c.af_len))
+        CUDA_TRY(cudaMalloc(&b->d_H, sizeof(float2) * (size_t)c.n_rx * fftconv_n_for(c.af_len)));
     CUDA_TRY(cudaMalloc(&b->d_R, sizeof(float) * (size_t)c.n_rx * b->r_stride));
     CUDA_TRY(cudaMalloc(&b->d_a, sizeof(float2) * (size_t)c.n_rx * b->a_stride));
     CUDA_TRY(cudaMalloc(&b->d_peaks, sizeof(float) * (size_t)c.n_rx * b->max_blocks));
@@ -419,12 +532,14 @@ extern "C" int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out)
     b->a_stride = (b->max_out + 1) / 2 * 2;
     b->g_dirty = true;
     b->force_generic = false;
+    b->force_direct_fir = false;
     b->timing = false;
     b->launches = 0;
     b->pending = false;
     for (int r = 0; r < PYSDR_MAX_RX; ++r) {
         b->inc[r] = 0; b->acc0[r] = 0; b->mode[r] = PYSDR_MODE_IQ; b->af_cplx[r] = 0; b->bfo_inc[r] = 0;
         b->demod_set[r] = false;
+        b->h_dirty[r] = true;
     }
     int rc = bank_alloc(b);
     if (rc) { delete b; return rc; }
@@ -443,6 +558,7 @@ extern "C" int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out)
 
 extern "C" int pysdr_bank_destroy(pysdr_bank *b) {
     if (!b) return PYSDR_OK;
+    cudaFree(b->d_H);
     cudaFree(b->d_hist); cudaFree(b->d_g); cudaFree(b->d_C); cudaFree(b->d_af); cudaFree(b->d_R);
     cudaFree(b->d_a); cudaFree(b->d_peaks); cudaFree(b->d_gains); cudaFree(b->d_agc);
     delete b;
@@ -497,6 +613,7 @@ extern "C" int pysdr_bank_set_demod(pysdr_bank *b, int rx, int mode, const float
     b->af_cplx[rx] = is_complex;
     b->bfo_inc[rx] = bfo_inc;
     b->demod_set[rx] = true;
+    b->h_dirty[rx] = true;
     return PYSDR_OK;
 }
 
@@ -536,6 +653,11 @@ extern "C" int64_t pysdr_bank_position(const pysdr_bank *b) { return b ? b->n0 :
 extern "C" int64_t pysdr_bank_n_blocks(const pysdr_bank *b, int64_t n_in) {
     if (!b) return -1;
     return (n_in + b->cfg.in_chunk - 1) / b->cfg.in_chunk;
+}
+extern "C" int pysdr_bank_force_direct_fir(pysdr_bank *b, int on) {
+    if (!b) return PYSDR_ERR_ARG;
+    b->force_direct_fir = on != 0;
+    return PYSDR_OK;
 }
 extern "C" int pysdr_bank_force_generic(pysdr_bank *b, int on) {
     if (!b) return PYSDR_ERR_ARG;
@@ -677,12 +799,33 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
     }
 
     const int L = c.af_len;
+    const bool use_fft = b->d_H && !b->force_direct_fir;
+    if (use_fft) {
+        // K2 fast path: fused detection + overlap-save AF filter for all receivers in one launch
+        const int nfft = fftconv_n_for(L);
+        for (int r = 0; r < c.n_rx; ++r) {
+            if (!b->h_dirty[r]) continue;
+            rc = fftconv_prepare_taps(b->d_af + (size_t)r * L, L, b->d_H + (size_t)r * nfft, st);
+            if (rc) return rc;
+            b->launches++;
+            b->h_dirty[r] = false;
+        }
+        FftConvArgs f;
+        f.C = b->d_C; f.c_stride = b->c_stride; f.H = b->d_H; f.L = L; f.n_out = n_out; f.m0 = m0;
+        f.out = (float *)b->d_a; f.a_stride = b->a_stride;
+        for (int r = 0; r < PYSDR_MAX_RX; ++r) { f.mode[r] = b->mode[r]; f.bfo_inc[r] = b->bfo_inc[r]; }
+        rc = fftconv_launch(f, c.n_rx, st);
+        if (rc) return rc;
+        b->launches++;
+    }
     for (int r = 0; r < c.n_rx; ++r) {
         float2 *C = b->d_C + (size_t)r * b->c_stride;
         float *R = b->d_R + (size_t)r * b->r_stride;
         float *aout = (float *)(b->d_a + (size_t)r * b->a_stride);
         const int mode = b->mode[r];
-        if (mode == PYSDR_MODE_AM || mode == PYSDR_MODE_NFM) {
+        if (use_fft) {
+            rc = PYSDR_OK;
+        } else if (mode == PYSDR_MODE_AM || mode == PYSDR_MODE_NFM) {
             const i64 nr = (L - 1) + n_out;
             i64 blocks = (nr + 255) / 256;
             if (blocks > 148 * 8) blocks = 148 * 8;
@@ -696,12 +839,14 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
             rc = launch_fir<2>(b, r, C + 2, n_out, aout, mode == PYSDR_MODE_CW, m0, st);
         }
         if (rc) return rc;
-        if (mode != PYSDR_MODE_IQ) {
-            block_peak_kernel<<<(unsigned)n_blocks, 256, 0, st>>>(aout, d_peaks + (size_t)r * n_blocks, B0, c.in_chunk,
-                                                                 c.up, c.down, m0, n_out);
-            LAUNCH_CHECK();
-            b->launches++;
-        }
+        (void)aout;
+    }
+    {
+        dim3 grid((unsigned)n_blocks, (unsigned)c.n_rx);       // IQ-mode rows produce unused values
+        block_peak_kernel<<<grid, 256, 0, st>>>((const float *)b->d_a, 2 * b->a_stride, d_peaks, n_blocks, B0, c.in_chunk,
+                                                c.up, c.down, m0, n_out);
+        LAUNCH_CHECK();
+        b->launches++;
     }
     // roll the complex memory: C[0..hc) <- C[n_out .. n_out+hc)
     roll_kernel<<<c.n_rx, 1024, 0, st>>>(b->d_C, b->c_stride, n_out, b->hc);
@@ -738,7 +883,7 @@ extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks,
         CUDA_TRY(cudaEventRecord(e, st));
         b->evs.push_back(e);
     }
-    agc_scan_kernel<<<1, 32, 0, st>>>(s);
+    agc_scan_kernel<<<c.n_rx, AGC_THREADS, 0, st>>>(s);
     LAUNCH_CHECK();
     b->launches++;
     for (int r = 0; r < c.n_rx; ++r) {

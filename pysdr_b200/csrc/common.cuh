@@ -77,3 +77,20 @@ int k1_launch_fast(const K1Args &a, cudaStream_t st);
 int k1_fast_lp_pad(int lp);
 // # of kernel launches the fast path needs for n_rx receivers (receiver groups of 1/2/4)
 int k1_fast_groups(int lp, int n_rx);
+
+// ---- K2 fast path (k2_fftconv.cu) ---------------------------------------------------------------------
+struct FftConvArgs {
+    const float2 *C;          // complex memory + new samples, rows of c_stride: C[rx][0..hc+n_out)
+    i64 c_stride;
+    const float2 *H;          // per receiver: FFT of the AF taps in position order, scaled 1/N
+    int L;                    // AF FIR length
+    i64 n_out, m0;
+    float *out;               // pre-AGC audio rows of 2*a_stride floats
+    i64 a_stride;
+    int mode[PYSDR_MAX_RX];
+    u64 bfo_inc[PYSDR_MAX_RX];
+};
+int fftconv_supported(int L);
+int fftconv_n_for(int L);
+int fftconv_prepare_taps(const float2 *d_taps, int L, float2 *d_H, cudaStream_t st);
+int fftconv_launch(const FftConvArgs &a, int n_rx, cudaStream_t st);

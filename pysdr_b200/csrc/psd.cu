@@ -4,151 +4,135 @@
 // 618-626,689-695).
 //
 // One CTA owns one (line, split) work item: it loops over its frames, loading chunk_size samples times
-// the window into shared memory (zero padded to nfft), runs an in-place shared-memory FFT and
-// accumulates |X|^2 in registers.  cuFFT is not used anywhere (tests cross-check against numpy).
+// the window into shared memory (zero padded to nfft), runs the shared-memory radix-16 FFT (fft_smem.cuh)
+// and accumulates |X|^2 in registers in POSITION order; only the final line is permuted to bins and
+// fftshifted.  cuFFT is not used anywhere (tests cross-check against numpy).
 #include "common.cuh"
-
-#define PSD_THREADS 512
+#include "fft_smem.cuh"
 
 struct pysdr_psd {
-    int chunk, nfft, hop, log2n;
+    int chunk, nfft, hop;
     double wsum2;
     float *d_win;
-    float2 *d_tw;          // nfft/2 twiddles e^{-j 2 pi k / nfft}
-    float *d_part;         // partial sums workspace
+    float *d_part;         // partial sums workspace [lines][split][nfft] (position order)
     size_t part_cap;
     i64 launches;
 };
 
-__device__ __forceinline__ unsigned bitrev(unsigned v, int bits) { return __brev(v) >> (32 - bits); }
-
-// in-place radix-2 decimation-in-frequency FFT; output in bit-reversed order
-__device__ void fft_smem_dif(float2 *s, const float2 *__restrict__ tw, int n, int log2n, int tid, int nthreads) {
-    for (int stage = 0; stage < log2n; ++stage) {
-        const int half = n >> (stage + 1);
-        const int tw_stride = 1 << stage;
-        for (int b = tid; b < (n >> 1); b += nthreads) {
-            const int grp = b / half;
-            const int pos = b - grp * half;
-            const int i0 = grp * 2 * half + pos;
-            const int i1 = i0 + half;
-            const float2 u = s[i0], v = s[i1];
-            const float2 w = __ldg(tw + pos * tw_stride);
-            const float dr = u.x - v.x, di = u.y - v.y;
-            s[i0] = make_float2(u.x + v.x, u.y + v.y);
-            s[i1] = make_float2(dr * w.x - di * w.y, dr * w.y + di * w.x);
-        }
-        __syncthreads();
-    }
-}
-
 // grid (n_split, n_lines). Frames of line l: [l*navg, (l+1)*navg); split s takes frames s, s+n_split, ...
-template <bool CPLX>
-__global__ void __launch_bounds__(PSD_THREADS)
-psd_frames_kernel(const void *__restrict__ xv, i64 n, const float *__restrict__ win, const float2 *__restrict__ tw, int chunk,
-                  int nfft, int log2n, int hop, int navg, int n_split, float *__restrict__ part /* [lines][split][nfft] */) {
+template <int N, bool CPLX>
+__global__ void __launch_bounds__(FftPlan<N>::THREADS)
+psd_frames_kernel(const void *__restrict__ xv, const float *__restrict__ win, int chunk, int hop, int navg, int n_split,
+                  float *__restrict__ part) {
     extern __shared__ __align__(16) float2 s[];
+    constexpr int T = FftPlan<N>::THREADS;
+    constexpr int PER = (N + T - 1) / T;
     const int tid = threadIdx.x;
     const int line = blockIdx.y, split = blockIdx.x;
-    const int per = nfft / PSD_THREADS;          // nfft >= PSD_THREADS enforced by host (else per = 0 -> handled)
-    float acc[32];
+    float acc[PER];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int i = 0; i < PER; ++i) acc[i] = 0.f;
     for (int f = split; f < navg; f += n_split) {
         const i64 start = ((i64)line * navg + f) * hop;
-        for (int e = tid; e < nfft; e += PSD_THREADS) {
+        for (int e = tid; e < N; e += T) {
             float2 v = make_float2(0.f, 0.f);
             if (e < chunk) {
-                const float w = win[e];
+                const float w = __ldg(win + e);
                 if (CPLX) {
                     const float2 xx = ((const float2 *)xv)[start + e];
                     v = make_float2(xx.x * w, xx.y * w);
                 } else {
-                    v = make_float2(((const float *)xv)[start + e] * w, 0.f);
+                    v.x = ((const float *)xv)[start + e] * w;
                 }
             }
-            s[e] = v;
+            s[FFT_PAD(e)] = v;
         }
         __syncthreads();
-        fft_smem_dif(s, tw, nfft, log2n, tid, PSD_THREADS);
-        if (per >= 1) {
+        fft_smem<N, false>(s, tid);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if (i < per) {
-                    const int k = tid + i * PSD_THREADS;
-                    const float2 X = s[bitrev((unsigned)k, log2n)];
-                    acc[i] += X.x * X.x + X.y * X.y;
-                }
+        for (int i = 0; i < PER; ++i) {
+            const int p = tid + i * T;
+            if (p < N) {
+                const float2 X = s[FFT_PAD(p)];
+                acc[i] = fmaf(X.x, X.x, fmaf(X.y, X.y, acc[i]));
             }
-        } else if (tid < nfft) {
-            const float2 X = s[bitrev((unsigned)tid, log2n)];
-            acc[0] += X.x * X.x + X.y * X.y;
         }
         __syncthreads();
     }
-    float *p = part + ((size_t)line * n_split + split) * nfft;
-    if (per >= 1) {
+    float *pp = part + ((size_t)line * n_split + split) * N;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (i < per) p[tid + i * PSD_THREADS] = acc[i];
-    } else if (tid < nfft) {
-        p[tid] = acc[0];
+    for (int i = 0; i < PER; ++i) {
+        const int p = tid + i * T;
+        if (p < N) pp[p] = acc[i];
     }
 }
 
-// out[line][fftshift(k)] = dB( sum_split part / (navg * wsum2) )
-__global__ void psd_finalize_kernel(const float *__restrict__ part, int nfft, int n_split, float scale, int dB,
-                                    float *__restrict__ out) {
+// out[line][fftshift(bin(p))] = dB( sum_split part[p] / (navg * wsum2) )
+template <int N>
+__global__ void psd_finalize_kernel(const float *__restrict__ part, int n_split, float scale, int dB, float *__restrict__ out) {
     const int line = blockIdx.y;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nfft) return;
-    const float *p = part + (size_t)line * n_split * nfft + k;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const float *q = part + (size_t)line * n_split * N + p;
     float sum = 0.f;
-    for (int sp = 0; sp < n_split; ++sp) sum += p[(size_t)sp * nfft];
+    for (int sp = 0; sp < n_split; ++sp) sum += q[(size_t)sp * N];
     float v = sum * scale;
     if (dB) v = 10.f * log10f(fmaxf(v, 1.0e-30f));
-    const int ks = (k + nfft / 2) % nfft;        // fftshift
-    out[(size_t)line * nfft + ks] = v;
+    const int k = fft_pos_to_freq<N>(p);
+    out[(size_t)line * N + ((k + N / 2) % N)] = v;                       // fftshift
 }
 
 extern "C" int pysdr_psd_create(int32_t chunk, int32_t nfft, int32_t hop, const float *window, pysdr_psd **out) {
-    if (!out || !window || chunk < 1 || nfft < chunk || hop < 1 || (nfft & (nfft - 1)) != 0 || nfft > 16384 || nfft < 2) {
-        pysdr_set_error("psd_create: need 1 <= chunk <= nfft, nfft a power of two <= 16384 (got chunk=%d nfft=%d hop=%d)", chunk,
+    if (!out || !window || chunk < 1 || nfft < chunk || hop < 1 || (nfft & (nfft - 1)) != 0 || nfft > 16384 || nfft < 64) {
+        pysdr_set_error("psd_create: need 1 <= chunk <= nfft, nfft a power of two in [64,16384] (got chunk=%d nfft=%d hop=%d)", chunk,
                         nfft, hop);
         return PYSDR_ERR_ARG;
     }
-    if (nfft > PSD_THREADS * 32) { pysdr_set_error("psd_create: nfft too large"); return PYSDR_ERR_ARG; }
     pysdr_psd *p = new pysdr_psd();
     p->chunk = chunk; p->nfft = nfft; p->hop = hop;
-    p->log2n = 0;
-    while ((1 << p->log2n) < nfft) p->log2n++;
     p->wsum2 = 0.0;
     for (int i = 0; i < chunk; ++i) p->wsum2 += (double)window[i] * (double)window[i];
     p->d_part = nullptr; p->part_cap = 0; p->launches = 0;
-    std::vector<float2> tw(nfft / 2 > 0 ? nfft / 2 : 1);
-    for (int k = 0; k < nfft / 2; ++k) {
-        const double ang = -2.0 * 3.14159265358979323846 * (double)k / (double)nfft;
-        tw[k] = make_float2((float)cos(ang), (float)sin(ang));
-    }
-    if (cudaMalloc(&p->d_win, sizeof(float) * chunk) != cudaSuccess || cudaMalloc(&p->d_tw, sizeof(float2) * tw.size()) != cudaSuccess) {
+    if (cudaMalloc(&p->d_win, sizeof(float) * chunk) != cudaSuccess) {
         pysdr_set_error("psd_create: cudaMalloc failed");
         delete p;
         return PYSDR_ERR_CUDA;
     }
     CUDA_TRY(cudaMemcpy(p->d_win, window, sizeof(float) * chunk, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(p->d_tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
     *out = p;
     return PYSDR_OK;
 }
 
 extern "C" int pysdr_psd_destroy(pysdr_psd *p) {
     if (!p) return PYSDR_OK;
-    cudaFree(p->d_win); cudaFree(p->d_tw); cudaFree(p->d_part);
+    cudaFree(p->d_win); cudaFree(p->d_part);
     delete p;
     return PYSDR_OK;
 }
 
 extern "C" int64_t pysdr_psd_launch_count(const pysdr_psd *p) { return p ? p->launches : -1; }
+
+template <int N>
+static int psd_launch(pysdr_psd *p, const void *d_x, int is_complex, int navg, int n_split, i64 n_lines, int dB, float *d_out,
+                      cudaStream_t st) {
+    const size_t smem = sizeof(float2) * FFT_SMEM_ELEMS(N);
+    if (smem > 48 * 1024) {
+        CUDA_TRY(cudaFuncSetAttribute(psd_frames_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(psd_frames_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    dim3 grid((unsigned)n_split, (unsigned)n_lines);
+    if (is_complex)
+        psd_frames_kernel<N, true><<<grid, FftPlan<N>::THREADS, smem, st>>>(d_x, p->d_win, p->chunk, p->hop, navg, n_split, p->d_part);
+    else
+        psd_frames_kernel<N, false><<<grid, FftPlan<N>::THREADS, smem, st>>>(d_x, p->d_win, p->chunk, p->hop, navg, n_split, p->d_part);
+    LAUNCH_CHECK();
+    const float scale = (float)(1.0 / ((double)navg * p->wsum2));
+    dim3 g2((unsigned)((N + 255) / 256), (unsigned)n_lines);
+    psd_finalize_kernel<N><<<g2, 256, 0, st>>>(p->d_part, n_split, scale, dB, d_out);
+    LAUNCH_CHECK();
+    p->launches += 2;
+    return PYSDR_OK;
+}
 
 extern "C" int pysdr_psd_lines(pysdr_psd *p, const void *d_x, int64_t n, int is_complex, int32_t navg, int dB, float *d_out,
                                int64_t *n_lines_p, void *stream) {
@@ -158,6 +142,7 @@ extern "C" int pysdr_psd_lines(pysdr_psd *p, const void *d_x, int64_t n, int is_
     const i64 n_lines = n_frames / navg;
     if (n_lines_p) *n_lines_p = n_lines;
     if (n_lines == 0) return PYSDR_OK;
+    if (n_lines > 65535) { pysdr_set_error("psd_lines: more than 65535 lines per call"); return PYSDR_ERR_CAPACITY; }
     int n_split = 1;
     if (n_lines < 296) {
         n_split = (int)((296 + n_lines - 1) / n_lines);
@@ -169,26 +154,19 @@ extern "C" int pysdr_psd_lines(pysdr_psd *p, const void *d_x, int64_t n, int is_
         CUDA_TRY(cudaMalloc(&p->d_part, sizeof(float) * need));
         p->part_cap = need;
     }
-    const size_t smem = sizeof(float2) * (size_t)p->nfft;
-    if (smem > 48 * 1024) {
-        CUDA_TRY(cudaFuncSetAttribute(psd_frames_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(psd_frames_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    switch (p->nfft) {
+        case 64: return psd_launch<64>(p, d_x, is_complex, navg, n_split, n_lines, dB, d_out, st);
+        case 128: return psd_launch<128>(p, d_x, is_complex, navg, n_split, n_lines, dB, d_out, st);
+        case 256: return psd_launch<256>(p, d_x, is_complex, navg, n_split, n_lines, dB, d_out, st);
+        case 512: return psd_launch<512>(p, d_x, is_complex, navg, n_split, n_lines, dB, d_out, st);
+        case 1024: return psd_launch<1024>(p, d_x, is_complex, navg, n_split, n_lines, dB, d_out, st);
+        case 2048: return psd_launch<2048>(p, d_x, is_complex, navg, n_split, n_lines, dB, d_out, st);
+        case 4096: return psd_launch<4096>(p, d_x, is_complex, navg, n_split, n_lines, dB, d_out, st);
+        case 8192: return psd_launch<8192>(p, d_x, is_complex, navg, n_split, n_lines, dB, d_out, st);
+        case 16384: return psd_launch<16384>(p, d_x, is_complex, navg, n_split, n_lines, dB, d_out, st);
     }
-    if (n_lines > 65535) { pysdr_set_error("psd_lines: more than 65535 lines per call"); return PYSDR_ERR_CAPACITY; }
-    dim3 grid((unsigned)n_split, (unsigned)n_lines);
-    if (is_complex)
-        psd_frames_kernel<true><<<grid, PSD_THREADS, smem, st>>>(d_x, n, p->d_win, p->d_tw, p->chunk, p->nfft, p->log2n, p->hop, navg,
-                                                                n_split, p->d_part);
-    else
-        psd_frames_kernel<false><<<grid, PSD_THREADS, smem, st>>>(d_x, n, p->d_win, p->d_tw, p->chunk, p->nfft, p->log2n, p->hop, navg,
-                                                                 n_split, p->d_part);
-    LAUNCH_CHECK();
-    const float scale = (float)(1.0 / ((double)navg * p->wsum2));
-    dim3 g2((unsigned)((p->nfft + 255) / 256), (unsigned)n_lines);
-    psd_finalize_kernel<<<g2, 256, 0, st>>>(p->d_part, p->nfft, n_split, scale, dB, d_out);
-    LAUNCH_CHECK();
-    p->launches += 2;
-    return PYSDR_OK;
+    pysdr_set_error("psd_lines: unsupported nfft %d", p->nfft);
+    return PYSDR_ERR_ARG;
 }
 
 // ---- waterfall (reference Plotting.py) ---------------------------------------------------------------
