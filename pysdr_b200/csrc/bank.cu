@@ -455,7 +455,8 @@ struct pysdr_bank {
     bool force_direct_fir;                  // testing: use the direct-form AF FIR instead of the FFT path
     float2 *d_H;                            // [n_rx][Nfft] FFT of AF taps (position order, 1/N folded in)
     float2 *d_hist, *d_g, *d_C, *d_af;
-    float *d_R, *d_a, *d_peaks, *d_gains;
+    float2 *d_a;                            // pre-AGC audio, rows of a_stride float2 (IQ mode fills complex)
+    float *d_R, *d_peaks, *d_gains;
     AgcState *d_agc;
     // pending front->back
     i64 pend_n_out, pend_m0, pend_B0, pend_blocks;

@@ -61,6 +61,10 @@ struct Bits {
     static constexpr int M = 1 << SB;
 };
 
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 template <int NRXP, int TPL>
 __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a, const FastGeom g) {
     constexpr int RB = Bits<NRXP>::RB;
@@ -69,7 +73,8 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
     constexpr int SLOW = 1 << (SB - 1);          // # values of the non-swizzled low s bits
 
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned long long *bars = (unsigned long long *)smem;          // K1F_STAGES mbarriers
+    unsigned long long *bars = (unsigned long long *)smem;          // K1F_STAGES "full" mbarriers
+    int *done_cnt = (int *)(smem + 32);                              // K1F_STAGES consumer counters
     float2 *stage0 = (float2 *)(smem + 64);
 
     const int tid = threadIdx.x;
@@ -81,12 +86,12 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
     const int S = g.S;
 
     if (tid == 0) {
-        for (int s = 0; s < K1F_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        for (int s = 0; s < K1F_STAGES; ++s) { mbar_init(smem_u32(&bars[s]), 1); done_cnt[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // tile geometry helpers ---------------------------------------------------------------------
+    // tile geometry ---------------------------------------------------------------------------------
     auto tile_a2 = [&](i64 T, i64 &a2, int &cnt2) {
         const i64 q0 = g.q_first + T * S;
         const i64 ar = q0 * down - need_pad - a.n0;              // rel index of first needed element
@@ -95,152 +100,191 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
         int cnt = (int)(br - a2);
         cnt2 = cnt + (cnt & 1);
     };
-    auto tile_interior = [&](i64 a2, int cnt2) { return a2 >= 0 && a2 + cnt2 <= a.n_in; };
 
-    auto issue_tile = [&](i64 T, int st) {       // all threads call; after a __syncthreads that freed `st`
+    // Fill stage `st` with tile T.  Called by ONE warp (all 32 lanes).  Every tile completes exactly one phase
+    // of bars[st]: interior tiles by the bulk copy's complete_tx, edge tiles (stream start/end, zero fill,
+    // carried history) by an explicit arrive after plain stores.
+    auto produce = [&](i64 T, int st) {
         if (T >= g.n_tiles) return;
         i64 a2; int cnt2;
         tile_a2(T, a2, cnt2);
         float2 *dst = stage0 + (size_t)st * K1F_STAGE_ELEMS;
-        if (tile_interior(a2, cnt2)) {
-            if (tid == 0) {
+        const unsigned bar = smem_u32(&bars[st]);
+        if (a2 >= 0 && a2 + cnt2 <= a.n_in) {
+            if (lane == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 const unsigned bytes = (unsigned)cnt2 * 8u;
-                mbar_expect_tx(smem_u32(&bars[st]), bytes);
-                bulk_g2s(smem_u32(dst), a.x + a2, bytes, smem_u32(&bars[st]));
+                mbar_expect_tx(bar, bytes);
+                bulk_g2s(smem_u32(dst), a.x + a2, bytes, bar);
             }
         } else {
-            for (int e = tid; e < cnt2; e += K1F_THREADS) {
+            for (int e = lane; e < cnt2; e += 32) {
                 const i64 rel = a2 + e;
                 float2 v = make_float2(0.f, 0.f);
                 if (rel >= 0) { if (rel < a.n_in) v = a.x[rel]; }
                 else if (rel >= -(i64)a.need) v = a.hist[a.need + rel];
                 dst[e] = v;
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar);
         }
     };
 
-    // per-lane swizzles ---------------------------------------------------------------------------
-    const int sw_s = (lane >> 4) & 1;                                   // flips the top s bit
+    // per-lane constants ------------------------------------------------------------------------------
+    const int sw_s = (lane >> 4) & 1;                                   // flips the top s bit of a slot
     const int sw_r = (NRXP > 1) ? ((lane >> (4 - RB)) & (NRXP - 1)) : 0;
+    const int s_log = (((lane >> 4) & 1) << (SB - 1)) | ((lane >> 1) & (SLOW - 1));   // output this lane stores
+    const int r_log = (NRXP > 1) ? ((lane >> (4 - RB)) & (NRXP - 1)) : 0;
+    const int rx = g.rx0 + r_log;
+    const bool rx_ok = rx < a.n_rx;
+    const u64 my_inc = rx_ok ? a.inc[rx] : 0ull;
+    const u64 my_acc = rx_ok ? a.acc[rx] : 0ull;
+    float2 *my_out = nullptr;                                           // even lanes -> C memory, odd lanes -> rx.iq copy
+    if (rx_ok) {
+        if ((lane & 1) == 0) my_out = a.c_out + (size_t)rx * a.c_stride + a.hc;
+        else if (a.bb_out) my_out = a.bb_out + (size_t)rx * a.bb_stride;
+    }
 
-    float2 tap[NRXP][TPL];
-    int tap_phase_i = -1;
+    float tre[NRXP][TPL], tim[NRXP][TPL];
+    int cur_i = -1, o_i = 0;
 
-    // prologue: fill the ring
     const i64 T0 = blockIdx.x;
     const i64 Tstep = gridDim.x;
-    for (int s = 0; s < K1F_STAGES; ++s) issue_tile(T0 + (i64)s * Tstep, s);
-    __syncthreads();
+    if (warp < K1F_STAGES) produce(T0 + (i64)warp * Tstep, warp);
 
     const int tasks_per_tile = up * (S / M);
-    unsigned phase_bits = 0;                 // per-stage mbarrier parity (only bulk tiles advance it)
+    const int di = K1F_WARPS % up, ds = K1F_WARPS / up;
+    unsigned phase_bits = 0;
     i64 it = 0;
     for (i64 T = T0; T < g.n_tiles; T += Tstep, ++it) {
         const int st = (int)(it % K1F_STAGES);
-        i64 a2; int cnt2;
-        tile_a2(T, a2, cnt2);
-        if (tile_interior(a2, cnt2)) {
-            mbar_wait(smem_u32(&bars[st]), (phase_bits >> st) & 1u);
-            phase_bits ^= (1u << st);
-        }
+        mbar_wait(smem_u32(&bars[st]), (phase_bits >> st) & 1u);
+        phase_bits ^= (1u << st);
         const float2 *xs = stage0 + (size_t)st * K1F_STAGE_ELEMS;
         const i64 q0 = g.q_first + T * S;
+        i64 a2; int cnt2;
+        tile_a2(T, a2, cnt2);
         const int shift = (int)((q0 * down - need_pad - a.n0) - a2);     // 0 or 1
+        const i64 ob = q0 * up - a.m0;                                   // output index of the tile's first output
+        const i64 relb = q0 * down - a.n0;                               // input index (rel. x[0]) of its first sample
+        const u64 pbase = my_acc + my_inc * (u64)relb;
 
+        int i = warp % up, sblk = warp / up;
         for (int t = warp; t < tasks_per_tile; t += K1F_WARPS) {
-            const int i = t % up;
-            const int sblk = t / up;
-            const int idn = i * down;
-            const int o_i = idn / up;
-            const int p_i = idn - o_i * up;
-            if (i != tap_phase_i) {                                     // (re)load this phase's taps
+            if (i != cur_i) {                                           // (re)load this phase's taps
+                const int idn = i * down;
+                o_i = idn / up;
+                const int p_i = idn - o_i * up;
 #pragma unroll
                 for (int r = 0; r < NRXP; ++r) {
                     const int rr = g.rx0 + (r ^ sw_r);
                     const float2 *gp = a.g + ((size_t)rr * up + p_i) * a.lp_pad + lane;
 #pragma unroll
-                    for (int k = 0; k < TPL; ++k)
-                        tap[r][k] = (rr < a.n_rx) ? __ldg(gp + 32 * k) : make_float2(0.f, 0.f);
+                    for (int k = 0; k < TPL; ++k) {
+                        const float2 v = (rr < a.n_rx) ? __ldg(gp + 32 * k) : make_float2(0.f, 0.f);
+                        tre[r][k] = v.x;
+                        tim[r][k] = v.y;
+                    }
                 }
-                tap_phase_i = i;
+                cur_i = i;
             }
-            float acc[32];
+            float are[16], aim[16];
 #pragma unroll
-            for (int v = 0; v < 32; ++v) acc[v] = 0.f;
+            for (int v = 0; v < 16; ++v) { are[v] = 0.f; aim[v] = 0.f; }
 
 #pragma unroll
             for (int stop = 0; stop < 2; ++stop) {
 #pragma unroll
                 for (int sl = 0; sl < SLOW; ++sl) {
                     const int s_eff = ((stop ^ sw_s) << (SB - 1)) | sl;
-                    const int e_m = (sblk * M + s_eff) * down + o_i + need_pad + shift - lane;
+                    const float2 *xp = xs + ((sblk * M + s_eff) * down + o_i + need_pad + shift - lane);
                     float2 xv[TPL];
 #pragma unroll
-                    for (int k = 0; k < TPL; ++k) xv[k] = xs[e_m - 32 * k];
+                    for (int k = 0; k < TPL; ++k) xv[k] = xp[-32 * k];
 #pragma unroll
                     for (int k = 0; k < TPL; ++k) {
+                        // x-stationary order: each x component feeds 2*NRXP consecutive FMAs
 #pragma unroll
                         for (int r = 0; r < NRXP; ++r) {
-                            const int slot = (stop << 4) | (r << (4 - RB)) | (sl << 1);
-                            acc[slot] = fmaf(tap[r][k].x, xv[k].x, acc[slot]);
-                            acc[slot + 1] = fmaf(tap[r][k].x, xv[k].y, acc[slot + 1]);
+                            const int slot = (stop << 3) | (r << (3 - RB)) | sl;
+                            are[slot] = fmaf(tre[r][k], xv[k].x, are[slot]);
                         }
 #pragma unroll
                         for (int r = 0; r < NRXP; ++r) {
-                            const int slot = (stop << 4) | (r << (4 - RB)) | (sl << 1);
-                            acc[slot] = fmaf(-tap[r][k].y, xv[k].y, acc[slot]);
-                            acc[slot + 1] = fmaf(tap[r][k].y, xv[k].x, acc[slot + 1]);
+                            const int slot = (stop << 3) | (r << (3 - RB)) | sl;
+                            aim[slot] = fmaf(tim[r][k], xv[k].x, aim[slot]);
+                        }
+#pragma unroll
+                        for (int r = 0; r < NRXP; ++r) {
+                            const int slot = (stop << 3) | (r << (3 - RB)) | sl;
+                            aim[slot] = fmaf(tre[r][k], xv[k].y, aim[slot]);
+                        }
+#pragma unroll
+                        for (int r = 0; r < NRXP; ++r) {
+                            const int slot = (stop << 3) | (r << (3 - RB)) | sl;
+                            are[slot] = fmaf(-tim[r][k], xv[k].y, are[slot]);
                         }
                     }
                 }
             }
 
-            // butterfly: lane bit 4 and the RB bits below it are swizzled (no selects) ...
+            // butterfly over lanes: bit 4 and the RB bits below it are swizzled (no selects) ...
 #pragma unroll
             for (int step = 0; step < 1 + RB; ++step) {
                 const int off = 16 >> step;
-                const int H = 16 >> step;                               // slots kept
+                const int H = 8 >> step;                                // slots kept (per array)
 #pragma unroll
-                for (int v = 0; v < H; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[H + v], off);
+                for (int v = 0; v < H; ++v) {
+                    are[v] += __shfl_xor_sync(0xffffffffu, are[H + v], off);
+                    aim[v] += __shfl_xor_sync(0xffffffffu, aim[H + v], off);
+                }
             }
             // ... the remaining low s bits use selects
 #pragma unroll
             for (int step = 1 + RB; step < 4; ++step) {
                 const int off = 16 >> step;
-                const int H = 16 >> step;
+                const int H = 8 >> step;
                 const bool upper = (lane & off) != 0;
 #pragma unroll
                 for (int v = 0; v < H; ++v) {
-                    const float send = upper ? acc[v] : acc[H + v];
-                    const float keep = upper ? acc[H + v] : acc[v];
-                    acc[v] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    const float sre = upper ? are[v] : are[H + v];
+                    const float kre = upper ? are[H + v] : are[v];
+                    const float sim = upper ? aim[v] : aim[H + v];
+                    const float kim = upper ? aim[H + v] : aim[v];
+                    are[v] = kre + __shfl_xor_sync(0xffffffffu, sre, off);
+                    aim[v] = kim + __shfl_xor_sync(0xffffffffu, sim, off);
                 }
             }
-            const float sr = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 1);
-            const float si = acc[1] + __shfl_xor_sync(0xffffffffu, acc[1], 1);
+            const float sr = are[0] + __shfl_xor_sync(0xffffffffu, are[0], 1);
+            const float si = aim[0] + __shfl_xor_sync(0xffffffffu, aim[0], 1);
 
-            // epilogue: lane -> (s, r)
-            const int s_log = (((lane >> 4) & 1) << (SB - 1)) | ((lane >> 1) & (SLOW - 1));
-            const int r_log = (NRXP > 1) ? ((lane >> (4 - RB)) & (NRXP - 1)) : 0;
-            const int rx = g.rx0 + r_log;
-            const i64 q = q0 + (i64)sblk * M + s_log;
-            const i64 m = q * up + i;
-            const i64 oi = m - a.m0;
-            if (rx < a.n_rx && oi >= 0 && oi < a.n_out) {
-                const i64 rel = q * down + o_i - a.n0;
-                const float2 cs = nco_cs(a.acc[rx] + a.inc[rx] * (u64)rel);
+            // epilogue: de-rotate by the exact LO phase of the output's newest input sample and store
+            const int qrel = sblk * M + s_log;
+            const i64 oi = ob + (i64)(qrel * up + i);
+            if (my_out && oi >= 0 && oi < a.n_out) {
+                const u64 ph = pbase + my_inc * (u64)(unsigned)(qrel * down + o_i);
+                const float ang = (float)(int)(ph >> 32) * 1.4629180792671596e-09f;      // 2*pi*2^-32
+                float sn, cs;
+                __sincosf(ang, &sn, &cs);
                 float2 y;
-                y.x = sr * cs.x + si * cs.y;
-                y.y = si * cs.x - sr * cs.y;
-                if ((lane & 1) == 0) a.c_out[(size_t)rx * a.c_stride + a.hc + oi] = y;
-                else if (a.bb_out) a.bb_out[(size_t)rx * a.bb_stride + oi] = y;
+                y.x = fmaf(sr, cs, si * sn);                            // (sr + j si)(cos - j sin)
+                y.y = fmaf(si, cs, -sr * sn);
+                my_out[oi] = y;
             }
+            i += di; sblk += ds;
+            if (i >= up) { i -= up; sblk += 1; }
         }
-        __syncthreads();                                                // stage `st` is free
-        issue_tile(T + (i64)K1F_STAGES * Tstep, st);
-        // edge tiles are written with plain stores: make them visible before they are consumed
-        // (the __syncthreads at the end of the next iteration orders them; K1F_STAGES >= 2).
+
+        // release the stage: the LAST warp to finish this tile refills it with tile T + STAGES*Tstep
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+            __threadfence_block();
+            last = (atomicAdd(&done_cnt[st], 1) == K1F_WARPS - 1);
+            if (last) done_cnt[st] = 0;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) produce(T + (i64)K1F_STAGES * Tstep, st);
     }
 }
 

@@ -257,10 +257,10 @@ def test_front_back_split_with_replayed_peaks_equals_streaming():
     pk = torch.zeros((2, 3), dtype=torch.float32, device="cuda")
     sh.process_front(xd[3 * C:], pk, halo_in_place=True)
     am2, _, _ = sh.process_back(prev_peaks=pk_all[:, :3].contiguous())
-    torch.testing.assert_close(pk, pk_all[:, 3:], rtol=0, atol=0)
+    torch.testing.assert_close(pk, pk_all[:, 3:], rtol=1e-5, atol=0)   # overlap-save block boundaries differ: FFT round-off
     for r in range(2):
         # earlier blocks' AGC is replayed as a parallel composition (re-associated float64): equal to ~1e-7
-        np.testing.assert_allclose(am2[r].cpu().numpy(), ref[r][m3:], rtol=2e-6, atol=1e-9)
+        assert_parity(am2[r].cpu().numpy(), ref[r][m3:], "shard vs single stream rx%d" % r, rel_tol=2e-5, snr_min=90)
 
 
 # ------------------------------------------------------------------------------------------------ L1 surface
