@@ -110,23 +110,32 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
         tile_a2(T, a2, cnt2);
         float2 *dst = stage0 + (size_t)st * K1F_STAGE_ELEMS;
         const unsigned bar = smem_u32(&bars[st]);
-        if (a2 >= 0 && a2 + cnt2 <= a.n_in) {
-            if (lane == 0) {
+        // part of the tile that exists in x[0, n_in), shrunk to 16-byte aligned ends -> one bulk copy
+        i64 blo = a2 > 0 ? a2 : 0, bhi = (a2 + cnt2 < a.n_in) ? a2 + cnt2 : a.n_in;
+        blo += (blo + par) & 1;
+        bhi -= (bhi + par) & 1;
+        const bool bulk = bhi > blo;
+        if (!bulk) { blo = a2; bhi = a2; }
+        // everything else (carried history before x[0], zero fill past the end, odd edge elements): plain stores
+        const int n_head = (int)(blo - a2), n_tail = (int)(a2 + cnt2 - bhi);
+        for (int e = lane; e < n_head + n_tail; e += 32) {
+            const int ee = e < n_head ? e : (int)(bhi - a2) + (e - n_head);
+            const i64 rel = a2 + ee;
+            float2 v = make_float2(0.f, 0.f);
+            if (rel >= 0) { if (rel < a.n_in) v = a.x[rel]; }
+            else if (rel >= -(i64)a.need) v = a.hist[a.need + rel];
+            dst[ee] = v;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (bulk) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                const unsigned bytes = (unsigned)cnt2 * 8u;
+                const unsigned bytes = (unsigned)(bhi - blo) * 8u;
                 mbar_expect_tx(bar, bytes);
-                bulk_g2s(smem_u32(dst), a.x + a2, bytes, bar);
+                bulk_g2s(smem_u32(dst + (blo - a2)), a.x + blo, bytes, bar);
+            } else {
+                mbar_arrive(bar);
             }
-        } else {
-            for (int e = lane; e < cnt2; e += 32) {
-                const i64 rel = a2 + e;
-                float2 v = make_float2(0.f, 0.f);
-                if (rel >= 0) { if (rel < a.n_in) v = a.x[rel]; }
-                else if (rel >= -(i64)a.need) v = a.hist[a.need + rel];
-                dst[e] = v;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar);
         }
     };
 
@@ -154,6 +163,7 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
 
     const int tasks_per_tile = up * (S / M);
     const int di = K1F_WARPS % up, ds = K1F_WARPS / up;
+    const int i_first = warp % up, sblk_first = warp / up;
     unsigned phase_bits = 0;
     i64 it = 0;
     for (i64 T = T0; T < g.n_tiles; T += Tstep, ++it) {
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
         const i64 relb = q0 * down - a.n0;                               // input index (rel. x[0]) of its first sample
         const u64 pbase = my_acc + my_inc * (u64)relb;
 
-        int i = warp % up, sblk = warp / up;
+        int i = i_first, sblk = sblk_first;
         for (int t = warp; t < tasks_per_tile; t += K1F_WARPS) {
             if (i != cur_i) {                                           // (re)load this phase's taps
                 const int idn = i * down;
