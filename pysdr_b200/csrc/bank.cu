@@ -244,9 +244,9 @@ struct AgcScanArgs {
 // agc.m loop filter otherwise), w_b = min(ref / max(maxbuf_b, 1e-9), 1e4), maxbuf_b = max of the last 8 peaks.
 // maxbuf/w are data-parallel.  f_b(g) = min(A, C + D*g) is closed under composition
 //     (f2 o f1)(g) = min( min(A2, C2 + D2*A1),  (C2 + D2*C1) + (D2*D1)*g )
-// so the replay of EARLIER shards' blocks (time-sharded runs) is an ordered parallel reduction; this call's own
-// blocks run the recurrence sequentially in one thread (1 DFMA + 1 DMNMX per block) so that chunk-at-a-time and
-// whole-capture processing produce bit-identical gains.  One CTA per receiver.
+// so the recurrence over blocks — this call's own blocks and, in time-sharded runs, the replay of all EARLIER
+// shards' blocks — is an ordered parallel scan in float64 (re-association changes gains at the 1e-16 level,
+// far below the float32 gain that is applied).  One CTA per receiver.
 #define AGC_TILE 2048
 #define AGC_THREADS 256
 
@@ -307,40 +307,51 @@ __global__ void __launch_bounds__(AGC_THREADS) agc_scan_kernel(AgcScanArgs p) {
             if (i == len - 1) s_mb = (double)mb;
         }
         __syncthreads();
-        if (in_prev) {
-            // ordered parallel composition of this tile's block functions
-            AgcFn f; f.A = 1.0e300; f.C = 0.0; f.D = 1.0;                  // identity
+        {
+            // ordered parallel scan of the tile's block functions; thread t owns `per` consecutive blocks
+            const double g_in = s_g;
             const int per = (len + AGC_THREADS - 1) / AGC_THREADS;
+            const int i0 = tid * per;
+            AgcFn f; f.A = 1.0e300; f.C = 0.0; f.D = 1.0;                  // identity
             for (int j = 0; j < per; ++j) {
-                const int i = tid * per + j;
+                const int i = i0 + j;
                 if (i < len) { AgcFn g; g.A = s_w[i]; g.C = beta * s_w[i]; g.D = D; f = agc_compose(f, g); }
             }
+            AgcFn incl = f;
             for (int o = 1; o < 32; o <<= 1) {                             // inclusive ordered scan inside the warp
                 AgcFn lo;
-                lo.A = __shfl_up_sync(0xffffffffu, f.A, o);
-                lo.C = __shfl_up_sync(0xffffffffu, f.C, o);
-                lo.D = __shfl_up_sync(0xffffffffu, f.D, o);
-                if ((tid & 31) >= o) f = agc_compose(lo, f);
+                lo.A = __shfl_up_sync(0xffffffffu, incl.A, o);
+                lo.C = __shfl_up_sync(0xffffffffu, incl.C, o);
+                lo.D = __shfl_up_sync(0xffffffffu, incl.D, o);
+                if ((tid & 31) >= o) incl = agc_compose(lo, incl);
             }
-            if ((tid & 31) == 31) s_fn[tid >> 5] = f;
+            if ((tid & 31) == 31) s_fn[tid >> 5] = incl;
+            AgcFn ex;                                                      // lanes before this one in the warp
+            ex.A = __shfl_up_sync(0xffffffffu, incl.A, 1);
+            ex.C = __shfl_up_sync(0xffffffffu, incl.C, 1);
+            ex.D = __shfl_up_sync(0xffffffffu, incl.D, 1);
             __syncthreads();
-            if (tid == 0) {
-                AgcFn t = s_fn[0];
-                for (int w = 1; w < AGC_THREADS / 32; ++w) t = agc_compose(t, s_fn[w]);
-                // gain before the tile's last block (for err) is not tracked in the replay; err is refreshed below
-                s_g = fmin(t.A, fma(t.D, s_g, t.C));
+            AgcFn pre; pre.A = 1.0e300; pre.C = 0.0; pre.D = 1.0;
+            for (int w = 0; w < (tid >> 5); ++w) pre = agc_compose(pre, s_fn[w]);
+            if ((tid & 31) > 0) pre = agc_compose(pre, ex);
+            double g = fmin(pre.A, fma(pre.D, g_in, pre.C));               // gain entering this thread's blocks
+            if (!in_prev) {
+                const i64 b0 = t0 - n_prev;
+                for (int j = 0; j < per; ++j) {
+                    const int i = i0 + j;
+                    if (i < len) {
+                        const double w = s_w[i];
+                        if (i == len - 1) s_err = w - g;
+                        g = fmin(w, fma(D, g, beta * w));
+                        gains[b0 + i] = (float)g;
+                    }
+                }
             }
-        } else if (tid == 0) {
-            double g = s_g, err = s_err;
-            const i64 b0 = t0 - n_prev;
-#pragma unroll 4
-            for (int i = 0; i < len; ++i) {
-                const double w = s_w[i];
-                err = w - g;
-                g = fmin(w, fma(D, g, beta * w));
-                gains[b0 + i] = (float)g;
+            __syncthreads();                                               // every thread has read s_g
+            if (tid == AGC_THREADS - 1) {
+                const AgcFn tot = agc_compose(pre, f);
+                s_g = fmin(tot.A, fma(tot.D, g_in, tot.C));
             }
-            s_g = g; s_err = err;
         }
         __syncthreads();
         float ctxv = 0.f;                                                  // context for the next tile:
@@ -362,11 +373,19 @@ __global__ void __launch_bounds__(AGC_THREADS) agc_scan_kernel(AgcScanArgs p) {
     }
 }
 
-// K2e: am = a*gain ; am_dc = am - mean_block(am) for AM/USB.  grid (n_blocks), launch per receiver.
+// K2e: am = a*gain ; am_dc = am - mean_block(am) for AM/USB.  grid (n_blocks, n_rx); IQ rows are skipped.
+struct ApplyKinds { int kind[PYSDR_MAX_RX]; };     // 0 skip (IQ), 1 real, 2 real + per-block DC removal
 __global__ void __launch_bounds__(256)
-agc_apply_kernel(const float *__restrict__ a, const float *__restrict__ gains, float *__restrict__ am,
-                 float *__restrict__ am_dc, int dc_remove, i64 B0, i64 in_chunk, int up, int down, i64 m0,
+agc_apply_kernel(const float *__restrict__ a, i64 a_row, const float *__restrict__ gains, i64 g_row, float *__restrict__ am,
+                 float *__restrict__ am_dc, i64 am_row, ApplyKinds kinds, i64 B0, i64 in_chunk, int up, int down, i64 m0,
                  i64 n_out) {
+    const int kind = kinds.kind[blockIdx.y];
+    if (kind == 0) return;
+    const int dc_remove = kind == 2;
+    a += (size_t)blockIdx.y * a_row;
+    gains += (size_t)blockIdx.y * g_row;
+    am += (size_t)blockIdx.y * am_row;
+    if (am_dc) am_dc += (size_t)blockIdx.y * am_row;
     i64 lo, hi;
     block_range(blockIdx.x, B0, in_chunk, up, down, m0, n_out, lo, hi);
     const float g = gains[blockIdx.x];
@@ -887,7 +906,11 @@ extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks,
     agc_scan_kernel<<<c.n_rx, AGC_THREADS, 0, st>>>(s);
     LAUNCH_CHECK();
     b->launches++;
-    for (int r = 0; r < c.n_rx; ++r) {
+    ApplyKinds kinds;
+    bool any_real = false;
+    for (int r = 0; r < PYSDR_MAX_RX; ++r) {
+        kinds.kind[r] = 0;
+        if (r >= c.n_rx) continue;
         const float *aout = (const float *)(b->d_a + (size_t)r * b->a_stride);
         float *am = d_am + (size_t)r * 2 * out_stride;
         float *amdc = d_am_dc ? d_am_dc + (size_t)r * 2 * out_stride : nullptr;
@@ -903,12 +926,16 @@ extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks,
                 b->launches++;
             }
         } else {
-            const int dc = (b->mode[r] == PYSDR_MODE_AM || b->mode[r] == PYSDR_MODE_USB) ? 1 : 0;
-            agc_apply_kernel<<<(unsigned)n_blocks, 256, 0, st>>>(aout, b->d_gains + (size_t)r * b->max_blocks, am, amdc, dc,
-                                                                b->pend_B0, c.in_chunk, c.up, c.down, b->pend_m0, n_out);
-            LAUNCH_CHECK();
-            b->launches++;
+            kinds.kind[r] = (b->mode[r] == PYSDR_MODE_AM || b->mode[r] == PYSDR_MODE_USB) ? 2 : 1;
+            any_real = true;
         }
+    }
+    if (any_real) {
+        dim3 grid((unsigned)n_blocks, (unsigned)c.n_rx);
+        agc_apply_kernel<<<grid, 256, 0, st>>>((const float *)b->d_a, 2 * b->a_stride, b->d_gains, b->max_blocks, d_am, d_am_dc,
+                                               2 * out_stride, kinds, b->pend_B0, c.in_chunk, c.up, c.down, b->pend_m0, n_out);
+        LAUNCH_CHECK();
+        b->launches++;
     }
     if (b->timing) {
         cudaEvent_t e;

@@ -40,28 +40,44 @@ af_fftconv_kernel(const FftConvArgs a) {
     const i64 avail = (i64)(L - 1) + a.n_out;                             // valid src samples
     const float2 *C = a.C + (size_t)rx * a.c_stride;                      // C[k+2] <-> src[k] for complex modes
 
-    // ---- load + fused detection --------------------------------------------------------------------------
-    for (int e = tid; e < N; e += T) {
-        const i64 k = k0 + e;
-        float2 u = make_float2(0.f, 0.f);
-        if (k < avail) {
-            const float2 c2 = C[k + 2];
-            if (mode == PYSDR_MODE_AM) {
-                u.x = sqrtf(c2.x * c2.x + c2.y * c2.y);
-            } else if (mode == PYSDR_MODE_NFM) {
-                const float2 c0 = C[k], c1 = C[k + 1];
-                const float dr = c2.x - c0.x, di = c2.y - c0.y;
-                u.x = c1.x * di - c1.y * dr;                              // nfm.m:126
-            } else {
-                u = c2;
+    // ---- load + fused detection (fully unrolled: all global loads of a thread are in flight together) -------
+    constexpr int PER = N / T;
+    {
+        float2 c0[PER], c1[PER], c2[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const i64 k = k0 + tid + i * T;
+            c0[i] = c1[i] = c2[i] = make_float2(0.f, 0.f);
+            if (k < avail) {
+                c2[i] = C[k + 2];
+                if (mode == PYSDR_MODE_NFM) { c0[i] = C[k]; c1[i] = C[k + 1]; }
             }
         }
-        s[FFT_PAD(e)] = u;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            float2 u = c2[i];
+            if (mode == PYSDR_MODE_AM) {
+                u = make_float2(sqrtf(c2[i].x * c2[i].x + c2[i].y * c2[i].y), 0.f);
+            } else if (mode == PYSDR_MODE_NFM) {
+                const float dr = c2[i].x - c0[i].x, di = c2[i].y - c0[i].y;
+                u = make_float2(c1[i].x * di - c1[i].y * dr, 0.f);        // nfm.m:126
+            }
+            s[FFT_PAD(tid + i * T)] = u;
+        }
     }
     __syncthreads();
     fft_smem<N, false>(s, tid);
-    const float2 *H = a.H + (size_t)rx * N;
-    for (int p = tid; p < N; p += T) s[FFT_PAD(p)] = cmul(s[FFT_PAD(p)], __ldg(H + p));
+    {
+        const float2 *H = a.H + (size_t)rx * N;
+        float2 h[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) h[i] = __ldg(H + tid + i * T);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int p = tid + i * T;
+            s[FFT_PAD(p)] = cmul(s[FFT_PAD(p)], h[i]);
+        }
+    }
     __syncthreads();
     fft_smem<N, true>(s, tid);
 
