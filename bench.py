@@ -231,7 +231,7 @@ def run_own(args):
     n = n_chunks * C                                   # samples per GPU per step
     offs = receiver_offsets(P)
     from pysdr_b200.dist import ShardedCapture
-    bank = ReceiverBank(P, offs, max_in=n, device=dev)
+    bank = ReceiverBank(P, offs, max_in=n + (C if rank > 0 else 0), device=dev)
     shard = ShardedCapture(bank, P, rank, world, n_chunks)          # plan: warm-up chunk + K1 halo for rank > 0
     plan = shard.plan
     warm = plan['warm_chunks']

@@ -51,27 +51,42 @@ def exchange_agc_peaks(peaks, rank, world, group=None):
 
 
 class ShardedCapture:
-    """Per-rank driver of one time shard on the GPU bank (used by bench.py for N>1 and by receiver-level tools)."""
+    """Per-rank driver of one time shard on the GPU bank (used by bench.py for N>1 and by receiver-level tools).
+
+    The warm-up chunk(s) that rebuild the audio-rate filter memory are processed in the SAME call as the shard
+    (one K1 launch over [start - warm*C, start + n)); their outputs are simply not returned."""
 
     def __init__(self, bank, P, rank, world, chunks_per_rank):
         self.bank, self.P, self.rank, self.world = bank, P, rank, world
         self.plan = shard_plan(P, rank, world, chunks_per_rank)
         dev = bank.device
-        self.peaks = torch.zeros((bank.n_rx, self.plan['n_blocks']), dtype=torch.float32, device=dev)
-        self.warm_pk = torch.zeros((bank.n_rx, max(1, self.plan['warm_chunks'])), dtype=torch.float32, device=dev)
+        w = self.plan['warm_chunks']
+        self.peaks_ext = torch.zeros((bank.n_rx, w + self.plan['n_blocks']), dtype=torch.float32, device=dev)
+        self.own = torch.zeros((bank.n_rx, self.plan['n_blocks']), dtype=torch.float32, device=dev)
+        C = int(P.IN_CHUNK_SIZE)
+        up, down = int(P.UP), int(P.DOWN)
+        s0 = self.plan['start']
+        self.skip_out = (-((-up * s0) // down)) - (-((-up * (s0 - w * C)) // down))     # outputs of the warm-up blocks
+        if bank.max_in < self.plan['n'] + w * C:
+            raise ValueError("bank.max_in must cover the shard plus its %d warm-up chunk(s)" % w)
 
     def step(self, xbuf, want_dc=False):
-        """xbuf: device tensor holding samples [first_sample, start+n) of the capture."""
+        """xbuf: device tensor holding samples [first_sample, start+n) of the capture.
+        Returns (am, iq, am_dc) views of this rank's shard."""
         p, b = self.plan, self.bank
         C = int(self.P.IN_CHUNK_SIZE)
-        main = xbuf[p['lead']:]
-        if p['warm_chunks']:
-            b.seek(p['start'] - p['warm_chunks'] * C)
-            b.process_front(xbuf[p['halo']:p['lead']], self.warm_pk, halo_in_place=True)
-            b.process_back(want_dc=False)                                # outputs discarded: memories are now exact
-            b.process_front(main, self.peaks, halo_in_place=True)
+        w = p['warm_chunks']
+        if w:
+            b.seek(p['start'] - w * C)
+            b.process_front(xbuf[p['halo']:], self.peaks_ext, halo_in_place=True)
+            self.own.copy_(self.peaks_ext[:, w:])
         else:
             b.seek(0)
-            b.process_front(main, self.peaks)
-        prev = exchange_agc_peaks(self.peaks, self.rank, self.world)
-        return b.process_back(prev_peaks=prev, want_dc=want_dc)
+            b.process_front(xbuf[p['lead']:], self.peaks_ext)
+            self.own = self.peaks_ext
+        prev = exchange_agc_peaks(self.own, self.rank, self.world)
+        if prev is not None and w:
+            prev = prev[:, :prev.shape[1] - w].contiguous()          # the warm-up blocks' peaks are our own
+        am, iq, dc = b.process_back(prev_peaks=prev, want_dc=want_dc)
+        k = self.skip_out
+        return [a[k:] for a in am], [a[k:] for a in iq], [a[k:] for a in dc]

@@ -14,12 +14,14 @@ def synth_iq(n, srate, offsets_hz, modes, seed=1234, device="cpu", n0=0, noise_d
     out = torch.empty(n, dtype=torch.complex64, device=dev)
     g = torch.Generator(device=dev)
     sigma = 10.0 ** (noise_db / 20.0) / math.sqrt(2.0)
-    for b0 in range(0, n, block):
-        b1 = min(n, b0 + block)
-        g.manual_seed(seed + 7919 * ((n0 + b0) // block))
-        t = (torch.arange(b0, b1, device=dev, dtype=torch.float64) + float(n0)) / float(srate)
-        z = torch.randn(b1 - b0, 2, generator=g, device=dev, dtype=torch.float32) * sigma
-        acc = torch.view_as_complex(z).to(torch.complex128)
+    n0 = int(n0)
+    for kb in range(n0 // block, (n0 + n - 1) // block + 1):          # absolute blocks: shards of one capture agree
+        lo, hi = max(n0, kb * block), min(n0 + n, (kb + 1) * block)
+        b0, b1 = lo - n0, hi - n0
+        g.manual_seed(seed + 7919 * kb)
+        t = torch.arange(lo, hi, device=dev, dtype=torch.float64) / float(srate)
+        z = torch.randn(block, 2, generator=g, device=dev, dtype=torch.float32)[lo - kb * block:hi - kb * block] * sigma
+        acc = torch.view_as_complex(z.contiguous()).to(torch.complex128)
         for f0, mode in zip(offsets_hz, modes):
             w = 2.0 * math.pi * t
             if mode in ('AM', 'AM-Synch'):
