@@ -113,11 +113,13 @@ int pysdr_bank_process(pysdr_bank *b, const void *d_iq, int64_t n_in, int halo_i
  * caller may all-gather d_peaks across ranks (NCCL) and pass the peaks of ALL earlier blocks.
  *   d_peaks: float32[n_rx][n_blocks(n_in)] written by front (device).
  *   back:  d_prev_peaks float32[n_rx][n_prev] = peaks of the n_prev blocks preceding this call's
- *          first block (NULL/0: continue from the carried AGC state). */
+ *          first REAL block (NULL/0: continue from the carried AGC state);
+ *          skip_blocks = leading blocks of the front call that only warmed the filter memories (their audio and
+ *          peaks are not valid and are excluded from the recursion). */
 int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t n_in, int halo_in_place,
                              void *d_iq_bb, int64_t out_stride, float *d_peaks, int64_t *n_out,
                              void *stream);
-int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev,
+int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, int64_t skip_blocks,
                             float *d_am, float *d_am_dc, int64_t out_stride, void *stream);
 /* Move the stream position without processing (time shards): n0 must be a multiple of in_chunk.
  * LO/BFO accumulators follow; filter memories are cleared; n0 == 0 also resets the AGC (stream restart).

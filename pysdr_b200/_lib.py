@@ -49,7 +49,7 @@ SIGNATURES = {
     "pysdr_bank_n_blocks": (c_i64, [c_vp, c_i64]),
     "pysdr_bank_process": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),
     "pysdr_bank_process_front": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, ctypes.POINTER(c_i64), c_vp]),
-    "pysdr_bank_process_back": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "pysdr_bank_process_back": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "pysdr_bank_seek": (c_int, [c_vp, c_i64, c_vp]),
     "pysdr_bank_set_timing": (c_int, [c_vp, c_int]),
     "pysdr_bank_get_timing": (c_int, [c_vp, ctypes.POINTER(c_dbl), c_vp]),

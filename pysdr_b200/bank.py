@@ -202,10 +202,10 @@ class ReceiverBank:
         self.n_out = n_out.value
         return self.n_out
 
-    def process_back(self, prev_peaks=None, want_dc=True):
+    def process_back(self, prev_peaks=None, want_dc=True, skip_blocks=0):
         pp = ctypes.c_void_p(prev_peaks.data_ptr()) if prev_peaks is not None and prev_peaks.numel() else None
         n_prev = 0 if pp is None else prev_peaks.shape[1]
-        check(self.lib.pysdr_bank_process_back(self.h, pp, n_prev, ctypes.c_void_p(self._am.data_ptr()),
+        check(self.lib.pysdr_bank_process_back(self.h, pp, n_prev, int(skip_blocks), ctypes.c_void_p(self._am.data_ptr()),
                                                ctypes.c_void_p(self._am_dc.data_ptr()) if want_dc else None,
                                                self.max_out, _stream_ptr()))
         return self.views()

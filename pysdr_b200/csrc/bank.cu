@@ -236,6 +236,7 @@ struct AgcScanArgs {
     float *gains;                    // [n_rx][gains_stride]
     i64 gains_stride;
     i64 n_blocks;
+    i64 skip;                        // leading blocks of this call that are filter warm-up: not part of the recursion
     int n_rx;
     int enabled[PYSDR_MAX_RX];
 };
@@ -273,7 +274,10 @@ __global__ void __launch_bounds__(AGC_THREADS) agc_scan_kernel(AgcScanArgs p) {
     __shared__ AgcState st;
     __shared__ double s_g, s_err, s_mb;
     const float *prev = p.prev_peaks ? p.prev_peaks + (size_t)rx * p.n_prev : nullptr;
-    const float *own = p.peaks + (size_t)rx * p.peaks_stride;
+    const float *own = p.peaks + (size_t)rx * p.peaks_stride + p.skip;
+    gains += p.skip;
+    for (i64 b = tid; b < p.skip; b += AGC_THREADS) gains[b - p.skip] = 1.f;
+    const i64 n_own = p.n_blocks - p.skip;
     const i64 n_prev = prev ? p.n_prev : 0;
     if (tid == 0) {
         st = p.state[rx];
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(AGC_THREADS) agc_scan_kernel(AgcScanArgs p) {
     const double ref = st.ref, beta = st.beta, D = 1.0 - st.beta;
     const i64 k0 = st.k;
     if (tid < 7) s_pk[6 - tid] = (float)st.ring[(int)(((k0 - 1 - tid) % 8 + 8) % 8)];   // 7 peaks before element 0
-    const i64 n_total = n_prev + p.n_blocks;
+    const i64 n_total = n_prev + n_own;
     for (i64 t0 = 0; t0 < n_total;) {
         // a tile never straddles the prev/own boundary
         const bool in_prev = t0 < n_prev;
@@ -882,8 +886,8 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
     return PYSDR_OK;
 }
 
-extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, float *d_am,
-                                       float *d_am_dc, int64_t out_stride, void *stream) {
+extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, int64_t skip_blocks,
+                                       float *d_am, float *d_am_dc, int64_t out_stride, void *stream) {
     if (!b || !b->pending) { pysdr_set_error("process_back without process_front"); return PYSDR_ERR_STATE; }
     if (!d_am) { pysdr_set_error("process_back: d_am is null"); return PYSDR_ERR_ARG; }
     const pysdr_bank_config &c = b->cfg;
@@ -895,7 +899,8 @@ extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks,
     s.peaks = b->pend_peaks; s.peaks_stride = n_blocks;
     s.prev_peaks = (n_prev > 0) ? d_prev_peaks : nullptr; s.n_prev = n_prev;
     s.gains = b->d_gains; s.gains_stride = b->max_blocks;
-    s.n_blocks = n_blocks; s.n_rx = c.n_rx;
+    if (skip_blocks < 0 || skip_blocks >= n_blocks) { pysdr_set_error("process_back: bad skip_blocks"); return PYSDR_ERR_ARG; }
+    s.n_blocks = n_blocks; s.n_rx = c.n_rx; s.skip = skip_blocks;
     for (int r = 0; r < PYSDR_MAX_RX; ++r) s.enabled[r] = (r < c.n_rx && b->mode[r] != PYSDR_MODE_IQ) ? 1 : 0;
     if (b->timing) {
         cudaEvent_t e;
@@ -978,7 +983,7 @@ extern "C" int pysdr_bank_process(pysdr_bank *b, const void *d_iq, int64_t n_in,
     if (!b) { pysdr_set_error("null bank"); return PYSDR_ERR_ARG; }
     int rc = pysdr_bank_process_front(b, d_iq, n_in, halo_in_place, d_iq_bb, out_stride, b->d_peaks, n_out, stream);
     if (rc) return rc;
-    return pysdr_bank_process_back(b, nullptr, 0, d_am, d_am_dc, out_stride, stream);
+    return pysdr_bank_process_back(b, nullptr, 0, 0, d_am, d_am_dc, out_stride, stream);
 }
 
 __global__ void agc_reset_kernel(AgcState *s, int n) {

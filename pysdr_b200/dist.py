@@ -84,9 +84,7 @@ class ShardedCapture:
             b.seek(0)
             b.process_front(xbuf[p['lead']:], self.peaks_ext)
             self.own = self.peaks_ext
-        prev = exchange_agc_peaks(self.own, self.rank, self.world)
-        if prev is not None and w:
-            prev = prev[:, :prev.shape[1] - w].contiguous()          # the warm-up blocks' peaks are our own
-        am, iq, dc = b.process_back(prev_peaks=prev, want_dc=want_dc)
+        prev = exchange_agc_peaks(self.own, self.rank, self.world)  # peaks of ALL earlier blocks (incl. the warm-up ones,
+        am, iq, dc = b.process_back(prev_peaks=prev, want_dc=want_dc, skip_blocks=w)   # whose own peaks are not valid)
         k = self.skip_out
         return [a[k:] for a in am], [a[k:] for a in iq], [a[k:] for a in dc]
