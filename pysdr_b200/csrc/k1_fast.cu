@@ -57,7 +57,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
 template <int NRXP>
 struct Bits {
     static constexpr int RB = (NRXP == 4) ? 2 : (NRXP == 2 ? 1 : 0);
-    static constexpr int SB = 4 - RB;
+    static constexpr int SB = 3 - RB;          // 8 accumulator slots = 2^SB outputs x NRXP receivers
     static constexpr int M = 1 << SB;
 };
 
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
     // per-lane constants ------------------------------------------------------------------------------
     const int sw_s = (lane >> 4) & 1;                                   // flips the top s bit of a slot
     const int sw_r = (NRXP > 1) ? ((lane >> (4 - RB)) & (NRXP - 1)) : 0;
-    const int s_log = (((lane >> 4) & 1) << (SB - 1)) | ((lane >> 1) & (SLOW - 1));   // output this lane stores
+    const int s_log = (((lane >> 4) & 1) << (SB - 1)) | ((lane >> 2) & (SLOW - 1));   // output this lane stores
     const int r_log = (NRXP > 1) ? ((lane >> (4 - RB)) & (NRXP - 1)) : 0;
     const int rx = g.rx0 + r_log;
     const bool rx_ok = rx < a.n_rx;
@@ -150,11 +150,11 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
     const u64 my_acc = rx_ok ? a.acc[rx] : 0ull;
     float2 *my_out = nullptr;                                           // even lanes -> C memory, odd lanes -> rx.iq copy
     if (rx_ok) {
-        if ((lane & 1) == 0) my_out = a.c_out + (size_t)rx * a.c_stride + a.hc;
-        else if (a.bb_out) my_out = a.bb_out + (size_t)rx * a.bb_stride;
+        if ((lane & 3) == 0) my_out = a.c_out + (size_t)rx * a.c_stride + a.hc;
+        else if ((lane & 3) == 1 && a.bb_out) my_out = a.bb_out + (size_t)rx * a.bb_stride;
     }
 
-    float tre[NRXP][TPL], tim[NRXP][TPL];
+    float2 tap[NRXP][TPL];                                              // (g_re, g_im) pairs, FFMA2 operands
     int cur_i = -1, o_i = 0;
 
     const i64 T0 = blockIdx.x;
@@ -164,20 +164,78 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
     const int tasks_per_tile = up * (S / M);
     const int di = K1F_WARPS % up, ds = K1F_WARPS / up;
     const int i_first = warp % up, sblk_first = warp / up;
+    // ---- software-pipelined reduction: state of the task whose FMAs have just finished ---------------------
+    float p_re[8], p_im[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) { p_re[v] = 0.f; p_im[v] = 0.f; }
+    float2 *p_ptr = nullptr;
+    float p_ang = 0.f;
+    auto reduce_store = [&]() {
+        float are[8], aim[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) { are[v] = p_re[v]; aim[v] = p_im[v]; }
+        // butterfly over lanes: bit 4 and the RB bits below it are swizzled (no selects) ...
+#pragma unroll
+        for (int step = 0; step < 1 + RB; ++step) {
+            const int off = 16 >> step;
+            const int H = 4 >> step;                                    // slots kept (per array)
+#pragma unroll
+            for (int v = 0; v < H; ++v) {
+                are[v] += __shfl_xor_sync(0xffffffffu, are[H + v], off);
+                aim[v] += __shfl_xor_sync(0xffffffffu, aim[H + v], off);
+            }
+        }
+        // ... the remaining low s bits use selects
+#pragma unroll
+        for (int step = 1 + RB; step < 3; ++step) {
+            const int off = 16 >> step;
+            const int H = 4 >> step;
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int v = 0; v < H; ++v) {
+                const float sre = upper ? are[v] : are[H + v];
+                const float kre = upper ? are[H + v] : are[v];
+                const float sim = upper ? aim[v] : aim[H + v];
+                const float kim = upper ? aim[H + v] : aim[v];
+                are[v] = kre + __shfl_xor_sync(0xffffffffu, sre, off);
+                aim[v] = kim + __shfl_xor_sync(0xffffffffu, sim, off);
+            }
+        }
+        // ... and lane bits 1:0 are plain sums (every lane of a quad ends with the full dot product)
+        float sr = are[0], si = aim[0];
+        sr += __shfl_xor_sync(0xffffffffu, sr, 2);
+        si += __shfl_xor_sync(0xffffffffu, si, 2);
+        sr += __shfl_xor_sync(0xffffffffu, sr, 1);
+        si += __shfl_xor_sync(0xffffffffu, si, 1);
+        // de-rotate by the exact LO phase of the output's newest input sample and store
+        if (p_ptr) {
+            float sn, cs;
+            __sincosf(p_ang, &sn, &cs);
+            float2 y;
+            y.x = fmaf(sr, cs, si * sn);                                // (sr + j si)(cos - j sin)
+            y.y = fmaf(si, cs, -sr * sn);
+            *p_ptr = y;
+        }
+    };
+
     unsigned phase_bits = 0;
-    i64 it = 0;
-    for (i64 T = T0; T < g.n_tiles; T += Tstep, ++it) {
-        const int st = (int)(it % K1F_STAGES);
+    // per-tile state advanced incrementally (no 64-bit multiplies / divisions in the loop)
+    const i64 q_start = g.q_first + T0 * S;
+    i64 relb = q_start * down - a.n0;                                    // input index (rel. x[0]) of the tile's first sample
+    i64 ob = q_start * up - a.m0;                                        // output index of the tile's first output
+    u64 pbase = my_acc + my_inc * (u64)relb;                             // LO phase at relb
+    const i64 d_rel = Tstep * S * down, d_ob = Tstep * S * up;
+    const u64 d_ph = my_inc * (u64)d_rel;
+    const int tile_outs = S * up;
+    const int lane_off = need_pad - lane;
+    int st = 0;
+    for (i64 T = T0; T < g.n_tiles; T += Tstep) {
         mbar_wait(smem_u32(&bars[st]), (phase_bits >> st) & 1u);
         phase_bits ^= (1u << st);
         const float2 *xs = stage0 + (size_t)st * K1F_STAGE_ELEMS;
-        const i64 q0 = g.q_first + T * S;
-        i64 a2; int cnt2;
-        tile_a2(T, a2, cnt2);
-        const int shift = (int)((q0 * down - need_pad - a.n0) - a2);     // 0 or 1
-        const i64 ob = q0 * up - a.m0;                                   // output index of the tile's first output
-        const i64 relb = q0 * down - a.n0;                               // input index (rel. x[0]) of its first sample
-        const u64 pbase = my_acc + my_inc * (u64)relb;
+        const int shift = (int)((relb - need_pad + par) & 1);            // tile stored from an even-aligned element
+        const bool tile_full = ob >= 0 && ob + tile_outs <= a.n_out;     // every output of the tile is in range
+        float2 *outp = my_out ? my_out + ob : nullptr;
 
         int i = i_first, sblk = sblk_first;
         for (int t = warp; t < tasks_per_tile; t += K1F_WARPS) {
@@ -190,96 +248,53 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
                     const int rr = g.rx0 + (r ^ sw_r);
                     const float2 *gp = a.g + ((size_t)rr * up + p_i) * a.lp_pad + lane;
 #pragma unroll
-                    for (int k = 0; k < TPL; ++k) {
-                        const float2 v = (rr < a.n_rx) ? __ldg(gp + 32 * k) : make_float2(0.f, 0.f);
-                        tre[r][k] = v.x;
-                        tim[r][k] = v.y;
-                    }
+                    for (int k = 0; k < TPL; ++k) tap[r][k] = (rr < a.n_rx) ? __ldg(gp + 32 * k) : make_float2(0.f, 0.f);
                 }
                 cur_i = i;
             }
-            float are[16], aim[16];
+            reduce_store();                                             // previous task's reduction + store
+            // Packed FP32x2 FMAs (Blackwell FFMA2): A += (g_re,g_im)*(x_re,x_re), B += (g_re,g_im)*(x_im,x_im)
+            //   => re = A.x - B.y, im = A.y + B.x.  One issue slot per two FMAs.
+            float2 A[8], B[8];
 #pragma unroll
-            for (int v = 0; v < 16; ++v) { are[v] = 0.f; aim[v] = 0.f; }
+            for (int v = 0; v < 8; ++v) { A[v] = make_float2(0.f, 0.f); B[v] = make_float2(0.f, 0.f); }
 
 #pragma unroll
             for (int stop = 0; stop < 2; ++stop) {
 #pragma unroll
                 for (int sl = 0; sl < SLOW; ++sl) {
                     const int s_eff = ((stop ^ sw_s) << (SB - 1)) | sl;
-                    const float2 *xp = xs + ((sblk * M + s_eff) * down + o_i + need_pad + shift - lane);
+                    const float2 *xp = xs + ((sblk * M + s_eff) * down + o_i + lane_off + shift);
                     float2 xv[TPL];
 #pragma unroll
                     for (int k = 0; k < TPL; ++k) xv[k] = xp[-32 * k];
 #pragma unroll
                     for (int k = 0; k < TPL; ++k) {
-                        // x-stationary order: each x component feeds 2*NRXP consecutive FMAs
+                        const float2 xrr = make_float2(xv[k].x, xv[k].x), xii = make_float2(xv[k].y, xv[k].y);
 #pragma unroll
                         for (int r = 0; r < NRXP; ++r) {
-                            const int slot = (stop << 3) | (r << (3 - RB)) | sl;
-                            are[slot] = fmaf(tre[r][k], xv[k].x, are[slot]);
+                            const int slot = (stop << 2) | (r << (2 - RB)) | sl;
+                            A[slot] = __ffma2_rn(tap[r][k], xrr, A[slot]);
                         }
 #pragma unroll
                         for (int r = 0; r < NRXP; ++r) {
-                            const int slot = (stop << 3) | (r << (3 - RB)) | sl;
-                            aim[slot] = fmaf(tim[r][k], xv[k].x, aim[slot]);
-                        }
-#pragma unroll
-                        for (int r = 0; r < NRXP; ++r) {
-                            const int slot = (stop << 3) | (r << (3 - RB)) | sl;
-                            aim[slot] = fmaf(tre[r][k], xv[k].y, aim[slot]);
-                        }
-#pragma unroll
-                        for (int r = 0; r < NRXP; ++r) {
-                            const int slot = (stop << 3) | (r << (3 - RB)) | sl;
-                            are[slot] = fmaf(-tim[r][k], xv[k].y, are[slot]);
+                            const int slot = (stop << 2) | (r << (2 - RB)) | sl;
+                            B[slot] = __ffma2_rn(tap[r][k], xii, B[slot]);
                         }
                     }
                 }
             }
-
-            // butterfly over lanes: bit 4 and the RB bits below it are swizzled (no selects) ...
+            // hand this task's partial sums to the software pipeline: they are reduced across lanes, de-rotated and
+            // stored while the NEXT task's FMAs issue (the reduction is latency-bound, the FMA phase pipe-bound)
 #pragma unroll
-            for (int step = 0; step < 1 + RB; ++step) {
-                const int off = 16 >> step;
-                const int H = 8 >> step;                                // slots kept (per array)
-#pragma unroll
-                for (int v = 0; v < H; ++v) {
-                    are[v] += __shfl_xor_sync(0xffffffffu, are[H + v], off);
-                    aim[v] += __shfl_xor_sync(0xffffffffu, aim[H + v], off);
-                }
-            }
-            // ... the remaining low s bits use selects
-#pragma unroll
-            for (int step = 1 + RB; step < 4; ++step) {
-                const int off = 16 >> step;
-                const int H = 8 >> step;
-                const bool upper = (lane & off) != 0;
-#pragma unroll
-                for (int v = 0; v < H; ++v) {
-                    const float sre = upper ? are[v] : are[H + v];
-                    const float kre = upper ? are[H + v] : are[v];
-                    const float sim = upper ? aim[v] : aim[H + v];
-                    const float kim = upper ? aim[H + v] : aim[v];
-                    are[v] = kre + __shfl_xor_sync(0xffffffffu, sre, off);
-                    aim[v] = kim + __shfl_xor_sync(0xffffffffu, sim, off);
-                }
-            }
-            const float sr = are[0] + __shfl_xor_sync(0xffffffffu, are[0], 1);
-            const float si = aim[0] + __shfl_xor_sync(0xffffffffu, aim[0], 1);
-
-            // epilogue: de-rotate by the exact LO phase of the output's newest input sample and store
-            const int qrel = sblk * M + s_log;
-            const i64 oi = ob + (i64)(qrel * up + i);
-            if (my_out && oi >= 0 && oi < a.n_out) {
+            for (int v = 0; v < 8; ++v) { p_re[v] = A[v].x - B[v].y; p_im[v] = A[v].y + B[v].x; }
+            {
+                const int qrel = sblk * M + s_log;
+                const int oidx = qrel * up + i;                          // output index within the tile
+                const bool ok = outp && (tile_full || (ob + oidx >= 0 && ob + oidx < a.n_out));
+                p_ptr = ok ? outp + oidx : nullptr;
                 const u64 ph = pbase + my_inc * (u64)(unsigned)(qrel * down + o_i);
-                const float ang = (float)(int)(ph >> 32) * 1.4629180792671596e-09f;      // 2*pi*2^-32
-                float sn, cs;
-                __sincosf(ang, &sn, &cs);
-                float2 y;
-                y.x = fmaf(sr, cs, si * sn);                            // (sr + j si)(cos - j sin)
-                y.y = fmaf(si, cs, -sr * sn);
-                my_out[oi] = y;
+                p_ang = (float)(int)(ph >> 32) * 1.4629180792671596e-09f;                 // 2*pi*2^-32
             }
             i += di; sblk += ds;
             if (i >= up) { i -= up; sblk += 1; }
@@ -295,7 +310,10 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
         }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) produce(T + (i64)K1F_STAGES * Tstep, st);
+        relb += d_rel; ob += d_ob; pbase += d_ph;
+        st = (st + 1 == K1F_STAGES) ? 0 : st + 1;
     }
+    reduce_store();                                                     // drain the pipeline
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -331,7 +349,7 @@ int k1_fast_supported(int up, int down, int lp, int n_rx) {
     const int tpl = pick_tpl(lp);
     if (tpl < 0) return 0;
     const int nrxp = pick_nrxp(tpl, n_rx);
-    const int M = 16 / nrxp;
+    const int M = 8 / nrxp;
     if (pick_S(down, 32 * tpl, M) < M) return 0;
     if ((i64)up * down > (1 << 30)) return 0;
     return 1;
@@ -372,7 +390,7 @@ int k1_launch_fast(const K1Args &a, cudaStream_t st) {
         return PYSDR_ERR_ARG;
     }
     const int nrxp = pick_nrxp(tpl, a.n_rx);
-    const int M = 16 / nrxp;
+    const int M = 8 / nrxp;
     FastGeom g;
     g.S = pick_S(a.down, a.lp_pad, M);
     g.need_pad = a.lp_pad - 1;
