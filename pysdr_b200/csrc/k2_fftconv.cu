@@ -12,13 +12,13 @@
 
 template <int N>
 __global__ void __launch_bounds__(FftPlan<N>::THREADS)
-taps_fft_kernel(const float2 *__restrict__ taps, int L, float2 *__restrict__ Hpos) {
+taps_fft_kernel(const float2 *__restrict__ taps, int L, float2 *__restrict__ Hpos, const float2 *__restrict__ tw) {
     extern __shared__ __align__(16) float2 s[];
     constexpr int T = FftPlan<N>::THREADS;
     const int tid = threadIdx.x;
     for (int e = tid; e < N; e += T) s[FFT_PAD(e)] = (e < L) ? taps[e] : make_float2(0.f, 0.f);
     __syncthreads();
-    fft_smem<N, false>(s, tid);
+    fft_smem<N, false>(s, tid, tw);
     const float sc = 1.0f / (float)N;                                     // fold the inverse transform's 1/N
     for (int p = tid; p < N; p += T) {
         const float2 v = s[FFT_PAD(p)];
@@ -28,7 +28,7 @@ taps_fft_kernel(const float2 *__restrict__ taps, int L, float2 *__restrict__ Hpo
 
 template <int N>
 __global__ void __launch_bounds__(FftPlan<N>::THREADS)
-af_fftconv_kernel(const FftConvArgs a) {
+af_fftconv_kernel(const FftConvArgs a, const float2 *__restrict__ tw) {
     extern __shared__ __align__(16) float2 s[];
     constexpr int T = FftPlan<N>::THREADS;
     const int tid = threadIdx.x;
@@ -66,7 +66,7 @@ af_fftconv_kernel(const FftConvArgs a) {
         }
     }
     __syncthreads();
-    fft_smem<N, false>(s, tid);
+    fft_smem<N, false>(s, tid, tw);
     {
         const float2 *H = a.H + (size_t)rx * N;
         float2 h[PER];
@@ -79,7 +79,7 @@ af_fftconv_kernel(const FftConvArgs a) {
         }
     }
     __syncthreads();
-    fft_smem<N, true>(s, tid);
+    fft_smem<N, true>(s, tid, tw);
 
     // ---- store the V valid outputs -----------------------------------------------------------------------
     float *out = a.out + (size_t)rx * 2 * a.a_stride;
@@ -110,7 +110,9 @@ template <int N>
 static int taps_fft_launch(const float2 *d_taps, int L, float2 *d_H, cudaStream_t st) {
     const size_t smem = sizeof(float2) * FFT_SMEM_ELEMS(N);
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(taps_fft_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    taps_fft_kernel<N><<<1, FftPlan<N>::THREADS, smem, st>>>(d_taps, L, d_H);
+    const float2 *tw = fft_twiddles(N);
+    if (!tw) { pysdr_set_error("fft twiddle table allocation failed"); return PYSDR_ERR_CUDA; }
+    taps_fft_kernel<N><<<1, FftPlan<N>::THREADS, smem, st>>>(d_taps, L, d_H, tw);
     LAUNCH_CHECK();
     return PYSDR_OK;
 }
@@ -129,7 +131,9 @@ static int fftconv_launch_n(const FftConvArgs &a, int n_rx, cudaStream_t st) {
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(af_fftconv_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int V = N - (a.L - 1);
     dim3 grid((unsigned)((a.n_out + V - 1) / V), (unsigned)n_rx);
-    af_fftconv_kernel<N><<<grid, FftPlan<N>::THREADS, smem, st>>>(a);
+    const float2 *tw = fft_twiddles(N);
+    if (!tw) { pysdr_set_error("fft twiddle table allocation failed"); return PYSDR_ERR_CUDA; }
+    af_fftconv_kernel<N><<<grid, FftPlan<N>::THREADS, smem, st>>>(a, tw);
     LAUNCH_CHECK();
     return PYSDR_OK;
 }

@@ -23,7 +23,7 @@ struct pysdr_psd {
 template <int N, bool CPLX>
 __global__ void __launch_bounds__(FftPlan<N>::THREADS)
 psd_frames_kernel(const void *__restrict__ xv, const float *__restrict__ win, int chunk, int hop, int navg, int n_split,
-                  float *__restrict__ part) {
+                  float *__restrict__ part, const float2 *__restrict__ tw) {
     extern __shared__ __align__(16) float2 s[];
     constexpr int T = FftPlan<N>::THREADS;
     constexpr int PER = (N + T - 1) / T;
@@ -34,21 +34,28 @@ psd_frames_kernel(const void *__restrict__ xv, const float *__restrict__ win, in
     for (int i = 0; i < PER; ++i) acc[i] = 0.f;
     for (int f = split; f < navg; f += n_split) {
         const i64 start = ((i64)line * navg + f) * hop;
-        for (int e = tid; e < N; e += T) {
-            float2 v = make_float2(0.f, 0.f);
-            if (e < chunk) {
-                const float w = __ldg(win + e);
-                if (CPLX) {
-                    const float2 xx = ((const float2 *)xv)[start + e];
-                    v = make_float2(xx.x * w, xx.y * w);
-                } else {
-                    v.x = ((const float *)xv)[start + e] * w;
+        {                                                        // unrolled: all of a thread's loads in flight together
+            float2 xr[PER];
+            float wr[PER];
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int e = tid + i * T;
+                xr[i] = make_float2(0.f, 0.f);
+                wr[i] = 0.f;
+                if (e < chunk && e < N) {
+                    wr[i] = __ldg(win + e);
+                    if (CPLX) xr[i] = ((const float2 *)xv)[start + e];
+                    else xr[i].x = ((const float *)xv)[start + e];
                 }
             }
-            s[FFT_PAD(e)] = v;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int e = tid + i * T;
+                if (e < N) s[FFT_PAD(e)] = make_float2(xr[i].x * wr[i], xr[i].y * wr[i]);
+            }
         }
         __syncthreads();
-        fft_smem<N, false>(s, tid);
+        fft_smem<N, false>(s, tid, tw);
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             const int p = tid + i * T;
@@ -120,11 +127,13 @@ static int psd_launch(pysdr_psd *p, const void *d_x, int is_complex, int navg, i
         CUDA_TRY(cudaFuncSetAttribute(psd_frames_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(psd_frames_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+    const float2 *tw = fft_twiddles(N);
+    if (!tw) { pysdr_set_error("fft twiddle table allocation failed"); return PYSDR_ERR_CUDA; }
     dim3 grid((unsigned)n_split, (unsigned)n_lines);
     if (is_complex)
-        psd_frames_kernel<N, true><<<grid, FftPlan<N>::THREADS, smem, st>>>(d_x, p->d_win, p->chunk, p->hop, navg, n_split, p->d_part);
+        psd_frames_kernel<N, true><<<grid, FftPlan<N>::THREADS, smem, st>>>(d_x, p->d_win, p->chunk, p->hop, navg, n_split, p->d_part, tw);
     else
-        psd_frames_kernel<N, false><<<grid, FftPlan<N>::THREADS, smem, st>>>(d_x, p->d_win, p->chunk, p->hop, navg, n_split, p->d_part);
+        psd_frames_kernel<N, false><<<grid, FftPlan<N>::THREADS, smem, st>>>(d_x, p->d_win, p->chunk, p->hop, navg, n_split, p->d_part, tw);
     LAUNCH_CHECK();
     const float scale = (float)(1.0 / ((double)navg * p->wsum2));
     dim3 g2((unsigned)((N + 255) / 256), (unsigned)n_lines);
