@@ -410,6 +410,8 @@ class demodulator:
         """valid convolution: src has len(g)-1+n samples -> n outputs."""
         g = np.asarray(g)
         gw = g.astype(self.dtype if np.iscomplexobj(g) else self.rdtype)
+        if n == 0:
+            return np.zeros(0, np.result_type(gw.dtype, src.dtype))
         src = src[len(src) - (len(g) - 1 + n):]
         if self.exact or n < 256:
             return np.convolve(src, gw, mode='valid')

@@ -228,6 +228,9 @@ class ReceiverBank:
 
     def process_host(self, x_np, want_dc=True):
         """Host buffers in, host buffers out (the reference-facing call): H2D, kernels, D2H."""
+        if len(x_np) == 0:                                    # nothing in, nothing out (no state change)
+            e = [np.zeros(0, np.complex64 if self._mode_of(r) in ('IQ', 'RTTY') else np.float32) for r in range(self.n_rx)]
+            return e, [np.zeros(0, np.complex64) for _ in range(self.n_rx)], [v.copy() for v in e]
         x = torch.from_numpy(np.ascontiguousarray(x_np, np.complex64)).to(self.device, non_blocking=False)
         am, iq, dc = self.process(x, want_dc=want_dc)
         return [a.cpu().numpy() for a in am], [a.cpu().numpy() for a in iq], [a.cpu().numpy() for a in dc]

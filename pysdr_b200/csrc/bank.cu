@@ -822,6 +822,15 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
         b->launches++;
     }
 
+    if (n_out == 0) {                        // ragged tail too short to emit a sample: only the input memory moves
+        b->pend_n_out = 0; b->pend_m0 = m0; b->pend_B0 = B0; b->pend_blocks = n_blocks;
+        b->pend_peaks = d_peaks;
+        b->pending = true;
+        b->n0 += n_in;
+        if (n_out_p) *n_out_p = 0;
+        if ((rc = mark())) return rc;
+        return PYSDR_OK;
+    }
     const int L = c.af_len;
     const bool use_fft = b->d_H && !b->force_direct_fir;
     if (use_fft) {
@@ -894,6 +903,18 @@ extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks,
     cudaStream_t st = (cudaStream_t)stream;
     const i64 n_out = b->pend_n_out, n_blocks = b->pend_blocks;
     if (n_out > out_stride) { pysdr_set_error("process_back: out_stride too small"); return PYSDR_ERR_CAPACITY; }
+    if (n_out == 0) {                        // nothing was emitted: the AGC does not advance (like the reference's empty am)
+        if (b->timing) {
+            for (int k = 0; k < 2; ++k) {
+                cudaEvent_t e;
+                CUDA_TRY(cudaEventCreate(&e));
+                CUDA_TRY(cudaEventRecord(e, st));
+                b->evs.push_back(e);
+            }
+        }
+        b->pending = false;
+        return PYSDR_OK;
+    }
     AgcScanArgs s;
     s.state = b->d_agc;
     s.peaks = b->pend_peaks; s.peaks_stride = n_blocks;

@@ -1,0 +1,137 @@
+"""Edge cases of the C-ABI path: ragged / tiny inputs, error codes, maximum receiver count, mid-stream retune."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import receiver_oracle as rxo
+from oracle import sig_proc_oracle as odsp
+from tests.util import assert_parity, make_both
+
+pytestmark = pytest.mark.gpu
+
+
+def _noise(n, seed, scale=0.1):
+    rng = np.random.default_rng(seed)
+    return ((rng.normal(size=n) + 1j * rng.normal(size=n)) * scale).astype(np.complex64)
+
+
+def _bank(P, max_in):
+    from pysdr_b200.bank import ReceiverBank
+    from pysdr_b200.receiver import receiver_offsets
+    return ReceiverBank(P, receiver_offsets(P), max_in=max_in)
+
+
+@pytest.mark.parametrize("tail", [1, 2, 167, 499, 500, 501, 100000])
+def test_ragged_last_call(tail):
+    """A capture that does not end on an IN_CHUNK_SIZE boundary: whole chunks, then a short final call."""
+    P, Po = make_both(8, [1000, 1300], ['USB', 'AM'], af_bw_khz=[2, 5])
+    C = P.IN_CHUNK_SIZE
+    x = _noise(2 * C + tail, 3)
+    bank = _bank(P, C)
+    rxo.create_receivers(Po)
+    cuts = [0, C, 2 * C, 2 * C + tail]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        am, iq, _ = bank.process(torch.from_numpy(x[a:b]).cuda())
+        exp = odsp.n_out_total(b, P.UP, P.DOWN) - odsp.n_out_total(a, P.UP, P.DOWN)
+        assert bank.n_out == exp
+        for r in range(2):
+            ref = Po.rx[r].demod_data(x[a:b])
+            assert len(ref) == exp
+            if exp:
+                assert_parity(iq[r].cpu().numpy(), Po.rx[r].iq, "iq rx%d [%d,%d)" % (r, a, b))
+                assert_parity(am[r].cpu().numpy(), ref, "am rx%d [%d,%d)" % (r, a, b))
+    # the stream is now off the block grid: a further call must be refused loudly, not mis-segmented
+    from pysdr_b200._lib import PysdrError
+    if (2 * C + tail) % C:
+        with pytest.raises(PysdrError, match="boundary"):
+            bank.process(torch.from_numpy(x[:C]).cuda())
+
+
+def test_tiny_whole_stream_calls():
+    """Streams shorter than the filters (everything is start-up transient, x[<0] = 0)."""
+    P, Po = make_both(2.048, [1000], ['USB'], af_bw_khz=[2], nfilt=101)
+    for n in (1, 2, 42, 43, 127, 128, 129, 1000):
+        x = _noise(n, n)
+        bank = _bank(P, P.IN_CHUNK_SIZE)
+        am, iq, _ = bank.process(torch.from_numpy(x).cuda())
+        rxo.create_receivers(Po)
+        ref = Po.rx[0].demod_data(x)
+        assert bank.n_out == len(ref) == odsp.n_out_total(n, P.UP, P.DOWN)
+        assert_parity(iq[0].cpu().numpy(), Po.rx[0].iq, "iq n=%d" % n)
+        assert_parity(am[0].cpu().numpy(), ref, "am n=%d" % n, rel_tol=2e-4)
+
+
+def test_error_codes_are_loud():
+    from pysdr_b200._lib import PysdrError
+    from pysdr_b200.bank import ReceiverBank
+    P, _ = make_both(8, [1000], ['USB'])
+    bank = _bank(P, P.IN_CHUNK_SIZE)
+    with pytest.raises(PysdrError, match="exceeds"):
+        bank.process(torch.zeros(P.IN_CHUNK_SIZE + 1, dtype=torch.complex64, device="cuda"))
+    with pytest.raises(PysdrError):
+        bank.process(torch.zeros(16, dtype=torch.complex64))                       # host tensor
+    with pytest.raises(PysdrError):
+        bank.process(torch.zeros(16, dtype=torch.float32, device="cuda"))          # wrong dtype
+    with pytest.raises(PysdrError, match="multiple"):
+        bank.seek(12345)
+    with pytest.raises(PysdrError, match="1..8"):
+        ReceiverBank(P, [0.0] * 9)
+    P.MODE = 'WFM'
+    with pytest.raises(PysdrError, match="WFM"):
+        bank.process(torch.zeros(P.IN_CHUNK_SIZE, dtype=torch.complex64, device="cuda"))
+    import pysdr_b200.sig_proc as dsp
+    with pytest.raises(PysdrError, match="power of two"):
+        dsp.spectrum(8000., 32818, 65636, 0.)                                      # Plotting.py:370-375 geometry
+    sp = dsp.spectrum(48., 4096, 8192, 0.5)
+    assert len(sp.psd_est(np.zeros(100, np.complex64), True)) == 0                 # shorter than one frame -> []
+    rx = dsp.Receiver(make_both(2.048, [1000], ['USB'])[0], 1e5, 0, '1')
+    assert len(rx.demod_data(np.zeros(0, np.complex64))) == 0                      # empty chunk -> empty audio
+
+
+def test_eight_receivers_all_modes():
+    modes = ['AM', 'NFM', 'USB', 'LSB', 'CW', 'IQ', 'AM', 'CW']
+    fcs = [1000 + 150 * i for i in range(8)]
+    from pysdr_b200.params import RUN_TIME_PARAMS
+    from pysdr_b200.bank import ReceiverBank
+    P = RUN_TIME_PARAMS(['-fs', '8', '-fc'] + [str(f) for f in fcs[:6]] + ['-mode'] + modes[:6] + ['-foffset', '100',
+                        '-af_bw', '5', '10', '2', '3', '0.5', '20'])
+    # the reference caps receivers at MAX_RX=6 (params.py:270-276); the bank itself takes 8
+    assert P.NUM_RX == 6
+    P.MODE = modes
+    P.AF_BW = [5e3, 10e3, 2e3, 3e3, 500., 20e3, 5e3, 500.]
+    P.BFO = [0, 0, 0, 0, 700, 0, 0, 600]
+    offs = [P.FOFFSET + (f - fcs[0]) * 1e3 for f in fcs]
+    n = 2 * P.IN_CHUNK_SIZE
+    x = _noise(n, 17)
+    bank = ReceiverBank(P, offs, max_in=n)
+    am, iq, _ = bank.process(torch.from_numpy(x).cuda())
+    Po = rxo.make_P(8e6, [f * 1e3 for f in fcs[:6]], modes[:6], foffset=100e3)
+    Po.MODE, Po.AF_BW, Po.BFO = modes, P.AF_BW, P.BFO
+    for r in range(8):
+        orx = odsp.Receiver(Po, offs[r], r, str(r + 1))
+        ref = np.concatenate([orx.demod_data(x[c * P.IN_CHUNK_SIZE:(c + 1) * P.IN_CHUNK_SIZE]) for c in range(2)])
+        got = am[r].cpu().numpy()
+        assert got.dtype == (np.complex64 if modes[r] == 'IQ' else np.float32)
+        assert_parity(got, ref, "rx%d %s" % (r, modes[r]))
+
+
+def test_retune_and_filter_swap_mid_batch_stream():
+    """lo.change_freq / dec.h swaps between device-resident calls keep phase continuity (oracle semantics:
+    the new LO and taps also apply to the carried raw filter memory)."""
+    P, Po = make_both(8, [1000, 1250], ['USB', 'CW'], af_bw_khz=[2, .5])
+    C = P.IN_CHUNK_SIZE
+    x = _noise(4 * C, 23)
+    bank = _bank(P, 2 * C)
+    rxo.create_receivers(Po)
+    am, _, _ = bank.process(torch.from_numpy(x[:2 * C]).cuda())
+    got = [[a.cpu().numpy().copy()] for a in am]
+    ref = [[Po.rx[r].demod_data(x[c * C:(c + 1) * C]).copy() for c in range(2)] for r in range(2)]
+    f_new = bank.set_freq(1, 271828.1828)
+    assert f_new == Po.rx[1].lo.change_freq(271828.1828)
+    bank.set_dec_taps(0, bank.filter_bank[4])
+    Po.rx[0].dec.h = Po.rx[0].dec.filter_bank[4]
+    am, _, _ = bank.process(torch.from_numpy(x[2 * C:]).cuda())
+    for r in range(2):
+        got[r].append(am[r].cpu().numpy().copy())
+        ref[r] += [Po.rx[r].demod_data(x[c * C:(c + 1) * C]).copy() for c in (2, 3)]
+        assert_parity(np.concatenate(got[r]), np.concatenate(ref[r]), "retuned stream rx%d" % r)
