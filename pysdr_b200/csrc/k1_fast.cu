@@ -259,18 +259,24 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
 #pragma unroll
             for (int v = 0; v < 8; ++v) { A[v] = make_float2(0.f, 0.f); B[v] = make_float2(0.f, 0.f); }
 
+            // tap loop outermost, the M outputs of the task innermost: 2*M*NRXP independent FFMA2 chains per tap
+            const float2 *xp[M];
 #pragma unroll
             for (int stop = 0; stop < 2; ++stop) {
 #pragma unroll
                 for (int sl = 0; sl < SLOW; ++sl) {
                     const int s_eff = ((stop ^ sw_s) << (SB - 1)) | sl;
-                    const float2 *xp = xs + ((sblk * M + s_eff) * down + o_i + lane_off + shift);
-                    float2 xv[TPL];
+                    xp[stop * SLOW + sl] = xs + ((sblk * M + s_eff) * down + o_i + lane_off + shift);
+                }
+            }
 #pragma unroll
-                    for (int k = 0; k < TPL; ++k) xv[k] = xp[-32 * k];
+            for (int k = 0; k < TPL; ++k) {
 #pragma unroll
-                    for (int k = 0; k < TPL; ++k) {
-                        const float2 xrr = make_float2(xv[k].x, xv[k].x), xii = make_float2(xv[k].y, xv[k].y);
+                for (int stop = 0; stop < 2; ++stop) {
+#pragma unroll
+                    for (int sl = 0; sl < SLOW; ++sl) {
+                        const float2 xv = xp[stop * SLOW + sl][-32 * k];
+                        const float2 xrr = make_float2(xv.x, xv.x), xii = make_float2(xv.y, xv.y);
 #pragma unroll
                         for (int r = 0; r < NRXP; ++r) {
                             const int slot = (stop << 2) | (r << (2 - RB)) | sl;
