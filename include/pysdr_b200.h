@@ -152,6 +152,10 @@ int pysdr_lfilter_set_mode(int mode);
 int pysdr_lfilter(const double *b, int nb, const double *a, int na, const float *d_x, float *d_y,
                   int64_t n, int n_ch, int64_t stride, double *d_zi, void *stream);
 
+/* Elementwise helpers of the squelch detector (reference sigs/squelch.m:125-128 |z|, :141 sq1./sq2). */
+int pysdr_abs_f32(const float *d_x, float *d_y, int64_t n, void *stream);
+int pysdr_ratio_f32(const float *d_a, const float *d_b, float *d_r, float floor_v, int64_t n, void *stream);
+
 /* ---- a11: dsp.spectrum(fs,chunk,NFFT,overlap) (reference Plotting.py:376-377,462) --------------- */
 typedef struct pysdr_psd pysdr_psd;
 int pysdr_psd_create(int32_t chunk_size, int32_t nfft, int32_t hop, const float *window_host,

@@ -62,6 +62,8 @@ SIGNATURES = {
     "pysdr_bank_launch_count": (c_i64, [c_vp]),
     "pysdr_lfilter_set_mode": (c_int, [c_int]),
     "pysdr_lfilter": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
+    "pysdr_abs_f32": (c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "pysdr_ratio_f32": (c_int, [c_vp, c_vp, c_vp, ctypes.c_float, c_i64, c_vp]),
     "pysdr_psd_create": (c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_vp, ctypes.POINTER(c_vp)]),
     "pysdr_psd_destroy": (c_int, [c_vp]),
     "pysdr_psd_lines": (c_int, [c_vp, c_vp, c_i64, c_int, ctypes.c_int32, c_int, c_vp, ctypes.POINTER(c_i64), c_vp]),

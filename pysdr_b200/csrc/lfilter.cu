@@ -195,6 +195,37 @@ static int lfilter_run(const double *bn, const double *an, const float *d_x, flo
 static int g_lf_mode = 0;       // 0 auto, 1 force block scan, 2 force sequential
 extern "C" int pysdr_lfilter_set_mode(int mode) { g_lf_mode = mode; return PYSDR_OK; }
 
+// ---- elementwise helpers of the squelch detector (reference sigs/squelch.m:125-128, 141) ------------------
+__global__ void abs_f32_kernel(const float *__restrict__ x, float *__restrict__ y, i64 n) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) y[i] = fabsf(x[i]);
+}
+__global__ void ratio_f32_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ r, float floor_v,
+                                 i64 n) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) r[i] = a[i] / fmaxf(b[i], floor_v);
+}
+extern "C" int pysdr_abs_f32(const float *d_x, float *d_y, int64_t n, void *stream) {
+    if (!d_x || !d_y || n < 0) { pysdr_set_error("abs_f32: bad arguments"); return PYSDR_ERR_ARG; }
+    if (n == 0) return PYSDR_OK;
+    i64 blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    abs_f32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_x, d_y, n);
+    LAUNCH_CHECK();
+    return PYSDR_OK;
+}
+extern "C" int pysdr_ratio_f32(const float *d_a, const float *d_b, float *d_r, float floor_v, int64_t n, void *stream) {
+    if (!d_a || !d_b || !d_r || n < 0) { pysdr_set_error("ratio_f32: bad arguments"); return PYSDR_ERR_ARG; }
+    if (n == 0) return PYSDR_OK;
+    i64 blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    ratio_f32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_a, d_b, d_r, floor_v, n);
+    LAUNCH_CHECK();
+    return PYSDR_OK;
+}
+
 extern "C" int pysdr_lfilter(const double *b, int nb, const double *a, int na, const float *d_x, float *d_y,
                              int64_t n, int n_ch, int64_t stride, double *d_zi, void *stream) {
     if (!b || !a || nb < 1 || na < 1 || a[0] == 0.0 || !d_x || !d_y || n < 0 || n_ch < 1 || !d_zi) {

@@ -1,0 +1,66 @@
+"""Compute part of the reference's ``three_box_plot`` (Plotting.py:312-434 ctor, :444-631 plot) without Qt:
+PSD of the newest samples, waterfall shift-in / roll on retune, background level, peak picking and the
+dynamic-range clipped image.  The PSD and the NFFT x 100 waterfall live on the device (K3, pysdr_waterfall_push);
+only the peak picker runs on the host, on the NFFT-long row-mean vector, with the same scipy call as the reference
+(Plotting.py:594)."""
+import ctypes
+
+import numpy as np
+import torch
+from scipy import signal
+
+from . import _lib, sig_proc as dsp
+from ._lib import check
+from .bank import _stream_ptr
+
+
+class three_box_compute:
+    def __init__(self, P, fs, foff, chunk_size, Nfft, overlap, ncols=100):
+        self.P = P
+        self.foff = foff
+        self.fc = 0
+        if chunk_size > 65536:                                   # Plotting.py:370-375 (the reference's own workaround)
+            chunk_size = int(65636 / 2)
+            Nfft = 2 * chunk_size
+        self.psd = dsp.spectrum(fs, chunk_size, Nfft, overlap)
+        n = self.psd.NFFT
+        self.lib = _lib.load()
+        dev = self.psd.device
+        self.ncols = ncols
+        self.wf = torch.full((n, ncols), -1e38, dtype=torch.float32, device=dev)       # Plotting.py:385
+        self.img = torch.empty((n, ncols), dtype=torch.float32, device=dev)
+        self.bk = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.scratch = torch.empty(n * ncols + n + 8, dtype=torch.float32, device=dev)
+        self.wf_cnt = 0
+        self.wf_fc = 0
+        self.pk_frqs = np.zeros(0)
+
+    def plot(self, y, fc):
+        """One display frame (Plotting.py:444-631): returns dict(frq, PSD, image, bkgnd, peaks, pk_frqs)
+        or None when the periodogram fails (Plotting.py:463-465)."""
+        P = self.P
+        PSD = self.psd.periodogram(y, True)                      # Plotting.py:462
+        if len(PSD) == 0:
+            return None
+        frq = self.psd.frq - self.foff + fc                      # Plotting.py:467
+        self.fc = fc - self.foff
+        df = self.psd.frq[1] - self.psd.frq[0]                   # shift_waterfall, Plotting.py:689-695
+        nbins = int(float(fc - self.wf_fc) / df + 0.5)
+        if nbins != 0:
+            self.wf_fc = fc
+        if getattr(P, 'RIG_IF', 0) < 0:                          # Plotting.py:538-539
+            PSD = np.flipud(PSD)
+        if self.wf_cnt < self.ncols:
+            self.wf_cnt += 1
+        n = self.psd.NFFT
+        line = torch.from_numpy(np.ascontiguousarray(PSD, np.float32)).to(self.wf.device)
+        check(self.lib.pysdr_waterfall_push(ctypes.c_void_p(self.wf.data_ptr()), n, self.ncols, self.wf_cnt,
+                                            ctypes.c_void_p(line.data_ptr()), len(PSD), nbins, float(P.PAN_DR),
+                                            ctypes.c_void_p(self.img.data_ptr()), ctypes.c_void_p(self.bk.data_ptr()),
+                                            ctypes.c_void_p(self.scratch.data_ptr()), _stream_ptr()))
+        bkgnd = float(self.bk.item())
+        PSD2 = self.scratch[n * self.ncols:n * self.ncols + n].cpu().numpy()            # row means over the last wf_cnt lines
+        dist = P.PEAK_DIST / self.psd.df
+        peaks, _ = signal.find_peaks(PSD2, distance=dist, height=bkgnd + 10)            # Plotting.py:594
+        self.pk_frqs = frq[peaks]
+        return dict(frq=frq, PSD=PSD, image=self.img[:len(PSD)], bkgnd=bkgnd, peaks=peaks, pk_frqs=self.pk_frqs)

@@ -353,3 +353,75 @@ class ring_buffer3(ring_buffer2):
         while not self.buf.empty():
             self.push(self.buf.get())
         return super().pull(n, flush)
+
+
+# ---------------------------------------------------------------------------------------------------
+class lfilter_stream:
+    """``scipy.signal.lfilter(b, a, x, zi=z)`` with the state carried between calls, on the device
+    (reference sigs/iir.py:90-105: ``y1,z1 = lfilter(b,a,x1,zi=zi); y2,z2 = lfilter(b,a,x2,zi=z1)``).
+    Block-parallel linear scan in float64 (pysdr_lfilter); ``.z`` is scipy's ``zi`` vector."""
+
+    def __init__(self, b, a, n_ch=1):
+        self.lib = _lib.load()
+        self.b = np.ascontiguousarray(np.atleast_1d(b), np.float64)
+        self.a = np.ascontiguousarray(np.atleast_1d(a), np.float64)
+        self.order = max(len(self.a), len(self.b)) - 1
+        self.n_ch = int(n_ch)
+        self.device = _dev()
+        self.reset()
+
+    def reset(self):
+        self._z = torch.zeros((self.n_ch, max(1, self.order)), dtype=torch.float64, device=self.device)
+
+    @property
+    def z(self):
+        return self._z.cpu().numpy()[:, :self.order]
+
+    def run_dev(self, xd):
+        """xd: float32 CUDA tensor [n] or [n_ch, n] (contiguous) -> same shape."""
+        x2 = xd.reshape(self.n_ch, -1).contiguous()
+        n = x2.shape[1]
+        y = torch.empty_like(x2)
+        if self.order == 0:
+            return (x2 * float(self.b[0] / self.a[0])).reshape(xd.shape)
+        check(self.lib.pysdr_lfilter(self.b.ctypes.data_as(ctypes.c_void_p), len(self.b),
+                                     self.a.ctypes.data_as(ctypes.c_void_p), len(self.a),
+                                     ctypes.c_void_p(x2.data_ptr()), ctypes.c_void_p(y.data_ptr()), n, self.n_ch, n,
+                                     ctypes.c_void_p(self._z.data_ptr()), _stream_ptr()))
+        return y.reshape(xd.shape)
+
+    def run(self, x):
+        xd = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(self.device)
+        return self.run_dev(xd).cpu().numpy()
+
+
+class squelch:
+    """Noise squelch of reference sigs/squelch.m:92-145: the audio is split by an elliptic low-pass (3 kHz) and
+    high-pass (4 kHz) (:103-105), each band's envelope is smoothed by ``filter(alpha,[1 alpha-1],|z|)``, alpha=.001
+    (:125-128), and the squelch opens when the in-band / out-of-band ratio ``sq1./sq2`` (:141) exceeds ``thresh``.
+    All four recursions are block-parallel scans with carried state."""
+
+    def __init__(self, fs, alpha=0.001, thresh=2.0):
+        from scipy import signal as _sig
+        self.lib = _lib.load()
+        B1, A1 = _sig.ellip(5, 5, 40, 3000 / (fs / 2.0))
+        B2, A2 = _sig.ellip(5, 5, 40, 4000 / (fs / 2.0), 'high')
+        self.f1, self.f2 = lfilter_stream(B1, A1), lfilter_stream(B2, A2)
+        self.s1, self.s2 = lfilter_stream([alpha], [1, alpha - 1]), lfilter_stream([alpha], [1, alpha - 1])
+        self.thresh = thresh
+        self.device = _dev()
+
+    def _env(self, filt, smooth, yd):
+        z = filt.run_dev(yd)
+        check(self.lib.pysdr_abs_f32(ctypes.c_void_p(z.data_ptr()), ctypes.c_void_p(z.data_ptr()), z.numel(), _stream_ptr()))
+        return smooth.run_dev(z)
+
+    def run(self, y):
+        """y: real audio chunk (host) -> (ratio, open) arrays."""
+        yd = torch.from_numpy(np.ascontiguousarray(y, np.float32)).to(self.device)
+        sq1, sq2 = self._env(self.f1, self.s1, yd), self._env(self.f2, self.s2, yd)
+        r = torch.empty_like(sq1)
+        check(self.lib.pysdr_ratio_f32(ctypes.c_void_p(sq1.data_ptr()), ctypes.c_void_p(sq2.data_ptr()),
+                                       ctypes.c_void_p(r.data_ptr()), 1e-30, r.numel(), _stream_ptr()))
+        ratio = r.cpu().numpy()
+        return ratio, ratio > self.thresh

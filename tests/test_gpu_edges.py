@@ -135,3 +135,54 @@ def test_retune_and_filter_swap_mid_batch_stream():
         got[r].append(am[r].cpu().numpy().copy())
         ref[r] += [Po.rx[r].demod_data(x[c * C:(c + 1) * C]).copy() for c in (2, 3)]
         assert_parity(np.concatenate(got[r]), np.concatenate(ref[r]), "retuned stream rx%d" % r)
+
+
+def test_lfilter_stream_and_squelch_classes():
+    import pysdr_b200.sig_proc as dsp
+    from scipy import signal
+    rng = np.random.default_rng(9)
+    b, a = signal.butter(3, 0.05)
+    x = rng.normal(size=30000).astype(np.float32)
+    f = dsp.lfilter_stream(b, a)
+    y = np.concatenate([f.run(x[:7000]), f.run(x[7000:7001]), f.run(x[7001:])])
+    ref, zref = signal.lfilter(b, a, x.astype(np.float64), zi=np.zeros(3))
+    assert_parity(y, ref, "lfilter_stream")
+    np.testing.assert_allclose(f.z[0], zref, rtol=1e-6, atol=1e-9)
+    n = np.arange(48000)
+    for tone, expect_open in ((1000.0, True), (8000.0, False)):
+        sig = np.sin(2 * np.pi * tone * n / 48000).astype(np.float32)
+        sq, so = dsp.squelch(48000), odsp.squelch(48000)
+        r1, o1 = [], []
+        for c in range(0, len(sig), 12000):
+            r, o = sq.run(sig[c:c + 12000])
+            r1.append(r); o1.append(o)
+        rr, oo = so.run(sig.astype(np.float64))
+        r1 = np.concatenate(r1)
+        assert bool(np.concatenate(o1)[-1]) == bool(oo[-1]) == expect_open
+        np.testing.assert_allclose(r1[2000:], rr[2000:], rtol=2e-3)      # ratio of two small envelopes: float32 I/O
+
+
+def test_three_box_compute_matches_plotting_py_algebra():
+    from pysdr_b200.plotting import three_box_compute
+    from pysdr_b200.params import RUN_TIME_PARAMS
+    P = RUN_TIME_PARAMS(['-fs', '2.048', '-fc', '1000', '-mode', 'USB'])
+    P.PEAK_DIST = 2.0                                             # kHz units of the AF panel (fs given in kHz)
+    tb = three_box_compute(P, 48., 0, 1024, 2048, 0.5)
+    so = odsp.spectrum(48., 1024, 2048, 0.5)
+    ws = odsp.waterfall_state(2048, so.df, 100, pan_dr=P.PAN_DR, peak_dist=P.PEAK_DIST)
+    rng = np.random.default_rng(10)
+    t = np.arange(512 * 12)
+    x = (0.2 * np.exp(2j * np.pi * 0.11 * t) + 0.01 * (rng.normal(size=len(t)) + 1j * rng.normal(size=len(t)))).astype(np.complex64)
+    for k in range(12):
+        fc = 0.0 if k < 8 else 3.0                                # retune -> waterfall roll (Plotting.py:689-695)
+        seg = x[k * 512:(k + 1) * 512]
+        out = tb.plot(seg, fc)
+        PSDo = so.periodogram(seg, True)
+        img_ref, bk_ref, pk_ref = ws.push(PSDo, fc)
+        top = PSDo > PSDo.max() - 60
+        assert np.max(np.abs(out['PSD'] - PSDo)[top]) < 2e-3
+        assert abs(out['bkgnd'] - bk_ref) <= 2e-3 + 1e-5 * abs(bk_ref)
+        if k >= 2:
+            assert len(out['peaks']) >= 1 and abs(int(out['peaks'][np.argmax(out['PSD'][out['peaks']])]) -
+                                                  int(pk_ref[np.argmax(PSDo[pk_ref])])) <= 1
+        np.testing.assert_allclose(out['image'].cpu().numpy(), img_ref, rtol=0, atol=5e-2)
