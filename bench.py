@@ -175,7 +175,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": 4, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -355,13 +355,30 @@ def run_own(args):
                        "l2": "input per step (%.2f GB) exceeds L2; no flush needed" % (n * 8 / 1e9),
                        "timed_region": "inputs resident in HBM; CUDA events on the launch stream; max over ranks"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter) was diverted."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)                 # keep the driver-facing stdout for the JSON line only
+    os.dup2(2, 1)                            # anything else printed to fd 1 (e.g. "NCCL version ...") goes to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
