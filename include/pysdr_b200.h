@@ -26,7 +26,8 @@ enum {
     PYSDR_MODE_LSB = 2,
     PYSDR_MODE_CW = 3,
     PYSDR_MODE_IQ = 4,          /* also RTTY (IQ feed, receiver.py:286-290) */
-    PYSDR_MODE_NFM = 5
+    PYSDR_MODE_NFM = 5,
+    PYSDR_MODE_RAW = 6          /* Re{resampler output}, no demod filter: second stage of WFM (gui.py:1703,1759-1762) */
 };
 
 enum {
@@ -134,6 +135,12 @@ int pysdr_bank_set_state(pysdr_bank *b, const void *host_blob, int64_t size, voi
 /* Which K1 variant the next process() will use: 0 generic, 1 tap-stationary fast path. */
 int pysdr_bank_k1_variant(const pysdr_bank *b);
 int pysdr_bank_force_generic(pysdr_bank *b, int on);
+/* K1-only bank (WFM video stage: LO + FIR at the RF rate, UP = DOWN = 1): process() stops after K1 and only d_iq_bb
+ * is produced. */
+int pysdr_bank_set_k1_only(pysdr_bank *b, int on);
+/* 3-point FM discriminator at any rate (reference sigs/nfm.m:123-127) with two carried samples:
+ * out[n] = (Im(conj(y[n-1]) * (y[n] - y[n-2])), 0) as complex64; d_prev2: complex64[2] in/out. */
+int pysdr_fm_disc(const void *d_y, int64_t n, void *d_prev2, void *d_out, void *stream);
 /* AF filter variant: default = overlap-save FFT convolution in shared memory; on != 0 forces the direct-form FIR. */
 int pysdr_bank_force_direct_fir(pysdr_bank *b, int on);
 /* On-stream stage timing for bench.py's roofline: out4 = {sum K1 ms, sum rest-of-front ms, sum back ms,

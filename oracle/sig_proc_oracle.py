@@ -559,9 +559,56 @@ class Receiver:
     def _mode(self):
         return per_rx(self.P.MODE, self.irx)
 
+    # ---- WFM / WFM2: "BCB FM is wideband so we need to demodulate first before resampling" (reference
+    # gui.py:1703): video FIR at the RF rate (demod.wfm_video.h = demod.wfm_filter_bank[idx], gui.py:1704) ->
+    # FM discriminator at the RF rate -> resampler whose filter is chosen by the AF bandwidth ("the audio
+    # filtering is done in the resampler", gui.py:1759-1762) -> AGC.
+    # OPEN CHOICES: video FIR = firwin(FILT_LEN, VIDEO_BW/2, fs=SRATE); discriminator = the 3-point form of
+    # sigs/nfm.m:123-127; resampler low-pass cutoff = AF_BW (15 kHz when AF_BW is 0 / 'Max'), gain UP; optional
+    # one-pole de-emphasis P.DEEMPH_US (0 = off).  Mono only: stereo pilot recovery has no in-tree specification.
+    def _wfm_setup(self):
+        P = self.P
+        self.demod.wfm_filter_bank = [design_lowpass(P.FILT_LEN, min(0.5 * (bw_label_to_hz(lb) or P.VIDEO_BW), 0.45 * P.SRATE),
+                                                     P.SRATE) for lb in VIDEO_BWs]
+        self.demod.wfm_video.h = self.demod.wfm_filter_bank[_video_index(P)]
+        self.wfm_vid = decimator(P.SRATE, 1, 1, P.FILT_LEN, VIDEO_BWs, P.VIDEO_BW, self.dtype)
+        self.wfm_res = decimator(P.SRATE, P.UP, P.DOWN, P.FILT_LEN, VIDEO_BWs, P.VIDEO_BW, self.dtype)
+        self.wfm_prev2 = np.zeros(2, self.dtype)
+        self.wfm_deemph = None
+
+    def _demod_wfm(self, x):
+        P = self.P
+        if not hasattr(self, 'wfm_vid'):
+            self._wfm_setup()
+        self.wfm_vid.h = self.demod.wfm_video.h
+        y = self.wfm_vid.resamp(x, self.lo)                          # video-filtered baseband at SRATE
+        yy = np.concatenate((self.wfm_prev2, y))
+        d = yy[2:] - yy[:-2]
+        y1 = yy[1:-1]
+        fm = y1.real * d.imag - y1.imag * d.real                     # sigs/nfm.m:124-126, one sample of latency
+        self.wfm_prev2 = yy[len(yy) - 2:]
+        af_bw = per_rx(getattr(P, 'AF_BW', 0), self.irx) or 15e3
+        key = float(af_bw)
+        if getattr(self, '_wfm_res_key', None) != key:
+            self.wfm_res.h = design_lowpass(P.FILT_LEN, af_bw, P.SRATE * P.UP, gain=P.UP)
+            self._wfm_res_key = key
+        z = self.wfm_res.resamp(fm.astype(self.dtype), None)
+        self.iq = np.asarray(z, np.complex64)
+        a = self.agc.run(z.real)
+        tau = getattr(P, 'DEEMPH_US', 0) * 1e-6
+        if tau > 0:                                                  # OPEN CHOICE: de-emphasis after the block AGC
+            if self.wfm_deemph is None:
+                al = 1.0 - math.exp(-1.0 / (P.FS_OUT * tau))
+                self.wfm_deemph = iir_stream([al], [1, al - 1])
+            a = self.wfm_deemph.run(np.asarray(a, np.float32))       # the AGC output is float32 at the API surface
+        self.am = np.asarray(a, np.float32)
+        return self.am
+
     def demod_data(self, x):
         P = self.P
         x = np.asarray(x)
+        if self._mode() in ('WFM', 'WFM2'):
+            return self._demod_wfm(x)
         iq = self.dec.resamp_fast(x, self.lo) if self.fast else self.dec.resamp(x, self.lo)
         mode = self._mode()
         a = self.demod.demod(iq, mode, _af_index(P, self.irx), per_rx(getattr(P, 'BFO', 0), self.irx))

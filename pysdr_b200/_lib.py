@@ -58,6 +58,8 @@ SIGNATURES = {
     "pysdr_bank_set_state": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "pysdr_bank_k1_variant": (c_int, [c_vp]),
     "pysdr_bank_force_generic": (c_int, [c_vp, c_int]),
+    "pysdr_bank_set_k1_only": (c_int, [c_vp, c_int]),
+    "pysdr_fm_disc": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "pysdr_bank_force_direct_fir": (c_int, [c_vp, c_int]),
     "pysdr_bank_launch_count": (c_i64, [c_vp]),
     "pysdr_lfilter_set_mode": (c_int, [c_int]),

@@ -103,6 +103,10 @@ class ReceiverBank:
             if not force and key == self._demod_key[r]:
                 continue
             mid = design.MODE_IDS[mode]
+            if mode == 'RAW':
+                check(self.lib.pysdr_bank_set_demod(self.h, r, mid, None, 0, 0, ctypes.c_uint64(0)))
+                self._demod_key[r] = key
+                continue
             if mode in ('USB', 'SSB', 'LSB'):
                 g = self.filter_bank_cmpx[idx]
                 if mode == 'LSB':

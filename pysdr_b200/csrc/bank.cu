@@ -476,6 +476,7 @@ struct pysdr_bank {
     // device
     bool h_dirty[PYSDR_MAX_RX];             // AF taps changed: their position-order FFT must be refreshed
     bool force_direct_fir;                  // testing: use the direct-form AF FIR instead of the FFT path
+    bool k1_only;                           // WFM video stage: stop after K1
     float2 *d_H;                            // [n_rx][Nfft] FFT of AF taps (position order, 1/N folded in)
     float2 *d_hist, *d_g, *d_C, *d_af;
     float2 *d_a;                            // pre-AGC audio, rows of a_stride float2 (IQ mode fills complex)
@@ -557,6 +558,7 @@ extern "C" int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out)
     b->g_dirty = true;
     b->force_generic = false;
     b->force_direct_fir = false;
+    b->k1_only = false;
     b->timing = false;
     b->launches = 0;
     b->pending = false;
@@ -618,6 +620,10 @@ extern "C" int pysdr_bank_set_dec_taps(pysdr_bank *b, int rx, const float *h, in
 extern "C" int pysdr_bank_set_demod(pysdr_bank *b, int rx, int mode, const float *taps, int n, int is_complex,
                                     uint64_t bfo_inc) {
     CHECK_RX(b, rx);
+    if (mode == PYSDR_MODE_RAW) {                     // no demod filter: Re{resampler output} goes straight to the AGC
+        b->mode[rx] = mode; b->af_cplx[rx] = 0; b->bfo_inc[rx] = 0; b->demod_set[rx] = true;
+        return PYSDR_OK;
+    }
     if (mode < PYSDR_MODE_AM || mode > PYSDR_MODE_NFM || !taps || n != b->cfg.af_len) {
         pysdr_set_error("set_demod: mode=%d n=%d (af_len=%d)", mode, n, b->cfg.af_len);
         return PYSDR_ERR_ARG;
@@ -683,6 +689,50 @@ extern "C" int pysdr_bank_force_direct_fir(pysdr_bank *b, int on) {
     b->force_direct_fir = on != 0;
     return PYSDR_OK;
 }
+extern "C" int pysdr_bank_set_k1_only(pysdr_bank *b, int on) {
+    if (!b) return PYSDR_ERR_ARG;
+    b->k1_only = on != 0;
+    return PYSDR_OK;
+}
+
+// 3-point FM discriminator (reference sigs/nfm.m:123-127) at any rate, two carried samples.
+__global__ void fm_disc_kernel(const float2 *__restrict__ y, i64 n, const float2 *__restrict__ prev2, float2 *__restrict__ out) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const float2 c2 = y[i];
+        const float2 c1 = i >= 1 ? y[i - 1] : prev2[1];
+        const float2 c0 = i >= 2 ? y[i - 2] : prev2[i];       // i==0 -> prev2[0], i==1 -> prev2[1]
+        const float dr = c2.x - c0.x, di = c2.y - c0.y;
+        out[i] = make_float2(c1.x * di - c1.y * dr, 0.f);
+    }
+}
+__global__ void fm_disc_tail_kernel(const float2 *__restrict__ y, i64 n, float2 *prev2) {
+    // new carried samples = the last two of [prev2 | y]
+    const float2 a = n >= 2 ? y[n - 2] : (n == 1 ? prev2[1] : prev2[0]);
+    const float2 b = n >= 1 ? y[n - 1] : prev2[1];
+    prev2[0] = a;
+    prev2[1] = b;
+}
+extern "C" int pysdr_fm_disc(const void *d_y, int64_t n, void *d_prev2, void *d_out, void *stream) {
+    if (!d_y || !d_prev2 || !d_out || n < 0) { pysdr_set_error("fm_disc: bad arguments"); return PYSDR_ERR_ARG; }
+    if (n == 0) return PYSDR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    i64 blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    fm_disc_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float2 *)d_y, n, (const float2 *)d_prev2, (float2 *)d_out);
+    LAUNCH_CHECK();
+    fm_disc_tail_kernel<<<1, 1, 0, st>>>((const float2 *)d_y, n, (float2 *)d_prev2);
+    LAUNCH_CHECK();
+    return PYSDR_OK;
+}
+
+__global__ void real_part_kernel(const float2 *__restrict__ c, float *__restrict__ a, i64 n) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) a[i] = c[i].x;
+}
+
 extern "C" int pysdr_bank_force_generic(pysdr_bank *b, int on) {
     if (!b) return PYSDR_ERR_ARG;
     b->force_generic = on != 0;
@@ -773,7 +823,7 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
         return PYSDR_ERR_ALIGN;
     }
     for (int r = 0; r < c.n_rx; ++r)
-        if (!b->demod_set[r]) { pysdr_set_error("receiver %d has no demodulator (set_demod)", r); return PYSDR_ERR_STATE; }
+        if (!b->demod_set[r] && !b->k1_only) { pysdr_set_error("receiver %d has no demodulator (set_demod)", r); return PYSDR_ERR_STATE; }
     if (b->g_dirty) { int rc = upload_folded_taps(b, st); if (rc) return rc; }
 
     const i64 m0 = n_out_total(b->n0, c.up, c.down);
@@ -822,12 +872,13 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
         b->launches++;
     }
 
-    if (n_out == 0) {                        // ragged tail too short to emit a sample: only the input memory moves
+    if (n_out == 0 || b->k1_only) {          // ragged tail too short to emit a sample (only the input memory moves),
+                                             // or a K1-only bank (WFM video stage): no audio-rate stages
         b->pend_n_out = 0; b->pend_m0 = m0; b->pend_B0 = B0; b->pend_blocks = n_blocks;
         b->pend_peaks = d_peaks;
         b->pending = true;
         b->n0 += n_in;
-        if (n_out_p) *n_out_p = 0;
+        if (n_out_p) *n_out_p = n_out;
         if ((rc = mark())) return rc;
         return PYSDR_OK;
     }
@@ -856,7 +907,14 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
         float *R = b->d_R + (size_t)r * b->r_stride;
         float *aout = (float *)(b->d_a + (size_t)r * b->a_stride);
         const int mode = b->mode[r];
-        if (use_fft) {
+        if (mode == PYSDR_MODE_RAW) {                 // WFM second stage: a = Re{resampler output}
+            i64 blocks = (n_out + 255) / 256;
+            if (blocks > 148 * 8) blocks = 148 * 8;
+            real_part_kernel<<<(unsigned)blocks, 256, 0, st>>>(C + b->hc, aout, n_out);
+            LAUNCH_CHECK();
+            b->launches++;
+            rc = PYSDR_OK;
+        } else if (use_fft) {
             rc = PYSDR_OK;
         } else if (mode == PYSDR_MODE_AM || mode == PYSDR_MODE_NFM) {
             const i64 nr = (L - 1) + n_out;

@@ -34,6 +34,7 @@ af_fftconv_kernel(const FftConvArgs a, const float2 *__restrict__ tw) {
     const int tid = threadIdx.x;
     const int rx = blockIdx.y;
     const int mode = a.mode[rx];
+    if (mode == PYSDR_MODE_RAW) return;                                   // no demod filter for this receiver (whole CTA)
     const int L = a.L;
     const int V = N - (L - 1);
     const i64 k0 = (i64)blockIdx.x * V;                                   // first src index of this block

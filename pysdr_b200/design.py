@@ -22,7 +22,8 @@ RTLsrates = [0.25, 1.024, 1.536, 1.792, 1.92, 2.048, 2.16, 2.56, 2.88, 3.2]     
 SDRplaysrates = [0.25, 0.5, 1, 2, 2.048, 3, 4, 5, 6, 7, 8, 9, 10]                              # Tables.py:45
 MAX_RX = 6                                                                                    # params.py:33
 
-MODE_IDS = {"AM": 0, "AM-Synch": 0, "USB": 1, "SSB": 1, "LSB": 2, "CW": 3, "IQ": 4, "RTTY": 4, "NFM": 5}
+MODE_IDS = {"AM": 0, "AM-Synch": 0, "USB": 1, "SSB": 1, "LSB": 2, "CW": 3, "IQ": 4, "RTTY": 4, "NFM": 5,
+            "RAW": 6}       # RAW: internal second stage of the WFM chain (sig_proc._WfmChain)
 
 
 def bw_hz(label):
@@ -165,3 +166,15 @@ def phase_inc_to_freq(inc, fs):
     if inc >= (1 << 63):
         inc -= (1 << 64)
     return inc / 2.0 ** 64 * float(fs)
+
+
+def wfm_video_bank(srate, filt_len, video_bws=VIDEO_BWs, video_bw_other=200e3):
+    """demod.wfm_filter_bank (reference gui.py:1704): video FIRs at the RF rate, cutoff VIDEO_BW/2 ('Max'/'Other'
+    use P.VIDEO_BW)."""
+    return [lowpass(filt_len, min(0.5 * (bw_hz(lb) or video_bw_other), 0.45 * srate), srate) for lb in video_bws]
+
+
+def wfm_resampler_taps(srate, up, filt_len, af_bw):
+    """For WFM the audio filtering is done in the resampler (reference gui.py:1759-1762): low-pass at AF_BW
+    (15 kHz when AF_BW is 0 / 'Max'), designed at SRATE*UP with gain UP."""
+    return lowpass(filt_len, af_bw or 15e3, srate * up, gain=up)

@@ -64,6 +64,8 @@ class _Lo:
         return self._rx._bank.fo[0]
 
     def change_freq(self, f):
+        if self._rx._wfm is not None:
+            self._rx._wfm.vbank.set_freq(0, f)
         return self._rx._bank.set_freq(0, f)
 
 
@@ -100,9 +102,8 @@ class _Demod:
         self.filter_bank_real = b.filter_bank_real      # reference receiver.py:873
         self.filter_bank_cmpx = b.filter_bank_cmpx      # reference receiver.py:874
         self.am_pll = _Pll()
-        self.wfm_video = _Holder()
-        self.wfm_video.h = None
-        self.wfm_filter_bank = []
+        self.wfm_video = _WfmVideo(rx)                                   # reference gui.py:1704
+        self.wfm_filter_bank = design.wfm_video_bank(rx.P.SRATE, rx.P.FILT_LEN, design.VIDEO_BWs, rx.P.VIDEO_BW)
 
 
 class _Agc:
@@ -148,9 +149,22 @@ class Receiver:
         self.iq = np.zeros(0, np.complex64)
         self.am_dc = np.zeros(0, np.float32)
         self.mute_cnt = 0
+        self._wfm = None
         self._pw = torch.zeros(1, dtype=torch.float32, device=self._bank.device)
 
+    def _wfm_chain(self):
+        if self._wfm is None:
+            self._wfm = _WfmChain(self)
+        return self._wfm
+
     def demod_data(self, x):
+        if design.per_rx(self.P.MODE, self.irx) in ('WFM', 'WFM2'):      # demodulate first, then resample (gui.py:1703)
+            if len(x) == 0:
+                self.am, self.iq = np.zeros(0, np.float32), np.zeros(0, np.complex64)
+                return self.am
+            self.am, self.iq = self._wfm_chain().demod(x)
+            self.am_dc = self.am
+            return self.am
         am, iq, dc = self._bank.process_host(x)
         self.am, self.iq, self.am_dc = am[0], iq[0], dc[0]
         return self.am
@@ -425,3 +439,79 @@ class squelch:
                                        ctypes.c_void_p(r.data_ptr()), 1e-30, r.numel(), _stream_ptr()))
         ratio = r.cpu().numpy()
         return ratio, ratio > self.thresh
+
+
+# ---------------------------------------------------------------------------------------------------
+class _NS:
+    pass
+
+
+class _WfmChain:
+    """WFM / WFM2: video FIR at the RF rate -> FM discriminator at the RF rate -> resampler (AF low-pass) -> AGC
+    ("BCB FM is wideband so we need to demodulate first before resampling", reference gui.py:1703,1759-1762).
+    Built from two K1 launches (UP=DOWN=1 video stage, UP/DOWN resampler stage on the real discriminator output)
+    and pysdr_fm_disc; mono (no in-tree specification of the stereo decoder exists)."""
+
+    def __init__(self, rx):
+        P = rx.P
+        self.rx = rx
+        self.lib = _lib.load()
+        vid = _NS()
+        vid.SRATE, vid.UP, vid.DOWN, vid.FS_OUT = P.SRATE, 1, 1, int(P.SRATE)
+        vid.IN_CHUNK_SIZE, vid.FILT_LEN, vid.VIDEO_BW = P.IN_CHUNK_SIZE, P.FILT_LEN, P.VIDEO_BW
+        vid.MODE, vid.AF_BW, vid.AF_FILTER_NUM, vid.BFO, vid.VIDEO_FILTER_NUM = 'RAW', 0, 0, 0, None
+        self.vbank = ReceiverBank(vid, [rx._bank.fo[0]], max_in=int(P.IN_CHUNK_SIZE))
+        check(self.lib.pysdr_bank_set_k1_only(self.vbank.h, 1))
+        self.filter_bank = design.wfm_video_bank(P.SRATE, P.FILT_LEN, design.VIDEO_BWs, P.VIDEO_BW)
+        self.set_video(self.filter_bank[design.video_index(P)])
+        res = _NS()
+        res.SRATE, res.UP, res.DOWN, res.FS_OUT = P.SRATE, P.UP, P.DOWN, P.FS_OUT
+        res.IN_CHUNK_SIZE, res.FILT_LEN, res.VIDEO_BW = P.IN_CHUNK_SIZE, P.FILT_LEN, P.VIDEO_BW
+        res.MODE, res.AF_BW, res.AF_FILTER_NUM, res.BFO, res.VIDEO_FILTER_NUM = 'RAW', 0, 0, 0, None
+        self.rbank = ReceiverBank(res, [0.0], max_in=int(P.IN_CHUNK_SIZE))
+        dev = self.vbank.device
+        self.prev2 = torch.zeros(2, dtype=torch.complex64, device=dev)
+        self.fm = torch.empty(int(P.IN_CHUNK_SIZE), dtype=torch.complex64, device=dev)
+        self._res_key = None
+        self.deemph = None
+
+    def set_video(self, h):
+        self.h = np.asarray(h, np.float32)
+        self.vbank.set_dec_taps(0, self.h)
+
+    def demod(self, x):
+        P, rx = self.rx.P, self.rx
+        n = len(x)
+        xd = torch.from_numpy(np.ascontiguousarray(x, np.complex64)).to(self.vbank.device)
+        _, y, _ = self.vbank.process(xd, want_dc=False)
+        fm = self.fm[:n]
+        check(self.lib.pysdr_fm_disc(ctypes.c_void_p(y[0].data_ptr()), n, ctypes.c_void_p(self.prev2.data_ptr()),
+                                     ctypes.c_void_p(fm.data_ptr()), _stream_ptr()))
+        af_bw = float(design.per_rx(getattr(P, 'AF_BW', 0), rx.irx) or 0)
+        if af_bw != self._res_key:
+            self.rbank.set_dec_taps(0, design.wfm_resampler_taps(P.SRATE, P.UP, P.FILT_LEN, af_bw))
+            self._res_key = af_bw
+        am, iq, _ = self.rbank.process(fm, want_dc=False)
+        a = am[0]
+        tau = getattr(P, 'DEEMPH_US', 0) * 1e-6
+        if tau > 0:                                             # one-pole de-emphasis, block-parallel scan
+            if self.deemph is None:
+                al = 1.0 - np.exp(-1.0 / (P.FS_OUT * tau))
+                self.deemph = lfilter_stream([al], [1, al - 1])
+            a = self.deemph.run_dev(a.contiguous())
+        return a.cpu().numpy(), iq[0].cpu().numpy()
+
+
+class _WfmVideo:
+    """``rx.demod.wfm_video.h = rx.demod.wfm_filter_bank[idx]`` (reference gui.py:1704)."""
+
+    def __init__(self, rx):
+        self._rx = rx
+
+    @property
+    def h(self):
+        return self._rx._wfm_chain().h
+
+    @h.setter
+    def h(self, taps):
+        self._rx._wfm_chain().set_video(taps)

@@ -186,3 +186,32 @@ def test_three_box_compute_matches_plotting_py_algebra():
             assert len(out['peaks']) >= 1 and abs(int(out['peaks'][np.argmax(out['PSD'][out['peaks']])]) -
                                                   int(pk_ref[np.argmax(PSDo[pk_ref])])) <= 1
         np.testing.assert_allclose(out['image'].cpu().numpy(), img_ref, rtol=0, atol=5e-2)
+
+
+@pytest.mark.parametrize("deemph", [0, 75])
+def test_wfm_demod_first_then_resample(deemph):
+    """BASELINE config 4 geometry (2.4 MS/s replay rate, 1/50): WFM chain = video FIR @RF rate -> discriminator ->
+    resampler (AF low-pass) -> AGC (-> de-emphasis), reference gui.py:1703-1704,1759-1762.  Mono."""
+    import pysdr_b200.sig_proc as dsp
+    P, Po = make_both(2.4, [100000], ['WFM'], foffset_khz=100, srate_hz=2.4e6, af_bw_khz=[15])
+    assert (P.UP, P.DOWN, P.IN_CHUNK_SIZE, P.VIDEO_BW) == (1, 50, 51200, 200e3) == (Po.UP, Po.DOWN, Po.IN_CHUNK_SIZE, Po.VIDEO_BW)
+    P.DEEMPH_US = Po.DEEMPH_US = deemph
+    C = P.IN_CHUNK_SIZE
+    n = np.arange(5 * C)
+    ph = 2 * np.pi * P.FOFFSET * n / P.SRATE + (75e3 / 1e3) * np.sin(2 * np.pi * 1e3 * n / P.SRATE) \
+        + (20e3 / 5e3) * np.sin(2 * np.pi * 5e3 * n / P.SRATE)
+    x = (0.3 * np.exp(1j * ph) + _noise(len(n), 4, 0.003)).astype(np.complex64)
+    rx = dsp.Receiver(P, P.FOFFSET, 0, '1')
+    orx = odsp.Receiver(Po, Po.FOFFSET, 0, '1')
+    for c in range(5):
+        if c == 3:                                                  # video filter swap (gui.py:1704) and AF change
+            rx.demod.wfm_video.h = rx.demod.wfm_filter_bank[8]
+            orx._demod_wfm(np.zeros(0, np.complex64)) if not hasattr(orx, 'wfm_vid') else None
+            orx.demod.wfm_video.h = orx.demod.wfm_filter_bank[8]
+            P.AF_BW = Po.AF_BW = 10e3
+        am = rx.demod_data(x[c * C:(c + 1) * C])
+        ref = orx.demod_data(x[c * C:(c + 1) * C])
+        assert am.dtype == np.float32 and len(am) == len(ref) == 1024
+        assert_parity(rx.iq, orx.iq, "wfm resampled chunk %d" % c, rel_tol=2e-4, snr_min=74)
+        assert_parity(am, ref, "wfm audio chunk %d" % c, rel_tol=2e-4, snr_min=74)
+    assert np.max(np.abs(am)) > 0.05                                # a real demodulated tone, not silence
