@@ -21,13 +21,14 @@ extern "C" {
 
 /* demodulator kinds: reference Tables.py:34 MODES */
 enum {
-    PYSDR_MODE_AM = 0,          /* also AM-Synch (envelope)             */
+    PYSDR_MODE_AM = 0,          /* envelope detector                     */
     PYSDR_MODE_USB = 1,         /* also SSB                              */
     PYSDR_MODE_LSB = 2,
     PYSDR_MODE_CW = 3,
     PYSDR_MODE_IQ = 4,          /* also RTTY (IQ feed, receiver.py:286-290) */
     PYSDR_MODE_NFM = 5,
-    PYSDR_MODE_RAW = 6          /* Re{resampler output}, no demod filter: second stage of WFM (gui.py:1703,1759-1762) */
+    PYSDR_MODE_RAW = 6,         /* Re{resampler output}, no demod filter: second stage of WFM (gui.py:1703,1759-1762) */
+    PYSDR_MODE_AMSYNC = 7       /* AM-Synch: carrier PLL, in-phase arm (Tables.py:34; demod.am_pll, receiver.py:649) */
 };
 
 enum {
@@ -83,6 +84,9 @@ int pysdr_bank_set_dec_taps(pysdr_bank *b, int rx, const float *h, int n);
  * interleaved (re,im) pairs when is_complex. */
 int pysdr_bank_set_demod(pysdr_bank *b, int rx, int mode, const float *taps, int n, int is_complex,
                          uint64_t bfo_phase_inc);
+/* rx.demod.am_pll.reset()        reference receiver.py:649 ; loop state out2 = {phi [rad], w [rad/sample]} */
+int pysdr_bank_pll_reset(pysdr_bank *b, int rx);
+int pysdr_bank_pll_get(pysdr_bank *b, int rx, double out2[2], void *stream);
 /* rx.agc.reset()                 reference receiver.py:648 */
 int pysdr_bank_agc_reset(pysdr_bank *b, int rx);
 int pysdr_bank_agc_config(pysdr_bank *b, int rx, double ref, double beta);
@@ -174,6 +178,13 @@ int pysdr_psd_destroy(pysdr_psd *p);
 int pysdr_psd_lines(pysdr_psd *p, const void *d_x, int64_t n, int is_complex, int32_t navg, int dB,
                     float *d_out, int64_t *n_lines, void *stream);
 int64_t pysdr_psd_launch_count(const pysdr_psd *p);
+/* Quarter-symbol FFT filterbank of the RTTY executive (reference rtty.py:784-786,833-843): frame f starts at
+ * (f / sub)*hop + sub_off[f % sub] (hop = samples per symbol N, sub_off = RTTY_Params.NSTART, rtty.py:389-394);
+ * PYSDR_PSD_RAW: |X|^2 without the 1/(navg*sum w^2) normalisation and without the dB floor (rtty.py:841);
+ * PYSDR_PSD_FLIP: line = flipud(fftshift(.)) (rtty.py:843).  sub = 1, flags = 0 restores pysdr_psd_lines' default. */
+#define PYSDR_PSD_RAW 1
+#define PYSDR_PSD_FLIP 2
+int pysdr_psd_configure(pysdr_psd *p, int32_t sub, const int32_t *sub_off, int32_t flags);
 
 /* ---- a12: three_box_plot waterfall compute (reference Plotting.py:536-548,583-587,618-626,689-695)
  * d_wf float32[nfft][ncols] state; shift-in one line, optional roll by nbins, background =

@@ -370,12 +370,43 @@ def design_af_bank_cw(fs_out, ntaps, af_bws=AF_BWs):
     return bank
 
 
+PLL_BN_HZ = 50.0
+PLL_ZETA = 0.70710678118654752440
+
+
 class am_pll:
-    """Placeholder surface for AM-Synch (``demod.am_pll.reset()``, reference receiver.py:649).
-    OPEN CHOICE: AM-Synch falls back to envelope detection in this restatement (no in-tree law)."""
+    """AM-Synch carrier loop (``demod.am_pll.reset()``, reference receiver.py:649).  OPEN CHOICE (no in-tree law):
+    second-order PLL, atan2 phase detector, noise bandwidth 50 Hz, damping 1/sqrt(2), run at the audio rate:
+        v = z e^{-j phi};  e = atan2(Im v, Re v);  w += K2 e;  phi += w + K1 e  (wrapped to [-pi, pi))
+    ``run`` returns v (the detector uses Re v)."""
+
+    def __init__(self, fs):
+        th = PLL_BN_HZ / float(fs) / (PLL_ZETA + 1.0 / (4.0 * PLL_ZETA))
+        d = 1.0 + 2.0 * PLL_ZETA * th + th * th
+        self.k1 = 4.0 * PLL_ZETA * th / d
+        self.k2 = 4.0 * th * th / d
+        self.reset()
 
     def reset(self):
-        pass
+        self.phi = 0.0
+        self.w = 0.0
+
+    def run(self, z):
+        z = np.asarray(z, np.complex128)
+        v = np.empty(len(z), np.complex128)
+        phi, w, k1, k2 = self.phi, self.w, self.k1, self.k2
+        for i in range(len(z)):
+            vi = z[i] * complex(math.cos(phi), -math.sin(phi))
+            v[i] = vi
+            e = math.atan2(vi.imag, vi.real)
+            w += k2 * e
+            phi += w + k1 * e
+            if phi >= math.pi:
+                phi -= 2.0 * math.pi
+            elif phi < -math.pi:
+                phi += 2.0 * math.pi
+        self.phi, self.w = phi, w
+        return v
 
 
 class _holder:
@@ -393,7 +424,7 @@ class demodulator:
         self.filter_bank_real = design_af_bank_real(fs_out, filt_len, af_bws)
         self.filter_bank_cmpx = design_af_bank_cmpx(fs_out, filt_len, af_bws)
         self.filter_bank_lp = design_af_bank_cw(fs_out, filt_len, af_bws)
-        self.am_pll = am_pll()
+        self.am_pll = am_pll(fs_out)
         self.wfm_video = _holder()
         self.wfm_video.h = None
         self.wfm_filter_bank = []
@@ -422,8 +453,12 @@ class demodulator:
         iq = np.asarray(iq).astype(self.dtype)
         n = len(iq)
         m = self.m0 + np.arange(n)
+        if mode == 'AM-Synch':                           # the carried memory then holds DE-ROTATED samples
+            iq = self.am_pll.run(iq).astype(self.dtype)
         xx = np.concatenate((self.hist_c, iq))           # xx[k] <-> output index m0-(L+1)+k
-        if mode in ('AM', 'AM-Synch'):
+        if mode == 'AM-Synch':
+            a = self._fir(self.filter_bank_real[af_idx], xx[2:].real, n)
+        elif mode == 'AM':
             a = self._fir(self.filter_bank_real[af_idx], np.abs(xx[2:]), n)
         elif mode in ('USB', 'SSB', 'LSB'):
             g = self.filter_bank_cmpx[af_idx]

@@ -20,6 +20,9 @@ class PysdrError(RuntimeError):
     pass
 
 
+PSD_RAW, PSD_FLIP = 1, 2          # include/pysdr_b200.h PYSDR_PSD_*
+
+
 class BankConfig(ctypes.Structure):
     _fields_ = [("srate", c_dbl), ("up", ctypes.c_int32), ("down", ctypes.c_int32), ("in_chunk", c_i64),
                 ("n_rx", ctypes.c_int32), ("filt_len", ctypes.c_int32), ("af_len", ctypes.c_int32),
@@ -38,6 +41,8 @@ SIGNATURES = {
     "pysdr_bank_create": (c_int, [ctypes.POINTER(BankConfig), ctypes.POINTER(c_vp)]),
     "pysdr_bank_destroy": (c_int, [c_vp]),
     "pysdr_bank_reset": (c_int, [c_vp]),
+    "pysdr_bank_pll_reset": (c_int, [c_vp, c_int]),
+    "pysdr_bank_pll_get": (c_int, [c_vp, c_int, c_vp, c_vp]),
     "pysdr_bank_set_lo": (c_int, [c_vp, c_int, c_u64]),
     "pysdr_bank_set_dec_taps": (c_int, [c_vp, c_int, c_vp, c_int]),
     "pysdr_bank_set_demod": (c_int, [c_vp, c_int, c_int, c_vp, c_int, c_int, c_u64]),
@@ -70,6 +75,7 @@ SIGNATURES = {
     "pysdr_psd_destroy": (c_int, [c_vp]),
     "pysdr_psd_lines": (c_int, [c_vp, c_vp, c_i64, c_int, ctypes.c_int32, c_int, c_vp, ctypes.POINTER(c_i64), c_vp]),
     "pysdr_psd_launch_count": (c_i64, [c_vp]),
+    "pysdr_psd_configure": (c_int, [c_vp, ctypes.c_int32, c_vp, ctypes.c_int32]),
     "pysdr_waterfall_push": (c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_vp, ctypes.c_int32,
                                      ctypes.c_int32, ctypes.c_float, c_vp, c_vp, c_vp, c_vp]),
 }

@@ -127,6 +127,14 @@ class ReceiverBank:
     def agc_reset(self, rx):
         check(self.lib.pysdr_bank_agc_reset(self.h, rx))
 
+    def pll_reset(self, rx):
+        check(self.lib.pysdr_bank_pll_reset(self.h, rx))
+
+    def pll_get(self, rx):
+        out = (ctypes.c_double * 2)()
+        check(self.lib.pysdr_bank_pll_get(self.h, rx, out, _stream_ptr()))
+        return dict(phi=out[0], w=out[1])
+
     def agc_get(self, rx):
         out = (ctypes.c_double * 5)()
         check(self.lib.pysdr_bank_agc_get(self.h, rx, out, _stream_ptr()))

@@ -84,7 +84,7 @@ extern "C" int pysdr_mean_power(const void *d_x, int64_t n, float *d_out, void *
 // ------------------------------------------------------------------------------------------------
 // K2a: detection over the whole complex memory + new samples.  R[k] for k in [0, L-1+n_out):
 //   AM : |C[k+2]|          NFM: Re(C[k+1])*Im(d) - Im(C[k+1])*Re(d), d = C[k+2]-C[k]   (nfm.m:124-126)
-__global__ void detect_kernel(const float2 *__restrict__ C, float *__restrict__ R, i64 n, int nfm) {
+__global__ void detect_kernel(const float2 *__restrict__ C, float *__restrict__ R, i64 n, int nfm, int sync) {
     i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (; k < n; k += stride) {
@@ -94,6 +94,8 @@ __global__ void detect_kernel(const float2 *__restrict__ C, float *__restrict__ 
             const float2 c0 = C[k], c1 = C[k + 1];
             const float dr = c2.x - c0.x, di = c2.y - c0.y;
             v = c1.x * di - c1.y * dr;
+        } else if (sync) {
+            v = c2.x;                                         // AM-Synch: in-phase arm of the de-rotated memory
         } else {
             v = sqrtf(c2.x * c2.x + c2.y * c2.y);
         }
@@ -482,6 +484,8 @@ struct pysdr_bank {
     float2 *d_a;                            // pre-AGC audio, rows of a_stride float2 (IQ mode fills complex)
     float *d_R, *d_peaks, *d_gains;
     AgcState *d_agc;
+    double2 *d_pll;            // AM-Synch loop state (phi, w) per receiver
+    double pll_k1, pll_k2;
     // pending front->back
     i64 pend_n_out, pend_m0, pend_B0, pend_blocks;
     const float *pend_peaks;
@@ -507,6 +511,7 @@ static int bank_alloc(pysdr_bank *b) {
     CUDA_TRY(cudaMalloc(&b->d_peaks, sizeof(float) * (size_t)c.n_rx * b->max_blocks));
     CUDA_TRY(cudaMalloc(&b->d_gains, sizeof(float) * (size_t)c.n_rx * b->max_blocks));
     CUDA_TRY(cudaMalloc(&b->d_agc, sizeof(AgcState) * PYSDR_MAX_RX));
+    CUDA_TRY(cudaMalloc(&b->d_pll, sizeof(double2) * PYSDR_MAX_RX));
     return PYSDR_OK;
 }
 
@@ -523,6 +528,7 @@ extern "C" int pysdr_bank_reset(pysdr_bank *b) {
     b->pending = false;
     CUDA_TRY(cudaMemset(b->d_hist, 0, sizeof(float2) * (size_t)(b->need + 8)));
     CUDA_TRY(cudaMemset(b->d_C, 0, sizeof(float2) * (size_t)b->cfg.n_rx * b->c_stride));
+    CUDA_TRY(cudaMemset(b->d_pll, 0, sizeof(double2) * PYSDR_MAX_RX));
     AgcState st[PYSDR_MAX_RX];
     AgcState cur[PYSDR_MAX_RX];
     CUDA_TRY(cudaMemcpy(cur, b->d_agc, sizeof(cur), cudaMemcpyDeviceToHost));
@@ -545,6 +551,12 @@ extern "C" int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out)
     b->lp_pad = k1_fast_lp_pad(b->lp);
     b->need = b->lp - 1;
     b->hc = cfg->af_len + 1;
+    {   // AM-Synch loop gains: noise bandwidth 50 Hz, damping 1/sqrt(2) at the audio rate
+        const double fs_out = cfg->srate * cfg->up / cfg->down, zeta = 0.70710678118654752440, bn = 50.0;
+        const double th = bn / fs_out / (zeta + 1.0 / (4.0 * zeta)), d = 1.0 + 2.0 * zeta * th + th * th;
+        b->pll_k1 = 4.0 * zeta * th / d;
+        b->pll_k2 = 4.0 * th * th / d;
+    }
     if (b->need > 4096 || b->hc > 4096) {
         pysdr_set_error("filter memories above 4096 samples are not supported (need=%d hc=%d)", b->need, b->hc);
         delete b;
@@ -586,7 +598,7 @@ extern "C" int pysdr_bank_destroy(pysdr_bank *b) {
     if (!b) return PYSDR_OK;
     cudaFree(b->d_H);
     cudaFree(b->d_hist); cudaFree(b->d_g); cudaFree(b->d_C); cudaFree(b->d_af); cudaFree(b->d_R);
-    cudaFree(b->d_a); cudaFree(b->d_peaks); cudaFree(b->d_gains); cudaFree(b->d_agc);
+    cudaFree(b->d_a); cudaFree(b->d_peaks); cudaFree(b->d_gains); cudaFree(b->d_agc); cudaFree(b->d_pll);
     delete b;
     return PYSDR_OK;
 }
@@ -624,7 +636,7 @@ extern "C" int pysdr_bank_set_demod(pysdr_bank *b, int rx, int mode, const float
         b->mode[rx] = mode; b->af_cplx[rx] = 0; b->bfo_inc[rx] = 0; b->demod_set[rx] = true;
         return PYSDR_OK;
     }
-    if (mode < PYSDR_MODE_AM || mode > PYSDR_MODE_NFM || !taps || n != b->cfg.af_len) {
+    if (mode < PYSDR_MODE_AM || (mode > PYSDR_MODE_NFM && mode != PYSDR_MODE_AMSYNC) || !taps || n != b->cfg.af_len) {
         pysdr_set_error("set_demod: mode=%d n=%d (af_len=%d)", mode, n, b->cfg.af_len);
         return PYSDR_ERR_ARG;
     }
@@ -644,6 +656,20 @@ extern "C" int pysdr_bank_set_demod(pysdr_bank *b, int rx, int mode, const float
     b->bfo_inc[rx] = bfo_inc;
     b->demod_set[rx] = true;
     b->h_dirty[rx] = true;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_pll_reset(pysdr_bank *b, int rx) {
+    CHECK_RX(b, rx);
+    CUDA_TRY(cudaMemset(b->d_pll + rx, 0, sizeof(double2)));
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_pll_get(pysdr_bank *b, int rx, double *out2, void *stream) {
+    CHECK_RX(b, rx);
+    if (!out2) { pysdr_set_error("pll_get: null output"); return PYSDR_ERR_ARG; }
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    CUDA_TRY(cudaMemcpy(out2, b->d_pll + rx, sizeof(double2), cudaMemcpyDeviceToHost));
     return PYSDR_OK;
 }
 
@@ -725,6 +751,46 @@ extern "C" int pysdr_fm_disc(const void *d_y, int64_t n, void *d_prev2, void *d_
     fm_disc_tail_kernel<<<1, 1, 0, st>>>((const float2 *)d_y, n, (float2 *)d_prev2);
     LAUNCH_CHECK();
     return PYSDR_OK;
+}
+
+// AM-Synch carrier PLL (open choice): second-order loop, atan2 phase detector.
+//     v = z e^{-j phi};  e = atan2(Im v, Re v);  w += K2 e;  phi += w + K1 e  (wrapped to [-pi, pi))
+// The new samples of C are replaced by v IN PLACE, so the carried memory holds de-rotated samples and the AF FIR
+// reads Re v.  Inherently serial at the audio rate: one warp per receiver, lane 0 runs the recurrence on a
+// shared-memory tile the whole warp loads and stores.
+struct PllModes { int mode[PYSDR_MAX_RX]; };
+#define PLL_TILE 512
+__global__ void __launch_bounds__(32) am_pll_kernel(float2 *__restrict__ Cbase, i64 c_stride, int hc, i64 n, const PllModes pm,
+                                                    double2 *__restrict__ state, double k1, double k2) {
+    const int rx = blockIdx.x;
+    if (pm.mode[rx] != PYSDR_MODE_AMSYNC) return;
+    __shared__ float2 t[PLL_TILE];
+    float2 *C = Cbase + (size_t)rx * c_stride + hc;
+    double phi = state[rx].x, w = state[rx].y;
+    const double PI = 3.14159265358979323846, TWO_PI = 6.28318530717958647692;
+    for (i64 base = 0; base < n; base += PLL_TILE) {
+        const int cnt = (int)((n - base < PLL_TILE) ? (n - base) : PLL_TILE);
+        for (int i = threadIdx.x; i < cnt; i += 32) t[i] = C[base + i];
+        __syncwarp();
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < cnt; ++i) {
+                float sn, cs;
+                sincosf((float)phi, &sn, &cs);
+                const float2 z = t[i];
+                const float vr = z.x * cs + z.y * sn, vi = z.y * cs - z.x * sn;
+                t[i] = make_float2(vr, vi);
+                const double e = (double)atan2f(vi, vr);
+                w += k2 * e;
+                phi += w + k1 * e;
+                if (phi >= PI) phi -= TWO_PI;
+                else if (phi < -PI) phi += TWO_PI;
+            }
+        }
+        __syncwarp();
+        for (int i = threadIdx.x; i < cnt; i += 32) C[base + i] = t[i];
+        __syncwarp();
+    }
+    if (threadIdx.x == 0) state[rx] = make_double2(phi, w);
 }
 
 __global__ void real_part_kernel(const float2 *__restrict__ c, float *__restrict__ a, i64 n) {
@@ -884,6 +950,16 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
     }
     const int L = c.af_len;
     const bool use_fft = b->d_H && !b->force_direct_fir;
+    {
+        PllModes pm;
+        bool any = false;
+        for (int r = 0; r < PYSDR_MAX_RX; ++r) { pm.mode[r] = b->mode[r]; any = any || (r < c.n_rx && b->mode[r] == PYSDR_MODE_AMSYNC); }
+        if (any) {
+            am_pll_kernel<<<c.n_rx, 32, 0, st>>>(b->d_C, (i64)b->c_stride, b->hc, n_out, pm, b->d_pll, b->pll_k1, b->pll_k2);
+            LAUNCH_CHECK();
+            b->launches++;
+        }
+    }
     if (use_fft) {
         // K2 fast path: fused detection + overlap-save AF filter for all receivers in one launch
         const int nfft = fftconv_n_for(L);
@@ -916,11 +992,11 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
             rc = PYSDR_OK;
         } else if (use_fft) {
             rc = PYSDR_OK;
-        } else if (mode == PYSDR_MODE_AM || mode == PYSDR_MODE_NFM) {
+        } else if (mode == PYSDR_MODE_AM || mode == PYSDR_MODE_NFM || mode == PYSDR_MODE_AMSYNC) {
             const i64 nr = (L - 1) + n_out;
             i64 blocks = (nr + 255) / 256;
             if (blocks > 148 * 8) blocks = 148 * 8;
-            detect_kernel<<<(unsigned)blocks, 256, 0, st>>>(C, R, nr, mode == PYSDR_MODE_NFM);
+            detect_kernel<<<(unsigned)blocks, 256, 0, st>>>(C, R, nr, mode == PYSDR_MODE_NFM, mode == PYSDR_MODE_AMSYNC);
             LAUNCH_CHECK();
             b->launches++;
             rc = launch_fir<0>(b, r, R, n_out, aout, 0, m0, st);
@@ -1081,6 +1157,7 @@ extern "C" int pysdr_bank_seek(pysdr_bank *b, int64_t n0_abs, void *stream) {
     b->n0 = n0_abs;
     b->pending = false;
     CUDA_TRY(cudaMemsetAsync(b->d_hist, 0, sizeof(float2) * (size_t)(b->need + 8), st));
+    CUDA_TRY(cudaMemsetAsync(b->d_pll, 0, sizeof(double2) * PYSDR_MAX_RX, st));
     CUDA_TRY(cudaMemset2DAsync(b->d_C, sizeof(float2) * (size_t)b->c_stride, 0, sizeof(float2) * (size_t)b->hc,
                                (size_t)b->cfg.n_rx, st));
     if (n0_abs == 0) {                       // back at the stream origin: a fresh set of receivers
@@ -1097,6 +1174,7 @@ struct StateHeader {
     int32_t n_rx, need, hc, pad;
     i64 n0;
     u64 inc[PYSDR_MAX_RX], acc0[PYSDR_MAX_RX];
+    double pll[PYSDR_MAX_RX][2];
 };
 
 extern "C" int64_t pysdr_bank_state_size(const pysdr_bank *b) {
@@ -1111,9 +1189,10 @@ extern "C" int pysdr_bank_get_state(pysdr_bank *b, void *blob, int64_t size, voi
     char *p = (char *)blob;
     StateHeader h;
     memset(&h, 0, sizeof(h));
-    h.magic = 0x50534452u; h.version = 1; h.n_rx = b->cfg.n_rx; h.need = b->need; h.hc = b->hc; h.n0 = b->n0;
+    h.magic = 0x50534452u; h.version = 2; h.n_rx = b->cfg.n_rx; h.need = b->need; h.hc = b->hc; h.n0 = b->n0;
     memcpy(h.inc, b->inc, sizeof(h.inc));
     memcpy(h.acc0, b->acc0, sizeof(h.acc0));
+    CUDA_TRY(cudaMemcpy(h.pll, b->d_pll, sizeof(h.pll), cudaMemcpyDeviceToHost));
     memcpy(p, &h, sizeof(h)); p += sizeof(h);
     CUDA_TRY(cudaMemcpy(p, b->d_agc, sizeof(AgcState) * PYSDR_MAX_RX, cudaMemcpyDeviceToHost)); p += sizeof(AgcState) * PYSDR_MAX_RX;
     if (b->need) CUDA_TRY(cudaMemcpy(p, b->d_hist, sizeof(float2) * (size_t)b->need, cudaMemcpyDeviceToHost));
@@ -1131,13 +1210,14 @@ extern "C" int pysdr_bank_set_state(pysdr_bank *b, const void *blob, int64_t siz
     const char *p = (const char *)blob;
     StateHeader h;
     memcpy(&h, p, sizeof(h)); p += sizeof(h);
-    if (h.magic != 0x50534452u || h.version != 1 || h.n_rx != b->cfg.n_rx || h.need != b->need || h.hc != b->hc) {
+    if (h.magic != 0x50534452u || h.version != 2 || h.n_rx != b->cfg.n_rx || h.need != b->need || h.hc != b->hc) {
         pysdr_set_error("set_state: blob does not match this bank's geometry");
         return PYSDR_ERR_STATE;
     }
     b->n0 = h.n0;
     memcpy(b->inc, h.inc, sizeof(h.inc));
     memcpy(b->acc0, h.acc0, sizeof(h.acc0));
+    CUDA_TRY(cudaMemcpy(b->d_pll, h.pll, sizeof(h.pll), cudaMemcpyHostToDevice));
     b->g_dirty = true;
     b->pending = false;
     CUDA_TRY(cudaMemcpy(b->d_agc, p, sizeof(AgcState) * PYSDR_MAX_RX, cudaMemcpyHostToDevice)); p += sizeof(AgcState) * PYSDR_MAX_RX;

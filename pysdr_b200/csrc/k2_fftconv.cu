@@ -57,7 +57,9 @@ af_fftconv_kernel(const FftConvArgs a, const float2 *__restrict__ tw) {
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             float2 u = c2[i];
-            if (mode == PYSDR_MODE_AM) {
+            if (mode == PYSDR_MODE_AMSYNC) {
+                u = make_float2(c2[i].x, 0.f);                           // in-phase arm of the PLL-de-rotated memory
+            } else if (mode == PYSDR_MODE_AM) {
                 u = make_float2(sqrtf(c2[i].x * c2[i].x + c2[i].y * c2[i].y), 0.f);
             } else if (mode == PYSDR_MODE_NFM) {
                 const float dr = c2[i].x - c0[i].x, di = c2[i].y - c0[i].y;

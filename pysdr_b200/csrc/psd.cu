@@ -17,13 +17,18 @@ struct pysdr_psd {
     float *d_part;         // partial sums workspace [lines][split][nfft] (position order)
     size_t part_cap;
     i64 launches;
+    int sub;               // frame f starts at (f / sub) * hop + sub_off[f % sub]   (sub = 1, sub_off = {0}: plain hop)
+    int sub_off[8];
+    int flags;             // PYSDR_PSD_RAW | PYSDR_PSD_FLIP
 };
+
+struct PsdSteps { int sub; int off[8]; };
 
 // grid (n_split, n_lines). Frames of line l: [l*navg, (l+1)*navg); split s takes frames s, s+n_split, ...
 template <int N, bool CPLX>
 __global__ void __launch_bounds__(FftPlan<N>::THREADS)
-psd_frames_kernel(const void *__restrict__ xv, const float *__restrict__ win, int chunk, int hop, int navg, int n_split,
-                  float *__restrict__ part, const float2 *__restrict__ tw) {
+psd_frames_kernel(const void *__restrict__ xv, const float *__restrict__ win, int chunk, int hop, const PsdSteps steps, int navg,
+                  int n_split, float *__restrict__ part, const float2 *__restrict__ tw) {
     extern __shared__ __align__(16) float2 s[];
     constexpr int T = FftPlan<N>::THREADS;
     constexpr int PER = (N + T - 1) / T;
@@ -33,7 +38,8 @@ psd_frames_kernel(const void *__restrict__ xv, const float *__restrict__ win, in
 #pragma unroll
     for (int i = 0; i < PER; ++i) acc[i] = 0.f;
     for (int f = split; f < navg; f += n_split) {
-        const i64 start = ((i64)line * navg + f) * hop;
+        const i64 fr = (i64)line * navg + f;
+        const i64 start = (steps.sub == 1) ? fr * hop : (fr / steps.sub) * hop + steps.off[fr % steps.sub];
         {                                                        // unrolled: all of a thread's loads in flight together
             float2 xr[PER];
             float wr[PER];
@@ -76,7 +82,8 @@ psd_frames_kernel(const void *__restrict__ xv, const float *__restrict__ win, in
 
 // out[line][fftshift(bin(p))] = dB( sum_split part[p] / (navg * wsum2) )
 template <int N>
-__global__ void psd_finalize_kernel(const float *__restrict__ part, int n_split, float scale, int dB, float *__restrict__ out) {
+__global__ void psd_finalize_kernel(const float *__restrict__ part, int n_split, float scale, int dB, int flags,
+                                    float *__restrict__ out) {
     const int line = blockIdx.y;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
@@ -84,9 +91,11 @@ __global__ void psd_finalize_kernel(const float *__restrict__ part, int n_split,
     float sum = 0.f;
     for (int sp = 0; sp < n_split; ++sp) sum += q[(size_t)sp * N];
     float v = sum * scale;
-    if (dB) v = 10.f * log10f(fmaxf(v, 1.0e-30f));
+    if (dB) v = 10.f * log10f((flags & PYSDR_PSD_RAW) ? v : fmaxf(v, 1.0e-30f));
     const int k = fft_pos_to_freq<N>(p);
-    out[(size_t)line * N + ((k + N / 2) % N)] = v;                       // fftshift
+    int col = (k + N / 2) % N;                                           // fftshift
+    if (flags & PYSDR_PSD_FLIP) col = N - 1 - col;                       // np.flipud of the shifted line (rtty.py:843)
+    out[(size_t)line * N + col] = v;
 }
 
 extern "C" int pysdr_psd_create(int32_t chunk, int32_t nfft, int32_t hop, const float *window, pysdr_psd **out) {
@@ -100,6 +109,8 @@ extern "C" int pysdr_psd_create(int32_t chunk, int32_t nfft, int32_t hop, const 
     p->wsum2 = 0.0;
     for (int i = 0; i < chunk; ++i) p->wsum2 += (double)window[i] * (double)window[i];
     p->d_part = nullptr; p->part_cap = 0; p->launches = 0;
+    p->sub = 1; p->flags = 0;
+    for (int i = 0; i < 8; ++i) p->sub_off[i] = 0;
     if (cudaMalloc(&p->d_win, sizeof(float) * chunk) != cudaSuccess) {
         pysdr_set_error("psd_create: cudaMalloc failed");
         delete p;
@@ -117,6 +128,20 @@ extern "C" int pysdr_psd_destroy(pysdr_psd *p) {
     return PYSDR_OK;
 }
 
+extern "C" int pysdr_psd_configure(pysdr_psd *p, int32_t sub, const int32_t *sub_off, int32_t flags) {
+    if (!p || sub < 1 || sub > 8 || (sub > 1 && !sub_off)) { pysdr_set_error("psd_configure: need 1 <= sub <= 8"); return PYSDR_ERR_ARG; }
+    for (int i = 0; i < sub; ++i) {
+        const int o = sub > 1 ? sub_off[i] : 0;
+        if (o < 0 || o >= p->hop || (i > 0 && o < p->sub_off[i - 1])) {
+            pysdr_set_error("psd_configure: sub-step offsets must be ascending within [0, hop)");
+            return PYSDR_ERR_ARG;
+        }
+        p->sub_off[i] = o;
+    }
+    p->sub = sub; p->flags = flags;
+    return PYSDR_OK;
+}
+
 extern "C" int64_t pysdr_psd_launch_count(const pysdr_psd *p) { return p ? p->launches : -1; }
 
 template <int N>
@@ -130,14 +155,17 @@ static int psd_launch(pysdr_psd *p, const void *d_x, int is_complex, int navg, i
     const float2 *tw = fft_twiddles(N);
     if (!tw) { pysdr_set_error("fft twiddle table allocation failed"); return PYSDR_ERR_CUDA; }
     dim3 grid((unsigned)n_split, (unsigned)n_lines);
+    PsdSteps steps;
+    steps.sub = p->sub;
+    for (int i = 0; i < 8; ++i) steps.off[i] = p->sub_off[i];
     if (is_complex)
-        psd_frames_kernel<N, true><<<grid, FftPlan<N>::THREADS, smem, st>>>(d_x, p->d_win, p->chunk, p->hop, navg, n_split, p->d_part, tw);
+        psd_frames_kernel<N, true><<<grid, FftPlan<N>::THREADS, smem, st>>>(d_x, p->d_win, p->chunk, p->hop, steps, navg, n_split, p->d_part, tw);
     else
-        psd_frames_kernel<N, false><<<grid, FftPlan<N>::THREADS, smem, st>>>(d_x, p->d_win, p->chunk, p->hop, navg, n_split, p->d_part, tw);
+        psd_frames_kernel<N, false><<<grid, FftPlan<N>::THREADS, smem, st>>>(d_x, p->d_win, p->chunk, p->hop, steps, navg, n_split, p->d_part, tw);
     LAUNCH_CHECK();
-    const float scale = (float)(1.0 / ((double)navg * p->wsum2));
+    const float scale = (p->flags & PYSDR_PSD_RAW) ? 1.0f / (float)navg : (float)(1.0 / ((double)navg * p->wsum2));
     dim3 g2((unsigned)((N + 255) / 256), (unsigned)n_lines);
-    psd_finalize_kernel<N><<<g2, 256, 0, st>>>(p->d_part, n_split, scale, dB, d_out);
+    psd_finalize_kernel<N><<<g2, 256, 0, st>>>(p->d_part, n_split, scale, dB, p->flags, d_out);
     LAUNCH_CHECK();
     p->launches += 2;
     return PYSDR_OK;
@@ -147,7 +175,15 @@ extern "C" int pysdr_psd_lines(pysdr_psd *p, const void *d_x, int64_t n, int is_
                                int64_t *n_lines_p, void *stream) {
     if (!p || !d_x || !d_out || navg < 1) { pysdr_set_error("psd_lines: bad arguments"); return PYSDR_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
-    const i64 n_frames = n < p->chunk ? 0 : 1 + (n - p->chunk) / p->hop;
+    i64 n_frames = 0;
+    if (p->sub == 1) {
+        n_frames = n < p->chunk ? 0 : 1 + (n - p->chunk) / p->hop;
+    } else if (n >= p->chunk) {                                    // frames with start(f) + chunk <= n (offsets ascending, < hop)
+        const i64 g = (n - p->chunk) / p->hop;
+        n_frames = g * p->sub;
+        for (int i = 0; i < p->sub; ++i)
+            if (g * p->hop + p->sub_off[i] + p->chunk <= n) n_frames = g * p->sub + i + 1;
+    }
     const i64 n_lines = n_frames / navg;
     if (n_lines_p) *n_lines_p = n_lines;
     if (n_lines == 0) return PYSDR_OK;

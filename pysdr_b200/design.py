@@ -22,7 +22,7 @@ RTLsrates = [0.25, 1.024, 1.536, 1.792, 1.92, 2.048, 2.16, 2.56, 2.88, 3.2]     
 SDRplaysrates = [0.25, 0.5, 1, 2, 2.048, 3, 4, 5, 6, 7, 8, 9, 10]                              # Tables.py:45
 MAX_RX = 6                                                                                    # params.py:33
 
-MODE_IDS = {"AM": 0, "AM-Synch": 0, "USB": 1, "SSB": 1, "LSB": 2, "CW": 3, "IQ": 4, "RTTY": 4, "NFM": 5,
+MODE_IDS = {"AM": 0, "AM-Synch": 7, "USB": 1, "SSB": 1, "LSB": 2, "CW": 3, "IQ": 4, "RTTY": 4, "NFM": 5,
             "RAW": 6}       # RAW: internal second stage of the WFM chain (sig_proc._WfmChain)
 
 

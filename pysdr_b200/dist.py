@@ -59,6 +59,9 @@ class ShardedCapture:
     def __init__(self, bank, P, rank, world, chunks_per_rank):
         self.bank, self.P, self.rank, self.world = bank, P, rank, world
         self.plan = shard_plan(P, rank, world, chunks_per_rank)
+        if world > 1 and any(bank._mode_of(r) == 'AM-Synch' for r in range(bank.n_rx)):
+            raise ValueError("AM-Synch carries a PLL state that has no exact hand-off between time shards; "
+                             "shard AM-Synch receivers by receiver (SURVEY 8(e) axis 1), not by time")
         dev = bank.device
         w = self.plan['warm_chunks']
         self.peaks_ext = torch.zeros((bank.n_rx, w + self.plan['n_blocks']), dtype=torch.float32, device=dev)

@@ -88,8 +88,21 @@ class _Dec:
 
 
 class _Pll:
+    """``rx.demod.am_pll`` — the AM-Synch carrier loop lives in the bank (am_pll_kernel, bank.cu)."""
+
+    def __init__(self, rx):
+        self._rx = rx
+
     def reset(self):                                     # reference receiver.py:649
-        pass
+        self._rx._bank.pll_reset(0)
+
+    @property
+    def phi(self):
+        return self._rx._bank.pll_get(0)['phi']
+
+    @property
+    def w(self):
+        return self._rx._bank.pll_get(0)['w']
 
 
 class _Holder:
@@ -101,7 +114,7 @@ class _Demod:
         b = rx._bank
         self.filter_bank_real = b.filter_bank_real      # reference receiver.py:873
         self.filter_bank_cmpx = b.filter_bank_cmpx      # reference receiver.py:874
-        self.am_pll = _Pll()
+        self.am_pll = _Pll(rx)
         self.wfm_video = _WfmVideo(rx)                                   # reference gui.py:1704
         self.wfm_filter_bank = design.wfm_video_bank(rx.P.SRATE, rx.P.FILT_LEN, design.VIDEO_BWs, rx.P.VIDEO_BW)
 

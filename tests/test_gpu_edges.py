@@ -1,4 +1,6 @@
 """Edge cases of the C-ABI path: ragged / tiny inputs, error codes, maximum receiver count, mid-stream retune."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -215,3 +217,80 @@ def test_wfm_demod_first_then_resample(deemph):
         assert_parity(rx.iq, orx.iq, "wfm resampled chunk %d" % c, rel_tol=2e-4, snr_min=74)
         assert_parity(am, ref, "wfm audio chunk %d" % c, rel_tol=2e-4, snr_min=74)
     assert np.max(np.abs(am)) > 0.05                                # a real demodulated tone, not silence
+
+
+def test_rtty_filterbank_vs_reference_run():
+    """The one PINNED parity target: device lines vs the fixture the reference's own
+    RTTY_Executive.run wrote (tests/golden/make_golden_rtty.py), fed in uneven pushes of whole symbols."""
+    from pysdr_b200.rtty import rtty_filterbank
+    from tests.util import rtty_input
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rtty_fbank.npz"))
+    fb = rtty_filterbank(48000)
+    assert (fb.N, fb.NFFT, fb.NSTART) == (int(g['N']), int(g['NFFT']), list(g['NSTART']))
+    x = rtty_input(int(g['n_sym']), fb.N)
+    parts, pos = [], 0
+    for k in (1, 1, 3, 2, 5):                                   # first symbol alone yields nothing (rtty.py:826-829)
+        parts.append(fb.push(x[pos * fb.N:(pos + k) * fb.N]))
+        pos += k
+    assert [len(p) for p in parts] == [0, 4, 12, 8, 20]
+    lines = np.concatenate(parts)
+    ref = g['lines'].astype(np.float64)
+    lin, rlin = 10.0 ** (lines / 10.0), 10.0 ** (ref / 10.0)
+    assert_parity(lin, rlin, "rtty filterbank power", rel_tol=1e-4, snr_min=80)
+    top = ref > ref.max() - 60.0
+    assert np.max(np.abs(lines[top] - ref[top])) < 2e-3         # dB, within 60 dB of the strongest bin
+    assert np.array_equal(np.argmax(lines, axis=1), np.argmax(ref, axis=1))
+
+
+def test_am_synch_pll_chain():
+    """AM-Synch: carrier PLL (open-choice law, oracle am_pll) -> in-phase arm -> AF FIR -> AGC; carrier 17 Hz off the
+    receiver centre so the loop has to pull in; mid-stream am_pll.reset() (reference receiver.py:649)."""
+    import pysdr_b200.sig_proc as dsp
+    P, Po = make_both(2.048, [1000], ['AM-Synch'], foffset_khz=100, af_bw_khz=[5])
+    C = P.IN_CHUNK_SIZE
+    n = np.arange(7 * C)
+    env = 1.0 + 0.6 * np.sin(2 * np.pi * 1e3 * n / P.SRATE) + 0.2 * np.sin(2 * np.pi * 2.3e3 * n / P.SRATE)
+    x = (0.2 * env * np.exp(2j * np.pi * (P.FOFFSET + 17.0) * n / P.SRATE + 0.7j) + _noise(len(n), 9, 0.002)).astype(np.complex64)
+    rx = dsp.Receiver(P, P.FOFFSET, 0, '1')
+    orx = odsp.Receiver(Po, Po.FOFFSET, 0, '1')
+    for c in range(7):
+        if c == 5:
+            rx.demod.am_pll.reset(); orx.demod.am_pll.reset()
+        am = rx.demod_data(x[c * C:(c + 1) * C])
+        ref = orx.demod_data(x[c * C:(c + 1) * C])
+        assert len(am) == len(ref)
+        assert_parity(am, ref, "am-synch chunk %d" % c, rel_tol=2e-4, snr_min=74)
+        assert abs(rx.demod.am_pll.phi - orx.demod.am_pll.phi) < 1e-4 and abs(rx.demod.am_pll.w - orx.demod.am_pll.w) < 1e-7
+    # locked: loop frequency = carrier offset, 17 Hz at 48 kHz
+    assert abs(rx.demod.am_pll.w * P.FS_OUT / (2 * np.pi) - 17.0) < 0.5
+
+
+def test_am_synch_in_bank_with_other_modes_and_direct_fir():
+    """AM-Synch next to AM/USB in one bank; FFT and direct-form AF filters both match the oracle; the state blob
+    carries the loop state across a bank hand-over."""
+    from pysdr_b200.receiver import receiver_offsets
+    P, Po = make_both(2.048, [1000, 1020, 1045], ['AM-Synch', 'AM', 'USB'], foffset_khz=100, af_bw_khz=[5, 5, 2])
+    C = P.IN_CHUNK_SIZE
+    n = np.arange(3 * C)
+    x = _noise(len(n), 21, 0.002).astype(np.complex128)
+    for k, off in enumerate(receiver_offsets(P)):
+        env = 1.0 + 0.5 * np.sin(2 * np.pi * (700.0 + 300 * k) * n / P.SRATE)
+        x = x + 0.1 * env * np.exp(2j * np.pi * (off + 11.0) * n / P.SRATE)
+    x = x.astype(np.complex64)
+    rxo.create_receivers(Po)
+    ref = [[], [], []]
+    for k in range(3):
+        for r in range(3):
+            ref[r].append(np.array(Po.rx[r].demod_data(x[k * C:(k + 1) * C])))
+    for direct in (0, 1):
+        bank = _bank(P, C)
+        bank.lib.pysdr_bank_force_direct_fir(bank.h, direct)
+        outs = [bank.process_host(x[k * C:(k + 1) * C], want_dc=False)[0] for k in range(2)]
+        blob = bank.get_state()
+        bank2 = _bank(P, C)
+        bank2.lib.pysdr_bank_force_direct_fir(bank2.h, direct)
+        bank2.set_state(blob)
+        outs.append(bank2.process_host(x[2 * C:3 * C], want_dc=False)[0])
+        for r in range(3):
+            got = np.concatenate([o[r] for o in outs])
+            assert_parity(got, np.concatenate(ref[r]), "rx%d direct=%d" % (r, direct), rel_tol=2e-4, snr_min=74)

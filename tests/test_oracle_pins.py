@@ -1,5 +1,7 @@
 """Pins the oracle against every known-answer item the reference tree holds for the path
 (SURVEY.md section 8c).  Reference line numbers are cited per test."""
+import os
+
 import numpy as np
 import pytest
 from scipy import signal
@@ -290,3 +292,18 @@ def test_replay_loop_quirks():
     assert all(len(a) in (1023, 1024, 1025) for a in out['am'][0])
     # DC-removed copy has zero mean per chunk; audio copy does not (receiver.py:250-252 vs :194)
     assert abs(np.mean(out['am_dc'][0][1])) < 1e-9
+
+
+def test_rtty_filterbank_matches_reference_run():
+    """PINNED: tests/golden/rtty_fbank.npz holds the lines the reference's own RTTY_Executive.run produced
+    (tests/golden/make_golden_rtty.py); the restated oracle must reproduce sizes and values."""
+    from oracle import rtty_oracle as ro
+    from tests.util import rtty_input
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rtty_fbank.npz"))
+    R = ro.RTTY_Params(48000)
+    assert (R.N, R.NFFT, R.NSTART, R.NBINS) == (int(g['N']), int(g['NFFT']), list(g['NSTART']), int(g['NBINS'])) == (1056, 2048, [0, 264, 528, 792], 7)
+    assert np.array_equal(R.frq, g['frq'])
+    assert np.allclose(np.kaiser(R.N, 8.6), g['window'], rtol=0, atol=0)
+    lines = ro.filterbank_lines(rtty_input(int(g['n_sym']), R.N), 48000)
+    assert lines.shape == g['lines'].shape == (44, 2048)
+    assert np.max(np.abs(lines - g['lines'])) < 1e-5            # float32 storage of values up to 74 dB

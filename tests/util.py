@@ -70,3 +70,14 @@ def golden_input(n, srate, offsets_hz, seed):
     for i, f in enumerate(offsets_hz):
         x += 0.1 * (1 + 0.5 * np.sin(2 * np.pi * (700.0 + 300 * i) * t)) * np.exp(2j * np.pi * (f + 900.0) * t)
     return x.astype(np.complex64)
+
+
+def rtty_input(n_sym, N, FS_OUT=48000, seed=505):
+    """Noise + a 45.45 baud FSK pair (mark 915 Hz / space 1085 Hz) + a weak carrier; complex64."""
+    n = n_sym * N
+    t = np.arange(n)
+    bits = ((np.arange(n_sym) * 7 + 3) % 5 < 2).astype(np.float64)
+    f = np.repeat(np.where(bits > 0, 915.0, 1085.0), N)
+    ph = 2 * np.pi * np.cumsum(f) / FS_OUT
+    x = lcg_iq(n, seed, scale=0.01).astype(np.complex128) + 0.2 * np.exp(1j * ph) + 0.02 * np.exp(-2j * np.pi * 3000.0 * t / FS_OUT)
+    return x.astype(np.complex64)
