@@ -84,6 +84,11 @@ int pysdr_bank_set_dec_taps(pysdr_bank *b, int rx, const float *h, int n);
  * interleaved (re,im) pairs when is_complex. */
 int pysdr_bank_set_demod(pysdr_bank *b, int rx, int mode, const float *taps, int n, int is_complex,
                          uint64_t bfo_phase_inc);
+/* WFM2 (Tables.py:34; BASELINE config 4): a 3-row resampler bank fed with the real FM multiplex — row 0 LO 0 (L+R),
+ * row 1 LO 38 kHz (L-R), row 2 LO 19 kHz (pilot), all rows in IQ mode — turns rows 0/1 into L/R after the AF
+ * filters: u = z2/|z2|, D = 2 Re{z1 conj(u)^2} (0 when |z2| <= pilot_min), L = Re z0 + D, R = Re z0 - D; one AGC
+ * (block peak = max of both) serves the pair; process_back returns L in row 0 and R in row 1 as float32. */
+int pysdr_bank_set_stereo(pysdr_bank *b, int on, double pilot_min);
 /* rx.demod.am_pll.reset()        reference receiver.py:649 ; loop state out2 = {phi [rad], w [rad/sample]} */
 int pysdr_bank_pll_reset(pysdr_bank *b, int rx);
 int pysdr_bank_pll_get(pysdr_bank *b, int rx, double out2[2], void *stream);

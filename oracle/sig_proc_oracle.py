@@ -607,14 +607,35 @@ class Receiver:
                                                      P.SRATE) for lb in VIDEO_BWs]
         self.demod.wfm_video.h = self.demod.wfm_filter_bank[_video_index(P)]
         self.wfm_vid = decimator(P.SRATE, 1, 1, P.FILT_LEN, VIDEO_BWs, P.VIDEO_BW, self.dtype)
-        self.wfm_res = decimator(P.SRATE, P.UP, P.DOWN, P.FILT_LEN, VIDEO_BWs, P.VIDEO_BW, self.dtype)
         self.wfm_prev2 = np.zeros(2, self.dtype)
+        self._wfm_stage2()
+
+    def _wfm_stage2(self):
+        """(Re)build everything after the discriminator; a WFM <-> WFM2 switch restarts this stage and the AGC, the
+        video stage keeps running."""
+        P = self.P
+        self.agc.reset()
+        self.wfm_res = decimator(P.SRATE, P.UP, P.DOWN, P.FILT_LEN, VIDEO_BWs, P.VIDEO_BW, self.dtype)
         self.wfm_deemph = None
+        self.wfm_stereo = self._mode() == 'WFM2'
+        self._wfm_res_key = None
+        if self.wfm_stereo:
+            # OPEN CHOICE (no in-tree stereo decoder): three resamplers on the real multiplex — LO 0 (L+R), 38 kHz (L-R),
+            # 19 kHz (pilot) — equal-delay AF stage ('Max' delta for the audio rows, 500 Hz low-pass for the pilot),
+            # feed-forward carrier (pilot/|pilot|)^2, L = S + D, R = S - D, one block AGC on max(|L|,|R|).
+            self.wfm_res_lo = [None, signal_generator(38e3, P.IN_CHUNK_SIZE, P.SRATE, True),
+                               signal_generator(19e3, P.IN_CHUNK_SIZE, P.SRATE, True)]
+            self.wfm_res3 = [self.wfm_res] + [decimator(P.SRATE, P.UP, P.DOWN, P.FILT_LEN, VIDEO_BWs, P.VIDEO_BW, self.dtype)
+                                              for _ in range(2)]
+            self.wfm_af3 = [demodulator(P.FS_OUT, P.FILT_LEN, AF_BWs, self.dtype, exact=not self.fast) for _ in range(3)]
+            self.wfm_deemph = None
 
     def _demod_wfm(self, x):
         P = self.P
         if not hasattr(self, 'wfm_vid'):
             self._wfm_setup()
+        elif self.wfm_stereo != (self._mode() == 'WFM2'):
+            self._wfm_stage2()
         self.wfm_vid.h = self.demod.wfm_video.h
         y = self.wfm_vid.resamp(x, self.lo)                          # video-filtered baseband at SRATE
         yy = np.concatenate((self.wfm_prev2, y))
@@ -626,11 +647,37 @@ class Receiver:
         key = float(af_bw)
         if getattr(self, '_wfm_res_key', None) != key:
             self.wfm_res.h = design_lowpass(P.FILT_LEN, af_bw, P.SRATE * P.UP, gain=P.UP)
+            if self.wfm_stereo:
+                self.wfm_res3[1].h = self.wfm_res3[2].h = self.wfm_res.h
             self._wfm_res_key = key
+        tau = getattr(P, 'DEEMPH_US', 0) * 1e-6
+        if self.wfm_stereo:
+            mpx = fm.astype(self.dtype)
+            z = [self.wfm_res3[r].resamp(mpx, self.wfm_res_lo[r]) for r in range(3)]
+            idx = [0, 0, AF_BWs.index('500 Hz')]
+            f = [self.wfm_af3[r].demod(z[r], 'IQ', idx[r], 0) for r in range(3)]
+            self.iq = np.asarray(z[0], np.complex64)
+            m2 = f[2].real ** 2 + f[2].imag ** 2
+            pmin = float(getattr(P, 'WFM_PILOT_MIN', 0.0))
+            ok = (m2 > pmin * pmin) & (m2 > 0)
+            u2 = np.where(ok, f[2] * f[2] / np.where(ok, m2, 1.0), 0.0)
+            D = 2.0 * (f[1] * np.conj(u2)).real
+            S = f[0].real
+            L, R = S + D, S - D
+            if len(L):
+                g = self.agc.update(max(np.max(np.abs(L)), np.max(np.abs(R))))
+                L, R = L * g, R * g
+            if tau > 0:
+                if self.wfm_deemph is None:
+                    al = 1.0 - math.exp(-1.0 / (P.FS_OUT * tau))
+                    self.wfm_deemph = [iir_stream([al], [1, al - 1]) for _ in range(2)]
+                L = self.wfm_deemph[0].run(np.asarray(L, np.float32))
+                R = self.wfm_deemph[1].run(np.asarray(R, np.float32))
+            self.am = (np.asarray(L, np.float32) + 1j * np.asarray(R, np.float32)).astype(np.complex64)
+            return self.am
         z = self.wfm_res.resamp(fm.astype(self.dtype), None)
         self.iq = np.asarray(z, np.complex64)
         a = self.agc.run(z.real)
-        tau = getattr(P, 'DEEMPH_US', 0) * 1e-6
         if tau > 0:                                                  # OPEN CHOICE: de-emphasis after the block AGC
             if self.wfm_deemph is None:
                 al = 1.0 - math.exp(-1.0 / (P.FS_OUT * tau))

@@ -41,6 +41,7 @@ SIGNATURES = {
     "pysdr_bank_create": (c_int, [ctypes.POINTER(BankConfig), ctypes.POINTER(c_vp)]),
     "pysdr_bank_destroy": (c_int, [c_vp]),
     "pysdr_bank_reset": (c_int, [c_vp]),
+    "pysdr_bank_set_stereo": (c_int, [c_vp, c_int, c_dbl]),
     "pysdr_bank_pll_reset": (c_int, [c_vp, c_int]),
     "pysdr_bank_pll_get": (c_int, [c_vp, c_int, c_vp, c_vp]),
     "pysdr_bank_set_lo": (c_int, [c_vp, c_int, c_u64]),

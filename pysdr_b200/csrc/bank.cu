@@ -485,6 +485,8 @@ struct pysdr_bank {
     float *d_R, *d_peaks, *d_gains;
     AgcState *d_agc;
     double2 *d_pll;            // AM-Synch loop state (phi, w) per receiver
+    bool stereo;               // WFM2 resampler bank: rows 0/1/2 = sum / difference / pilot -> L, R
+    float pilot_min;
     double pll_k1, pll_k2;
     // pending front->back
     i64 pend_n_out, pend_m0, pend_B0, pend_blocks;
@@ -571,6 +573,7 @@ extern "C" int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out)
     b->force_generic = false;
     b->force_direct_fir = false;
     b->k1_only = false;
+    b->stereo = false; b->pilot_min = 0.f;
     b->timing = false;
     b->launches = 0;
     b->pending = false;
@@ -656,6 +659,14 @@ extern "C" int pysdr_bank_set_demod(pysdr_bank *b, int rx, int mode, const float
     b->bfo_inc[rx] = bfo_inc;
     b->demod_set[rx] = true;
     b->h_dirty[rx] = true;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_set_stereo(pysdr_bank *b, int on, double pilot_min) {
+    if (!b) { pysdr_set_error("null bank"); return PYSDR_ERR_ARG; }
+    if (on && b->cfg.n_rx != 3) { pysdr_set_error("set_stereo: the stereo resampler bank has exactly 3 rows (sum, difference, pilot)"); return PYSDR_ERR_ARG; }
+    b->stereo = on != 0;
+    b->pilot_min = (float)pilot_min;
     return PYSDR_OK;
 }
 
@@ -791,6 +802,37 @@ __global__ void __launch_bounds__(32) am_pll_kernel(float2 *__restrict__ Cbase, 
         __syncwarp();
     }
     if (threadIdx.x == 0) state[rx] = make_double2(phi, w);
+}
+
+// WFM2 stereo matrix at the audio rate (open choice).  Rows of the resampler bank fed with the
+// real FM multiplex: z0 = sum channel (LO 0), z1 = difference channel (LO 38 kHz), z2 = pilot (LO 19 kHz, narrow AF
+// low-pass).  u = z2/|z2|;  S = Re z0;  D = 2 Re{ z1 conj(u)^2 }  (0 when |z2| <= pilot_min);  L = S + D, R = S - D.
+__global__ void stereo_matrix_kernel(const float2 *__restrict__ z0, const float2 *__restrict__ z1, const float2 *__restrict__ z2,
+                                     i64 n, float pilot_min, float *__restrict__ L, float *__restrict__ R) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const float2 p = z2[i], d = z1[i];
+        const float S = z0[i].x;
+        const float m2 = p.x * p.x + p.y * p.y;
+        float D = 0.f;
+        if (m2 > pilot_min * pilot_min && m2 > 0.f) {
+            const float inv = 1.0f / m2;                                  // u^2 = p^2 / |p|^2
+            const float u2r = (p.x * p.x - p.y * p.y) * inv, u2i = 2.f * p.x * p.y * inv;
+            D = 2.f * (d.x * u2r + d.y * u2i);                            // 2 Re{ d conj(u^2) }
+        }
+        L[i] = S + D;
+        R[i] = S - D;
+    }
+}
+
+__global__ void peak_link_kernel(float *__restrict__ p0, float *__restrict__ p1, i64 n) {   // one AGC for the stereo pair
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float m = fmaxf(p0[i], p1[i]);
+        p0[i] = m;
+        p1[i] = m;
+    }
 }
 
 __global__ void real_part_kernel(const float2 *__restrict__ c, float *__restrict__ a, i64 n) {
@@ -1008,10 +1050,30 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
         if (rc) return rc;
         (void)aout;
     }
+    if (b->stereo) {
+        for (int r = 0; r < 3; ++r)
+            if (b->mode[r] != PYSDR_MODE_IQ) { pysdr_set_error("stereo bank: all three rows must be in IQ mode"); return PYSDR_ERR_STATE; }
+        i64 blocks = (n_out + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        float *Ls = b->d_R, *Rs = b->d_R + b->r_stride;
+        stereo_matrix_kernel<<<(unsigned)blocks, 256, 0, st>>>(b->d_a, b->d_a + b->a_stride, b->d_a + 2 * b->a_stride, n_out,
+                                                               b->pilot_min, Ls, Rs);
+        LAUNCH_CHECK();
+        copy_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(Ls, (float *)b->d_a, n_out);
+        LAUNCH_CHECK();
+        copy_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(Rs, (float *)(b->d_a + b->a_stride), n_out);
+        LAUNCH_CHECK();
+        b->launches += 3;
+    }
     {
         dim3 grid((unsigned)n_blocks, (unsigned)c.n_rx);       // IQ-mode rows produce unused values
         block_peak_kernel<<<grid, 256, 0, st>>>((const float *)b->d_a, 2 * b->a_stride, d_peaks, n_blocks, B0, c.in_chunk,
                                                 c.up, c.down, m0, n_out);
+        LAUNCH_CHECK();
+        b->launches++;
+    }
+    if (b->stereo) {
+        peak_link_kernel<<<(unsigned)((n_blocks + 255) / 256), 256, 0, st>>>(d_peaks, d_peaks + n_blocks, n_blocks);
         LAUNCH_CHECK();
         b->launches++;
     }
@@ -1056,7 +1118,7 @@ extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks,
     s.gains = b->d_gains; s.gains_stride = b->max_blocks;
     if (skip_blocks < 0 || skip_blocks >= n_blocks) { pysdr_set_error("process_back: bad skip_blocks"); return PYSDR_ERR_ARG; }
     s.n_blocks = n_blocks; s.n_rx = c.n_rx; s.skip = skip_blocks;
-    for (int r = 0; r < PYSDR_MAX_RX; ++r) s.enabled[r] = (r < c.n_rx && b->mode[r] != PYSDR_MODE_IQ) ? 1 : 0;
+    for (int r = 0; r < PYSDR_MAX_RX; ++r) s.enabled[r] = (r < c.n_rx && (b->mode[r] != PYSDR_MODE_IQ || (b->stereo && r < 2))) ? 1 : 0;
     if (b->timing) {
         cudaEvent_t e;
         CUDA_TRY(cudaEventCreate(&e));
@@ -1074,7 +1136,7 @@ extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks,
         const float *aout = (const float *)(b->d_a + (size_t)r * b->a_stride);
         float *am = d_am + (size_t)r * 2 * out_stride;
         float *amdc = d_am_dc ? d_am_dc + (size_t)r * 2 * out_stride : nullptr;
-        if (b->mode[r] == PYSDR_MODE_IQ) {
+        if (b->mode[r] == PYSDR_MODE_IQ && !(b->stereo && r < 2)) {
             i64 n = 2 * n_out, blocks = (n + 255) / 256;
             if (blocks > 148 * 8) blocks = 148 * 8;
             copy_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(aout, am, n);

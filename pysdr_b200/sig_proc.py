@@ -166,8 +166,11 @@ class Receiver:
         self._pw = torch.zeros(1, dtype=torch.float32, device=self._bank.device)
 
     def _wfm_chain(self):
+        stereo = design.per_rx(self.P.MODE, self.irx) == 'WFM2'
+        if self._wfm is not None and self._wfm.stereo != stereo:      # WFM <-> WFM2: the stage after the discriminator
+            self._wfm.stage2(stereo)                                  # (and its AGC) restarts, the video stage runs on
         if self._wfm is None:
-            self._wfm = _WfmChain(self)
+            self._wfm = _WfmChain(self, stereo)
         return self._wfm
 
     def demod_data(self, x):
@@ -463,11 +466,17 @@ class _WfmChain:
     """WFM / WFM2: video FIR at the RF rate -> FM discriminator at the RF rate -> resampler (AF low-pass) -> AGC
     ("BCB FM is wideband so we need to demodulate first before resampling", reference gui.py:1703,1759-1762).
     Built from two K1 launches (UP=DOWN=1 video stage, UP/DOWN resampler stage on the real discriminator output)
-    and pysdr_fm_disc; mono (no in-tree specification of the stereo decoder exists)."""
+    and pysdr_fm_disc.  WFM is mono.  WFM2 is the stereo decoder (BASELINE config 4; no in-tree specification, the law
+    is an open choice stated in DESIGN.md section 3): the resampler stage becomes a 3-row bank on the multiplex — LO 0
+    (L+R), LO 38 kHz (L-R), LO 19 kHz (pilot, 500 Hz AF low-pass) — and pysdr_bank_set_stereo turns the rows into L/R
+    with feed-forward pilot recovery (carrier = (pilot/|pilot|)^2); ``am`` is then complex64 L + 1j*R."""
 
-    def __init__(self, rx):
+    PILOT_AF = '500 Hz'
+
+    def __init__(self, rx, stereo=False):
         P = rx.P
         self.rx = rx
+        self.stereo = bool(stereo)
         self.lib = _lib.load()
         vid = _NS()
         vid.SRATE, vid.UP, vid.DOWN, vid.FS_OUT = P.SRATE, 1, 1, int(P.SRATE)
@@ -477,14 +486,25 @@ class _WfmChain:
         check(self.lib.pysdr_bank_set_k1_only(self.vbank.h, 1))
         self.filter_bank = design.wfm_video_bank(P.SRATE, P.FILT_LEN, design.VIDEO_BWs, P.VIDEO_BW)
         self.set_video(self.filter_bank[design.video_index(P)])
+        dev = self.vbank.device
+        self.prev2 = torch.zeros(2, dtype=torch.complex64, device=dev)
+        self.fm = torch.empty(int(P.IN_CHUNK_SIZE), dtype=torch.complex64, device=dev)
+        self.stage2(stereo)
+
+    def stage2(self, stereo):
+        P = self.rx.P
+        self.stereo = bool(stereo)
         res = _NS()
         res.SRATE, res.UP, res.DOWN, res.FS_OUT = P.SRATE, P.UP, P.DOWN, P.FS_OUT
         res.IN_CHUNK_SIZE, res.FILT_LEN, res.VIDEO_BW = P.IN_CHUNK_SIZE, P.FILT_LEN, P.VIDEO_BW
         res.MODE, res.AF_BW, res.AF_FILTER_NUM, res.BFO, res.VIDEO_FILTER_NUM = 'RAW', 0, 0, 0, None
-        self.rbank = ReceiverBank(res, [0.0], max_in=int(P.IN_CHUNK_SIZE))
-        dev = self.vbank.device
-        self.prev2 = torch.zeros(2, dtype=torch.complex64, device=dev)
-        self.fm = torch.empty(int(P.IN_CHUNK_SIZE), dtype=torch.complex64, device=dev)
+        if self.stereo:
+            res.MODE = ['IQ', 'IQ', 'IQ']
+            res.AF_FILTER_NUM = [0, 0, design.AF_BWs.index(self.PILOT_AF)]
+            self.rbank = ReceiverBank(res, [0.0, 38e3, 19e3], max_in=int(P.IN_CHUNK_SIZE))
+            check(self.lib.pysdr_bank_set_stereo(self.rbank.h, 1, float(getattr(P, 'WFM_PILOT_MIN', 0.0))))
+        else:
+            self.rbank = ReceiverBank(res, [0.0], max_in=int(P.IN_CHUNK_SIZE))
         self._res_key = None
         self.deemph = None
 
@@ -502,16 +522,25 @@ class _WfmChain:
                                      ctypes.c_void_p(fm.data_ptr()), _stream_ptr()))
         af_bw = float(design.per_rx(getattr(P, 'AF_BW', 0), rx.irx) or 0)
         if af_bw != self._res_key:
-            self.rbank.set_dec_taps(0, design.wfm_resampler_taps(P.SRATE, P.UP, P.FILT_LEN, af_bw))
+            taps = design.wfm_resampler_taps(P.SRATE, P.UP, P.FILT_LEN, af_bw)
+            for r in range(self.rbank.n_rx):
+                self.rbank.set_dec_taps(r, taps)
             self._res_key = af_bw
         am, iq, _ = self.rbank.process(fm, want_dc=False)
-        a = am[0]
         tau = getattr(P, 'DEEMPH_US', 0) * 1e-6
-        if tau > 0:                                             # one-pole de-emphasis, block-parallel scan
-            if self.deemph is None:
-                al = 1.0 - np.exp(-1.0 / (P.FS_OUT * tau))
-                self.deemph = lfilter_stream([al], [1, al - 1])
-            a = self.deemph.run_dev(a.contiguous())
+        if tau > 0 and self.deemph is None:                     # one-pole de-emphasis, block-parallel scan
+            al = 1.0 - np.exp(-1.0 / (P.FS_OUT * tau))
+            self.deemph = [lfilter_stream([al], [1, al - 1]) for _ in range(2 if self.stereo else 1)]
+        if self.stereo:
+            n_out = self.rbank.n_out
+            lr = [self.rbank._am[r, :n_out] for r in (0, 1)]    # float32 L, R rows after the common AGC
+            if tau > 0:
+                lr = [self.deemph[r].run_dev(lr[r].contiguous()) for r in (0, 1)]
+            a = lr[0].cpu().numpy() + 1j * lr[1].cpu().numpy()
+            return a.astype(np.complex64), iq[0].cpu().numpy()
+        a = am[0]
+        if tau > 0:
+            a = self.deemph[0].run_dev(a.contiguous())
         return a.cpu().numpy(), iq[0].cpu().numpy()
 
 
