@@ -89,7 +89,7 @@ class ReceiverBank:
     def _mode_of(self, rx):
         m = design.per_rx(self.P.MODE, rx)
         if m not in design.MODE_IDS:
-            raise PysdrError("mode %r is not served by the B200 receive path (WFM/WFM2 are out of scope this round)" % (m,))
+            raise PysdrError("mode %r is not a ReceiverBank mode (WFM/WFM2 run through sig_proc.Receiver's WFM chain)" % (m,))
         return m
 
     def sync_demod(self, force=False):

@@ -354,3 +354,28 @@ def test_wfm_to_wfm2_switch_restarts_chain():
         if c != 2:                                  # chunk 2: stage-2 start-up, the pilot filter is still empty
             assert_parity(am.real, ref.real, "chunk %d" % c, rel_tol=3e-4, snr_min=70)
             assert_parity(am.imag, ref.imag, "chunk %d R" % c, rel_tol=3e-4, snr_min=70) if c > 2 else None
+
+
+def test_many_channel_bank_cfg5_geometry():
+    """BASELINE config 5 geometry (10 MS/s, 3/625, channels on a 9.6 kHz raster) at a testable size: 20 channels in
+    three groups, mixed modes, two chunks; every channel against its own oracle receiver."""
+    from pysdr_b200.channelizer import ChannelBank, raster_offsets
+    P, Po = make_both(10, [7000], ['USB'], af_bw_khz=[2])
+    assert (P.UP, P.DOWN, P.IN_CHUNK_SIZE) == (3, 625, 213333)
+    n_ch, C = 20, P.IN_CHUNK_SIZE
+    offs = raster_offsets(n_ch, 9600.0, 150e3)
+    modes = [['AM', 'NFM', 'USB', 'CW', 'LSB'][k % 5] for k in range(n_ch)]
+    afs = [[5e3, 10e3, 2e3, 500., 3e3][k % 5] for k in range(n_ch)]
+    n = np.arange(2 * C)
+    x = _noise(len(n), 77, 0.01).astype(np.complex128)
+    for k, f in enumerate(offs):
+        x = x + 0.02 * (1 + 0.5 * np.sin(2 * np.pi * (300.0 + 40 * k) * n / P.SRATE)) * np.exp(2j * np.pi * (f + 700.0) * n / P.SRATE)
+    x = x.astype(np.complex64)
+    cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=2 * C)
+    am, iq = cb.process(torch.from_numpy(x).cuda())
+    assert len(am) == n_ch and cb.n_out == odsp.n_out_total(2 * C, P.UP, P.DOWN)
+    for k in range(n_ch):
+        Pk = rxo.make_P(P.SRATE, [7000e3], modes[k], foffset=100e3, af_bw=afs[k], bfo=700.0)
+        orx = odsp.Receiver(Pk, offs[k], 0, str(k), fast=True)
+        ref = np.concatenate([np.array(orx.demod_data(x[c * C:(c + 1) * C])) for c in range(2)])
+        assert_parity(am[k].cpu().numpy(), ref, "channel %d (%s)" % (k, modes[k]), rel_tol=2e-4, snr_min=74)

@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Secondary measurement (not the headline bench line): BASELINE.json configs[4] geometry — N channel receivers on a
+9.6 kHz raster on one 10 MS/s stream (3/625 -> 48 kHz), processed in streaming blocks that are resident only while
+they are being worked on.  Reports input Msamples/s through all channels, the real-time factor and the FP32 rate of the
+K1 contraction (8 flop per complex tap MAC)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--channels", type=int, default=1024)
+    ap.add_argument("--block-chunks", type=int, default=188, help="IN_CHUNK_SIZE chunks per streaming block (188 = 4.0 s)")
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=1)
+    args = ap.parse_args()
+    import __graft_entry__ as ge
+    ge.build()
+    from pysdr_b200.channelizer import ChannelBank, raster_offsets
+    from pysdr_b200.params import RUN_TIME_PARAMS
+    from pysdr_b200.synth import synth_iq
+    P = RUN_TIME_PARAMS(['-fs', '10', '-mode', 'USB', '-fc', '7000', '-af_bw', '2'])
+    C = int(P.IN_CHUNK_SIZE)
+    n = args.block_chunks * C
+    offs = raster_offsets(args.channels, 9600.0, 0.0)
+    modes = [['AM', 'NFM', 'USB', 'CW'][k % 4] for k in range(args.channels)]
+    afs = [[5e3, 10e3, 2e3, 500.][k % 4] for k in range(args.channels)]
+    x = synth_iq(n, P.SRATE, offs[:4], modes[:4], seed=5, device="cuda")
+    cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=n)
+    for _ in range(args.warmup):
+        cb.process(x)
+    torch.cuda.synchronize()
+    l0 = cb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        cb.process(x)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = (time.time() - t0) / args.steps
+    ms = e0.elapsed_time(e1) / args.steps
+    lp = (int(P.FILT_LEN) + int(P.UP) - 1) // int(P.UP)
+    n_out = cb.n_out
+    flops = 8.0 * lp * n_out * args.channels
+    sec = n / P.SRATE
+    print(json.dumps({"workload": "cfg5 geometry: %d channels, 9.6 kHz raster, 10 MS/s, 3/625, %.2f s blocks (%d chunks), modes AM/NFM/USB/CW"
+                                  % (args.channels, sec, args.block_chunks),
+                      "ms_per_block": ms, "wall_ms_per_block": wall * 1e3, "Msamples_per_s": n / ms / 1e3,
+                      "realtime_factor": sec / (ms / 1e3), "k1_TFLOP_per_s(8 flop/tap)": flops / ms / 1e9,
+                      "one_hour_capture_s_on_1_gpu": 3600.0 / (sec / (ms / 1e3)),
+                      "gpu_launches_per_block": (cb.launch_count() - l0) // args.steps,
+                      "groups": len(cb.banks)}))
+
+
+if __name__ == "__main__":
+    main()
