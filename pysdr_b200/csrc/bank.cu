@@ -191,25 +191,40 @@ __device__ __forceinline__ void block_range(i64 b, i64 B0, i64 in_chunk, int up,
     hi = e > n_out ? n_out : e;
 }
 
-// K2c: peak of |a| per block.  grid (n_blocks, n_rx).
-__global__ void __launch_bounds__(256)
-block_peak_kernel(const float *__restrict__ a, i64 a_row, float *__restrict__ peaks, i64 peaks_row, i64 B0, i64 in_chunk,
-                  int up, int down, i64 m0, i64 n_out) {
+// Warp-uniform block range: lanes 0/1 do the two 64-bit divisions, the rest of the warp takes the result by shuffle.
+__device__ __forceinline__ void block_range_warp(i64 b, i64 B0, i64 in_chunk, int up, int down, i64 m0, i64 n_out,
+                                                 i64 &lo, i64 &hi) {
+    const int lane = threadIdx.x & 31;
+    i64 v = 0;
+    if (lane < 2) v = ((i64)up * (B0 + b + lane) * in_chunk + down - 1) / down - m0;
+    const i64 s = __shfl_sync(0xffffffffu, v, 0), e = __shfl_sync(0xffffffffu, v, 1);
+    lo = s < 0 ? 0 : s;
+    hi = e > n_out ? n_out : e;
+}
+
+// K2c: peak of |a| per block.  One warp per block (a block is ~OUT_CHUNK_SIZE = 1024 samples), 8 blocks per CTA,
+// 8 loads in flight per lane.  grid (ceil(n_blocks/8), n_rx).
+#define BLK_WARPS 8
+__global__ void __launch_bounds__(32 * BLK_WARPS)
+block_peak_kernel(const float *__restrict__ a, i64 a_row, float *__restrict__ peaks, i64 peaks_row, i64 n_blocks, i64 B0,
+                  i64 in_chunk, int up, int down, i64 m0, i64 n_out) {
+    const int lane = threadIdx.x & 31;
+    const i64 blk = (i64)blockIdx.x * BLK_WARPS + (threadIdx.x >> 5);
+    if (blk >= n_blocks) return;
     a += (size_t)blockIdx.y * a_row;
-    peaks += (size_t)blockIdx.y * peaks_row;
     i64 lo, hi;
-    block_range(blockIdx.x, B0, in_chunk, up, down, m0, n_out, lo, hi);
+    block_range_warp(blk, B0, in_chunk, up, down, m0, n_out, lo, hi);
     float mx = 0.f;
-    for (i64 i = lo + threadIdx.x; i < hi; i += blockDim.x) mx = fmaxf(mx, fabsf(a[i]));
-    __shared__ float sm[8];
+    for (i64 i = lo + lane; i < hi; i += 32 * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (i + 32 * u < hi) ? a[i + 32 * u] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) mx = fmaxf(mx, fabsf(v[u]));
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sm[w]);
-        peaks[blockIdx.x] = mx;
-    }
+    if (lane == 0) peaks[(size_t)blockIdx.y * peaks_row + blk] = mx;
 }
 
 // K2d: AGC recursion, one thread per receiver.  Law documented in oracle/sig_proc_oracle.py (class agc);
@@ -381,41 +396,39 @@ __global__ void __launch_bounds__(AGC_THREADS) agc_scan_kernel(AgcScanArgs p) {
 
 // K2e: am = a*gain ; am_dc = am - mean_block(am) for AM/USB.  grid (n_blocks, n_rx); IQ rows are skipped.
 struct ApplyKinds { int kind[PYSDR_MAX_RX]; };     // 0 skip (IQ), 1 real, 2 real + per-block DC removal
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * BLK_WARPS)
 agc_apply_kernel(const float *__restrict__ a, i64 a_row, const float *__restrict__ gains, i64 g_row, float *__restrict__ am,
-                 float *__restrict__ am_dc, i64 am_row, ApplyKinds kinds, i64 B0, i64 in_chunk, int up, int down, i64 m0,
-                 i64 n_out) {
+                 float *__restrict__ am_dc, i64 am_row, ApplyKinds kinds, i64 n_blocks, i64 B0, i64 in_chunk, int up, int down,
+                 i64 m0, i64 n_out) {
+    // one warp per block, 8 blocks per CTA: grid (ceil(n_blocks/8), n_rx)
     const int kind = kinds.kind[blockIdx.y];
     if (kind == 0) return;
+    const int lane = threadIdx.x & 31;
+    const i64 blk = (i64)blockIdx.x * BLK_WARPS + (threadIdx.x >> 5);
+    if (blk >= n_blocks) return;
     const int dc_remove = kind == 2;
     a += (size_t)blockIdx.y * a_row;
-    gains += (size_t)blockIdx.y * g_row;
     am += (size_t)blockIdx.y * am_row;
     if (am_dc) am_dc += (size_t)blockIdx.y * am_row;
     i64 lo, hi;
-    block_range(blockIdx.x, B0, in_chunk, up, down, m0, n_out, lo, hi);
-    const float g = gains[blockIdx.x];
+    block_range_warp(blk, B0, in_chunk, up, down, m0, n_out, lo, hi);
+    const float g = gains[(size_t)blockIdx.y * g_row + blk];
     float sum = 0.f;
-    for (i64 i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        const float v = a[i] * g;
-        am[i] = v;
-        sum += v;
+    for (i64 i = lo + lane; i < hi; i += 32 * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (i + 32 * u < hi) ? a[i + 32 * u] * g : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (i + 32 * u < hi) am[i + 32 * u] = v[u];
+            sum += v[u];
+        }
     }
     if (!am_dc) return;
-    __shared__ float sm[8];
-    __shared__ float mean_s;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < 8; ++w) t += sm[w];
-        mean_s = (hi > lo && dc_remove) ? t / (float)(hi - lo) : 0.f;
-    }
-    __syncthreads();
-    const float mean = mean_s;
-    for (i64 i = lo + threadIdx.x; i < hi; i += blockDim.x) am_dc[i] = a[i] * g - mean;
+    const float mean = (hi > lo && dc_remove) ? sum / (float)(hi - lo) : 0.f;
+    for (i64 i = lo + lane; i < hi; i += 32) am_dc[i] = a[i] * g - mean;
 }
 
 __global__ void copy_f32_kernel(const float *__restrict__ s, float *__restrict__ d, i64 n) {
@@ -1066,9 +1079,9 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
         b->launches += 3;
     }
     {
-        dim3 grid((unsigned)n_blocks, (unsigned)c.n_rx);       // IQ-mode rows produce unused values
-        block_peak_kernel<<<grid, 256, 0, st>>>((const float *)b->d_a, 2 * b->a_stride, d_peaks, n_blocks, B0, c.in_chunk,
-                                                c.up, c.down, m0, n_out);
+        dim3 grid((unsigned)((n_blocks + BLK_WARPS - 1) / BLK_WARPS), (unsigned)c.n_rx);   // IQ-mode rows produce unused values
+        block_peak_kernel<<<grid, 32 * BLK_WARPS, 0, st>>>((const float *)b->d_a, 2 * b->a_stride, d_peaks, n_blocks, n_blocks, B0,
+                                                            c.in_chunk, c.up, c.down, m0, n_out);
         LAUNCH_CHECK();
         b->launches++;
     }
@@ -1153,9 +1166,10 @@ extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks,
         }
     }
     if (any_real) {
-        dim3 grid((unsigned)n_blocks, (unsigned)c.n_rx);
-        agc_apply_kernel<<<grid, 256, 0, st>>>((const float *)b->d_a, 2 * b->a_stride, b->d_gains, b->max_blocks, d_am, d_am_dc,
-                                               2 * out_stride, kinds, b->pend_B0, c.in_chunk, c.up, c.down, b->pend_m0, n_out);
+        dim3 grid((unsigned)((n_blocks + BLK_WARPS - 1) / BLK_WARPS), (unsigned)c.n_rx);
+        agc_apply_kernel<<<grid, 32 * BLK_WARPS, 0, st>>>((const float *)b->d_a, 2 * b->a_stride, b->d_gains, b->max_blocks, d_am,
+                                                           d_am_dc, 2 * out_stride, kinds, n_blocks, b->pend_B0, c.in_chunk, c.up,
+                                                           c.down, b->pend_m0, n_out);
         LAUNCH_CHECK();
         b->launches++;
     }

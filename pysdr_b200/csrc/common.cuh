@@ -89,6 +89,8 @@ struct FftConvArgs {
     i64 a_stride;
     int mode[PYSDR_MAX_RX];
     u64 bfo_inc[PYSDR_MAX_RX];
+    int ua[PYSDR_MAX_RX];     // work units (filled by fftconv_launch): receiver ua[u], paired with ub[u] (or -1) when both
+    int ub[PYSDR_MAX_RX];     // have a real detector output and real taps: two real convolutions ride one complex FFT
 };
 int fftconv_supported(int L);
 int fftconv_n_for(int L);

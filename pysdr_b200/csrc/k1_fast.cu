@@ -17,8 +17,12 @@
 
 #define K1F_WARPS 12
 #define K1F_THREADS (K1F_WARPS * 32)
+#ifndef K1F_STAGES
 #define K1F_STAGES 3
+#endif
+#ifndef K1F_STAGE_ELEMS
 #define K1F_STAGE_ELEMS 9216          /* float2 per stage: 72 KB */
+#endif
 
 struct FastGeom {
     int S;                 // super-periods per tile

@@ -9,6 +9,7 @@
 // receiver.py:862).  One launch serves all receivers (blockIdx.y = receiver).
 #include "common.cuh"
 #include "fft_smem.cuh"
+#include <cuda_pipeline.h>
 
 template <int N>
 __global__ void __launch_bounds__(FftPlan<N>::THREADS)
@@ -26,51 +27,111 @@ taps_fft_kernel(const float2 *__restrict__ taps, int L, float2 *__restrict__ Hpo
     }
 }
 
+// Stage raw complex memory C[k0 .. k0+N+2) of one receiver into LINEAR shared memory with cp.async (16-byte copies, no
+// registers held, every copy of the CTA in flight at once); samples at or beyond `valid` are zero.
+template <int N, int T>
+__device__ __forceinline__ void k2_stage_raw(float2 *raw, const float2 *__restrict__ C, i64 k0, i64 valid, int tid) {
+    constexpr int CH = (N + 2) / 2;                                       // 16-byte chunks
+    if (k0 + N + 2 <= valid) {                                            // interior block: no bounds checks
+        const float2 *src = C + k0;
+#pragma unroll
+        for (int i = 0; i < CH / T; ++i) __pipeline_memcpy_async(raw + 2 * (tid + i * T), src + 2 * (tid + i * T), 16);
+        if (tid < CH - (CH / T) * T) __pipeline_memcpy_async(raw + 2 * (tid + (CH / T) * T), src + 2 * (tid + (CH / T) * T), 16);
+        return;
+    }
+    for (int c = tid; c < CH; c += T) {
+        const i64 k = k0 + 2 * c;
+        if (k + 1 < valid) {
+            __pipeline_memcpy_async(raw + 2 * c, C + k, 16);
+        } else {
+            raw[2 * c] = (k < valid) ? C[k] : make_float2(0.f, 0.f);
+            raw[2 * c + 1] = make_float2(0.f, 0.f);
+        }
+    }
+}
+
+// detector output for src index k0+e from the staged raw row (raw[e+2] <-> src[k0+e])
+__device__ __forceinline__ float2 k2_detect(const float2 *raw, int e, int mode, bool ok) {
+    if (!ok) return make_float2(0.f, 0.f);
+    const float2 c2 = raw[e + 2];
+    if (mode == PYSDR_MODE_AMSYNC) return make_float2(c2.x, 0.f);              // in-phase arm of the PLL-de-rotated memory
+    if (mode == PYSDR_MODE_AM) return make_float2(sqrtf(c2.x * c2.x + c2.y * c2.y), 0.f);
+    if (mode == PYSDR_MODE_NFM) {
+        const float2 c0 = raw[e], c1 = raw[e + 1];
+        const float dr = c2.x - c0.x, di = c2.y - c0.y;
+        return make_float2(c1.x * di - c1.y * dr, 0.f);                         // nfm.m:126
+    }
+    return c2;
+}
+
 template <int N>
 __global__ void __launch_bounds__(FftPlan<N>::THREADS)
 af_fftconv_kernel(const FftConvArgs a, const float2 *__restrict__ tw) {
     extern __shared__ __align__(16) float2 s[];
     constexpr int T = FftPlan<N>::THREADS;
+    constexpr int PER = N / T;
+    constexpr int HALF = PER / 2;
     const int tid = threadIdx.x;
-    const int rx = blockIdx.y;
+    const int rx = a.ua[blockIdx.y], rxb = a.ub[blockIdx.y];
+    const bool pair = (N == 4096) && rxb >= 0;
     const int mode = a.mode[rx];
-    if (mode == PYSDR_MODE_RAW) return;                                   // no demod filter for this receiver (whole CTA)
     const int L = a.L;
     const int V = N - (L - 1);
     const i64 k0 = (i64)blockIdx.x * V;                                   // first src index of this block
-    const i64 avail = (i64)(L - 1) + a.n_out;                             // valid src samples
-    const float2 *C = a.C + (size_t)rx * a.c_stride;                      // C[k+2] <-> src[k] for complex modes
+    const i64 avail = (i64)(L - 1) + a.n_out;                             // valid src samples; C holds avail + 2
+    const float2 *C = a.C + (size_t)rx * a.c_stride;                      // C[k+2] <-> src[k]
+    float *out = a.out + (size_t)rx * 2 * a.a_stride;
+    float2 *s2 = s + FFT_SMEM_ELEMS(N);                                   // second buffer (N = 4096 launches only)
 
-    // ---- load + fused detection (fully unrolled: all global loads of a thread are in flight together) -------
-    constexpr int PER = N / T;
+    // ---- stage raw samples (async), detect from shared memory, lay out for the FFT ---------------------------------
+    k2_stage_raw<N, T>(s, C, k0, avail + 2, tid);
+    if (pair) k2_stage_raw<N, T>(s2, a.C + (size_t)rxb * a.c_stride, k0, avail + 2, tid);
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    __syncthreads();
     {
-        float2 c0[PER], c1[PER], c2[PER];
+        float2 u[PER];
+        const int modeb = pair ? a.mode[rxb] : 0;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
-            const i64 k = k0 + tid + i * T;
-            c0[i] = c1[i] = c2[i] = make_float2(0.f, 0.f);
-            if (k < avail) {
-                c2[i] = C[k + 2];
-                if (mode == PYSDR_MODE_NFM) { c0[i] = C[k]; c1[i] = C[k + 1]; }
-            }
+            const int e = tid + i * T;
+            const bool ok = k0 + e < avail;
+            u[i] = k2_detect(s, e, mode, ok);
+            if (pair) u[i].y = k2_detect(s2, e, modeb, ok).x;             // two real detector outputs: u = det_a + j det_b
         }
+        __syncthreads();
 #pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            float2 u = c2[i];
-            if (mode == PYSDR_MODE_AMSYNC) {
-                u = make_float2(c2[i].x, 0.f);                           // in-phase arm of the PLL-de-rotated memory
-            } else if (mode == PYSDR_MODE_AM) {
-                u = make_float2(sqrtf(c2[i].x * c2[i].x + c2[i].y * c2[i].y), 0.f);
-            } else if (mode == PYSDR_MODE_NFM) {
-                const float dr = c2[i].x - c0[i].x, di = c2[i].y - c0[i].y;
-                u = make_float2(c1[i].x * di - c1[i].y * dr, 0.f);        // nfm.m:126
-            }
-            s[FFT_PAD(tid + i * T)] = u;
-        }
+        for (int i = 0; i < PER; ++i) s[FFT_PAD(tid + i * T)] = u[i];
     }
     __syncthreads();
     fft_smem<N, false>(s, tid, tw);
-    {
+
+    float2 *sw = s;                                                       // buffer the inverse transform runs in
+    if (pair) {
+        // Z[k] -> Xa[k] = (Z[k] + conj Z[N-k]) / 2,  Xb[k] = (Z[k] - conj Z[N-k]) / 2j;  W = Ha Xa + j Hb Xb  -> s2
+        const float2 *Ha = a.H + (size_t)rx * N, *Hb = a.H + (size_t)rxb * N;
+        sw = s2;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float2 ha[HALF], hb[HALF];
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) {
+                ha[i] = __ldg(Ha + tid + (h * HALF + i) * T);
+                hb[i] = __ldg(Hb + tid + (h * HALF + i) * T);
+            }
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) {
+                const int p = tid + (h * HALF + i) * T;
+                const int kp = (N - fft_pos_to_freq<N>(p)) & (N - 1);
+                const float2 zz = s[FFT_PAD(p)];
+                const float2 zq = s[FFT_PAD(fft_pos_to_freq<N>(kp))];     // digit reversal is an involution for N = 16^3
+                const float2 xa = make_float2(0.5f * (zz.x + zq.x), 0.5f * (zz.y - zq.y));
+                const float2 xb = make_float2(0.5f * (zz.y + zq.y), -0.5f * (zz.x - zq.x));
+                const float2 ya = cmul(xa, ha[i]), yb = cmul(xb, hb[i]);
+                s2[FFT_PAD(p)] = make_float2(ya.x - yb.y, ya.y + yb.x);
+            }
+        }
+    } else {
         const float2 *H = a.H + (size_t)rx * N;
         float2 h[PER];
 #pragma unroll
@@ -82,22 +143,37 @@ af_fftconv_kernel(const FftConvArgs a, const float2 *__restrict__ tw) {
         }
     }
     __syncthreads();
-    fft_smem<N, true>(s, tid, tw);
+    fft_smem<N, true>(sw, tid, tw);
 
-    // ---- store the V valid outputs -----------------------------------------------------------------------
-    float *out = a.out + (size_t)rx * 2 * a.a_stride;
-    for (int e = (L - 1) + tid; e < N; e += T) {
-        const i64 o = k0 + e - (L - 1);
-        if (o >= a.n_out) break;
-        const float2 c = s[FFT_PAD(e)];
-        if (mode == PYSDR_MODE_IQ) {
-            ((float2 *)out)[o] = c;
-        } else if (mode == PYSDR_MODE_CW) {
-            const float2 cs = nco_cs(a.bfo_inc[rx] * (u64)(a.m0 + o));
-            out[o] = c.x * cs.x - c.y * cs.y;                             // Re{ z * e^{+j th} }
-        } else {
-            out[o] = c.x;
+    // ---- store the valid outputs of this block (32-bit loop, pointers hoisted) -----------------------------------
+    const i64 left = a.n_out - k0;
+    const int lim = left < (i64)V ? (int)left : V;
+    const float2 *sv = sw;
+    float *o0 = out + k0;
+    if (pair) {
+        float *o1 = a.out + (size_t)rxb * 2 * a.a_stride + k0;
+#pragma unroll 4
+        for (int j = tid; j < lim; j += T) {
+            const float2 c = sv[FFT_PAD(j + L - 1)];
+            o0[j] = c.x;
+            o1[j] = c.y;
         }
+    } else if (mode == PYSDR_MODE_IQ) {
+        float2 *oc = (float2 *)out + k0;
+#pragma unroll 4
+        for (int j = tid; j < lim; j += T) oc[j] = sv[FFT_PAD(j + L - 1)];
+    } else if (mode == PYSDR_MODE_CW) {
+        const u64 inc = a.bfo_inc[rx];
+        const u64 ph0 = inc * (u64)(a.m0 + k0);
+#pragma unroll 4
+        for (int j = tid; j < lim; j += T) {
+            const float2 c = sv[FFT_PAD(j + L - 1)];
+            const float2 cs = nco_cs(ph0 + inc * (u64)j);
+            o0[j] = c.x * cs.x - c.y * cs.y;                              // Re{ z * e^{+j th} }
+        }
+    } else {
+#pragma unroll 4
+        for (int j = tid; j < lim; j += T) o0[j] = sv[FFT_PAD(j + L - 1)].x;
     }
 }
 
@@ -129,11 +205,30 @@ int fftconv_prepare_taps(const float2 *d_taps, int L, float2 *d_H, cudaStream_t 
 }
 
 template <int N>
-static int fftconv_launch_n(const FftConvArgs &a, int n_rx, cudaStream_t st) {
-    const size_t smem = sizeof(float2) * FFT_SMEM_ELEMS(N);
+static int fftconv_launch_n(const FftConvArgs &a0, int n_rx, cudaStream_t st) {
+    const size_t smem = sizeof(float2) * FFT_SMEM_ELEMS(N) * (N == 4096 ? 2 : 1);     // paired units use a second buffer
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(af_fftconv_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // work units: RAW rows have no demod filter; real-detector rows (AM / NFM / AM-Synch) pair up when the transform's
+    // digit reversal is an involution (N = 16^3), everything else runs alone
+    FftConvArgs a = a0;
+    int n_units = 0, open_unit = -1;
+    for (int r = 0; r < n_rx; ++r) {
+        const int m = a.mode[r];
+        if (m == PYSDR_MODE_RAW) continue;
+        const bool real_det = (m == PYSDR_MODE_AM || m == PYSDR_MODE_NFM || m == PYSDR_MODE_AMSYNC);
+        if (real_det && N == 4096 && open_unit >= 0) {
+            a.ub[open_unit] = r;
+            open_unit = -1;
+            continue;
+        }
+        a.ua[n_units] = r;
+        a.ub[n_units] = -1;
+        if (real_det && N == 4096) open_unit = n_units;
+        ++n_units;
+    }
+    if (n_units == 0) return PYSDR_OK;
     const int V = N - (a.L - 1);
-    dim3 grid((unsigned)((a.n_out + V - 1) / V), (unsigned)n_rx);
+    dim3 grid((unsigned)((a.n_out + V - 1) / V), (unsigned)n_units);
     const float2 *tw = fft_twiddles(N);
     if (!tw) { pysdr_set_error("fft twiddle table allocation failed"); return PYSDR_ERR_CUDA; }
     af_fftconv_kernel<N><<<grid, FftPlan<N>::THREADS, smem, st>>>(a, tw);
