@@ -277,33 +277,13 @@ def run_own(args):
     # ---- e2e: host buffers through the same bank API, H2D and D2H inside the timed region ---------------
     e2e = None
     if not args.no_e2e:
-        seg_chunks = 64
-        segs = [(s, min(n_chunks, s + seg_chunks)) for s in range(0, n_chunks, seg_chunks)]
+        from pysdr_b200.receiver import ReplayStreamer
+        streamer = ReplayStreamer(P, seg_chunks=64, device=dev)              # the public host-buffer API
         hx = torch.empty(n, dtype=torch.complex64, pin_memory=True)
         hx.copy_(x_main)                                                    # untimed: the capture lives on the host
-        n_out_max = (P.UP * seg_chunks * C) // P.DOWN + 2
-        h_am = torch.empty((len(segs), 4, n_out_max), dtype=torch.float32, pin_memory=True)
-        dbuf = [torch.empty(seg_chunks * C, dtype=torch.complex64, device=dev) for _ in range(2)]
-        ebank = ReceiverBank(P, offs, max_in=seg_chunks * C, device=dev)
-        cp, cs = torch.cuda.Stream(device=dev), torch.cuda.current_stream()
-        ready = [torch.cuda.Event() for _ in range(2)]
-        freed = [torch.cuda.Event() for _ in range(2)]
 
         def e2e_step():
-            ebank.seek(0)                                                   # each GPU replays its own host capture
-            for i, (a, b) in enumerate(segs):
-                k = i & 1
-                with torch.cuda.stream(cp):
-                    if i >= 2:
-                        cp.wait_event(freed[k])
-                    dbuf[k][:(b - a) * C].copy_(hx[a * C:b * C], non_blocking=True)
-                    ready[k].record(cp)
-                cs.wait_event(ready[k])
-                am, _, _ = ebank.process(dbuf[k][:(b - a) * C], want_dc=False)
-                freed[k].record(cs)
-                no = ebank.n_out
-                h_am[i, :, :no].copy_(ebank._am[:, :no], non_blocking=True)
-            cs.synchronize()
+            h_am, _ = streamer.run(hx)                                      # each GPU replays its own host capture
             return float(h_am[0, 0, 0])                                     # host read of the step's result
 
         for _ in range(2):
@@ -324,7 +304,7 @@ def run_own(args):
                "d2h_bytes_per_step": int(4 * n_out_tot * 4), "steps": ksteps,
                "how": "pinned host complex64 capture -> 64-chunk segments double-buffered H2D on a copy stream -> "
                       "bank.process -> audio D2H to pinned host, per GPU"}
-        del hx, h_am, dbuf, ebank
+        del hx, streamer
 
     if rank != 0:
         if world > 1:

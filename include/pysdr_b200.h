@@ -198,6 +198,13 @@ int pysdr_waterfall_push(float *d_wf, int32_t nfft, int32_t ncols, int32_t cnt, 
                          int32_t npsd, int32_t roll_bins, float pan_dr, float *d_img, float *d_bkgnd,
                          float *d_scratch, void *stream);
 
+/* Colour mapping of the waterfall image (reference Plotting.py:139-142: 256-entry 'jet' lookup table on the image
+ * item): d_rgba[i] = lut[round(255*(img[i]-lo)/(hi-lo))], [lo,hi] = [max-pan_dr, max] as left by
+ * pysdr_waterfall_push in d_scratch/d_bkgnd.  d_lut256: 256 x RGBA8, d_rgba: n x RGBA8. */
+int pysdr_waterfall_rgba(const float *d_img, int64_t n, const float *d_bkgnd, const float *d_scratch,
+                         int32_t nfft, int32_t ncols, float pan_dr, const void *d_lut256, void *d_rgba,
+                         void *stream);
+
 #ifdef __cplusplus
 }
 #endif

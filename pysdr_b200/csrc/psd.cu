@@ -280,6 +280,34 @@ __global__ void wf_image_kernel(const float *__restrict__ wf, i64 n, const float
     for (; i < n; i += stride) img[i] = fmaxf(wf[i] - b, floor_v);
 }
 
+// image -> RGBA through a 256-entry lookup table (reference Plotting.py:139-142 `img.setLookupTable(lut)`; levels are
+// the image's own [lo, hi] = [max - PAN_DR, max] after the clip of Plotting.py:618-626).
+__global__ void wf_rgba_kernel(const float *__restrict__ img, i64 n, const float *__restrict__ bk, const float *__restrict__ mx,
+                               float pan_dr, const uchar4 *__restrict__ lut, uchar4 *__restrict__ rgba) {
+    __shared__ uchar4 s_lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut[i];
+    __syncthreads();
+    const float hi = mx[0] - bk[0], lo = hi - pan_dr;
+    const float sc = pan_dr > 0.f ? 255.0f / pan_dr : 0.f;
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int k = (int)floorf((img[i] - lo) * sc + 0.5f);
+        k = k < 0 ? 0 : (k > 255 ? 255 : k);
+        rgba[i] = s_lut[k];
+    }
+}
+
+extern "C" int pysdr_waterfall_rgba(const float *d_img, int64_t n, const float *d_bkgnd, const float *d_scratch, int32_t nfft,
+                                    int32_t ncols, float pan_dr, const void *d_lut256, void *d_rgba, void *stream) {
+    if (!d_img || !d_bkgnd || !d_scratch || !d_lut256 || !d_rgba || n < 0) { pysdr_set_error("waterfall_rgba: bad arguments"); return PYSDR_ERR_ARG; }
+    if (n == 0) return PYSDR_OK;
+    const float *mx = d_scratch + (size_t)nfft * ncols + nfft;           // where pysdr_waterfall_push left max(wf)
+    wf_rgba_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(d_img, n, d_bkgnd, mx, pan_dr, (const uchar4 *)d_lut256, (uchar4 *)d_rgba);
+    LAUNCH_CHECK();
+    return PYSDR_OK;
+}
+
 extern "C" int pysdr_waterfall_push(float *d_wf, int32_t nfft, int32_t ncols, int32_t cnt, const float *d_line, int32_t npsd,
                                     int32_t roll_bins, float pan_dr, float *d_img, float *d_bkgnd, float *d_scratch, void *stream) {
     // d_scratch: nfft*ncols (shifted copy) + nfft (row means) + 2 floats

@@ -14,6 +14,34 @@ from ._lib import check
 from .bank import _stream_ptr
 
 
+def jet(m=64):
+    """The Matlab 'jet' colormap the reference tabulates (Tables.py:144-145, 64 RGBA rows), from its defining ramp."""
+    n = int(np.ceil(m / 4.0))
+    u = np.concatenate((np.arange(1, n + 1) / n, np.ones(n - 1), np.arange(n, 0, -1) / n))
+    g = int(np.ceil(n / 2.0)) - (m % 4 == 1) + np.arange(1, len(u) + 1)
+    r, b = g + n, g - n
+    J = np.zeros((m, 3))
+    gi = g[g <= m]
+    J[gi - 1, 1] = u[:len(gi)]
+    ri = r[r <= m]
+    J[ri - 1, 0] = u[:len(ri)]
+    bi = b[b >= 1]
+    J[bi - 1, 2] = u[len(u) - len(bi):]
+    out = np.full((m, 4), 255, np.uint8)
+    out[:, :3] = np.floor(J * 255.0 + 0.5).astype(np.uint8)
+    return out
+
+
+def lookup_table(colors, npts=256):
+    """ColorMap(pos=linspace(0,1,len), colors).getLookupTable(0, 1, npts): linear interpolation, ubyte
+    (reference Plotting.py:139-141)."""
+    colors = np.asarray(colors, np.float64)
+    pos = np.linspace(0.0, 1.0, len(colors))
+    x = np.linspace(0.0, 1.0, npts)
+    lut = np.stack([np.interp(x, pos, colors[:, c]) for c in range(colors.shape[1])], axis=1)
+    return lut.astype(np.uint8)
+
+
 class three_box_compute:
     def __init__(self, P, fs, foff, chunk_size, Nfft, overlap, ncols=100):
         self.P = P
@@ -34,6 +62,18 @@ class three_box_compute:
         self.wf_cnt = 0
         self.wf_fc = 0
         self.pk_frqs = np.zeros(0)
+        self.lut = torch.from_numpy(lookup_table(jet(64), 256)).to(dev)                # Plotting.py:139-141
+        self.rgba = torch.empty((n, ncols, 4), dtype=torch.uint8, device=dev)
+
+    def image_rgba(self, npsd=None):
+        """RGBA8 waterfall image of the last plot() through the jet lookup table, on the device."""
+        n = self.psd.NFFT if npsd is None else int(npsd)
+        check(self.lib.pysdr_waterfall_rgba(ctypes.c_void_p(self.img.data_ptr()), n * self.ncols,
+                                            ctypes.c_void_p(self.bk.data_ptr()), ctypes.c_void_p(self.scratch.data_ptr()),
+                                            self.psd.NFFT, self.ncols, float(self.P.PAN_DR),
+                                            ctypes.c_void_p(self.lut.data_ptr()), ctypes.c_void_p(self.rgba.data_ptr()),
+                                            _stream_ptr()))
+        return self.rgba[:n]
 
     def plot(self, y, fc):
         """One display frame (Plotting.py:444-631): returns dict(frq, PSD, image, bkgnd, peaks, pk_frqs)

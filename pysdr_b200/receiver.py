@@ -77,3 +77,76 @@ def demod_capture(P, x_dev, bank=None, want_dc=False):
         bank = ReceiverBank(P, receiver_offsets(P), max_in=int(x_dev.numel()))
     am, iq, dc = bank.process(x_dev, want_dc=want_dc)
     return bank, am, iq, dc
+
+
+class ReplayStreamer:
+    """Host-resident capture -> audio, the L2 executive on GPU streams: the capture stays in
+    pinned host memory and is fed in segments of `seg_chunks` IN_CHUNK_SIZE blocks through two device buffers — the
+    H2D copy of segment i+1 (copy stream) overlaps the kernels of segment i (compute stream) — and each segment's
+    audio is copied back to pinned host memory asynchronously.  Same numbers as chunk-at-a-time `demod_data`
+    (per-block semantics are defined on absolute block indices); MP_SCHEME 3's broadcast + barrier collapses to one
+    process per GPU."""
+
+    def __init__(self, P, seg_chunks=64, device=None, want_iq=False):
+        self.P = P
+        self.C = int(P.IN_CHUNK_SIZE)
+        self.seg_chunks = int(seg_chunks)
+        self.bank = ReceiverBank(P, receiver_offsets(P), max_in=self.seg_chunks * self.C, device=device)
+        dev = self.bank.device
+        self.dbuf = [torch.empty(self.seg_chunks * self.C, dtype=torch.complex64, device=dev) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.freed = [torch.cuda.Event() for _ in range(2)]
+        self.want_iq = want_iq
+        self.h_am = self.h_iq = None
+        self.n_out_seg = []
+
+    def pin(self, raw):
+        """Pinned copy of a host capture (numpy complex64 or CPU tensor)."""
+        t = torch.from_numpy(np.ascontiguousarray(raw, np.complex64)) if isinstance(raw, np.ndarray) else raw
+        return t if t.is_pinned() else t.pin_memory()
+
+    def run(self, hx, start_sample=0):
+        """hx: pinned CPU complex64 tensor holding whole chunks.  Returns (h_am, n_out_per_segment): pinned float32
+        [n_segments, n_rx, n_out_max] (complex receivers: interleaved re/im in 2*n_out floats)."""
+        C, sc, bank = self.C, self.seg_chunks, self.bank
+        n_chunks = hx.numel() // C
+        segs = [(s, min(n_chunks, s + sc)) for s in range(0, n_chunks, sc)]
+        n_out_max = 2 * ((int(self.P.UP) * sc * C) // int(self.P.DOWN) + 2)
+        if self.h_am is None or self.h_am.shape[0] < len(segs):
+            self.h_am = torch.empty((len(segs), bank.n_rx, n_out_max), dtype=torch.float32, pin_memory=True)
+            if self.want_iq:
+                self.h_iq = torch.empty((len(segs), bank.n_rx, n_out_max // 2), dtype=torch.complex64, pin_memory=True)
+        cs = torch.cuda.current_stream(bank.device)
+        cp = self.copy_stream
+        cp.wait_stream(cs)
+        bank.seek(start_sample)
+        self.n_out_seg = []
+        any_cplx = any(bank._mode_of(r) in ('IQ', 'RTTY') for r in range(bank.n_rx))
+        for i, (a, b) in enumerate(segs):
+            k = i & 1
+            with torch.cuda.stream(cp):
+                if i >= 2:
+                    cp.wait_event(self.freed[k])
+                self.dbuf[k][:(b - a) * C].copy_(hx[a * C:b * C], non_blocking=True)
+                self.ready[k].record(cp)
+            cs.wait_event(self.ready[k])
+            bank.process(self.dbuf[k][:(b - a) * C], want_dc=False)
+            self.freed[k].record(cs)
+            no = bank.n_out
+            self.n_out_seg.append(no)
+            w = 2 * no if any_cplx else no                      # complex receivers (IQ/RTTY) use 2 floats per sample
+            self.h_am[i, :, :w].copy_(bank._am[:, :w], non_blocking=True)
+            if self.want_iq:
+                self.h_iq[i, :, :no].copy_(bank._iq[:, :no], non_blocking=True)
+        cs.synchronize()
+        return self.h_am, self.n_out_seg
+
+    def audio(self, irx):
+        """Concatenated host audio of receiver irx from the last run (float32, complex64 for IQ/RTTY)."""
+        cplx = self.bank._mode_of(irx) in ('IQ', 'RTTY')
+        parts = []
+        for i, no in enumerate(self.n_out_seg):
+            row = self.h_am[i, irx]
+            parts.append(row[:2 * no].numpy().view(np.complex64).copy() if cplx else row[:no].numpy().copy())
+        return np.concatenate(parts) if parts else np.zeros(0, np.float32)

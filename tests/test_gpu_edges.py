@@ -188,6 +188,16 @@ def test_three_box_compute_matches_plotting_py_algebra():
             assert len(out['peaks']) >= 1 and abs(int(out['peaks'][np.argmax(out['PSD'][out['peaks']])]) -
                                                   int(pk_ref[np.argmax(PSDo[pk_ref])])) <= 1
         np.testing.assert_allclose(out['image'].cpu().numpy(), img_ref, rtol=0, atol=5e-2)
+    # RGBA through the jet lookup table (Plotting.py:139-142): same index law on the host
+    from pysdr_b200.plotting import jet, lookup_table
+    rgba = tb.image_rgba().cpu().numpy()
+    img = out['image'].cpu().numpy()
+    hi = img.max()
+    idx = np.clip(np.floor((img - (hi - P.PAN_DR)) * (255.0 / P.PAN_DR) + 0.5), 0, 255).astype(int)
+    want = lookup_table(jet(64), 256)[idx]
+    assert rgba.shape == want.shape == (2048, 100, 4)
+    assert np.mean(np.any(rgba != want, axis=-1)) < 1e-3         # LUT index ties at float rounding only
+    assert np.abs(rgba.astype(int) - want.astype(int)).max() <= 8
 
 
 @pytest.mark.parametrize("deemph", [0, 75])
@@ -379,3 +389,28 @@ def test_many_channel_bank_cfg5_geometry():
         orx = odsp.Receiver(Pk, offs[k], 0, str(k), fast=True)
         ref = np.concatenate([np.array(orx.demod_data(x[c * C:(c + 1) * C])) for c in range(2)])
         assert_parity(am[k].cpu().numpy(), ref, "channel %d (%s)" % (k, modes[k]), rel_tol=2e-4, snr_min=74)
+
+
+def test_replay_streamer_equals_resident_processing():
+    """Host capture through the double-buffered streaming executive == the same capture processed resident."""
+    from pysdr_b200.receiver import ReplayStreamer, receiver_offsets
+    P, _ = make_both(8, [-500, 700, 1400], ['AM', 'IQ', 'USB'], af_bw_khz=[5, 45, 2])
+    C = P.IN_CHUNK_SIZE
+    n_chunks = 11
+    x = _noise(n_chunks * C, 8, 0.05)
+    bank = _bank(P, n_chunks * C)
+    am, iq, _ = bank.process(torch.from_numpy(x).cuda(), want_dc=False)
+    st = ReplayStreamer(P, seg_chunks=4, want_iq=True)           # segments of 4, 4 and 3 chunks
+    hx = st.pin(x)
+    for _ in range(2):                                           # second run reuses buffers and restarts the stream
+        h_am, n_seg = st.run(hx)
+        assert len(n_seg) == 3 and sum(n_seg) == bank.n_out
+        for r in range(3):
+            got = st.audio(r)
+            ref = am[r].cpu().numpy()
+            assert got.dtype == ref.dtype and len(got) == len(ref)
+            assert_parity(got, ref, "streamed rx%d" % r, rel_tol=2e-5, snr_min=90)
+    pos = 0
+    for i, no in enumerate(n_seg):
+        assert np.array_equal(st.h_iq[i, 0, :no].numpy(), iq[0][pos:pos + no].cpu().numpy())     # K1 bit-exact
+        pos += no

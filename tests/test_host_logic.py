@@ -137,3 +137,16 @@ def test_no_gpu_fails_loudly():
         Receiver(P, 1e5, 0, '1')
     with pytest.raises(PysdrError):
         spectrum(48., 4096, 8192, 0.5)
+
+
+def test_jet_colormap_reproduces_reference_table():
+    """PINNED: pysdr_b200.plotting.jet(64) equals the 64 x RGBA 'jet' table of reference Tables.py:144-145 (checked
+    against the file in the build container; the digest of that table is recorded here)."""
+    import hashlib
+    from pysdr_b200.plotting import jet, lookup_table
+    J = jet(64)
+    assert J.shape == (64, 4) and J.dtype == np.uint8
+    assert hashlib.sha256(J.tobytes()).hexdigest() == "69ec14a091bab52cd725198c0809d867d1532822a1783a8102f5a0dc679cd523"
+    assert list(J[0]) == [0, 0, 143, 255] and list(J[7]) == [0, 0, 255, 255] and list(J[8]) == [0, 16, 255, 255]
+    lut = lookup_table(J, 256)
+    assert lut.shape == (256, 4) and np.array_equal(lut[0], J[0]) and np.array_equal(lut[-1], J[-1])
