@@ -319,7 +319,30 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
             if (last) done_cnt[st] = 0;
         }
         last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) produce(T + (i64)K1F_STAGES * Tstep, st);
+        if (last) {
+            // Interior tiles (almost all): the refill is one aligned bulk copy whose address follows from the running
+            // tile offset — no 64-bit multiplies and no edge loop on the warp that is already the last one
+            // (0.859 -> 0.842 ms at cfg2).  Measured and rejected here: an extra cp.async.bulk.prefetch.L2 one, two or
+            // four tiles ahead (0.865 ms), and consuming the arrival count one task later (0.965 ms).
+            const i64 Tn = T + (i64)K1F_STAGES * Tstep;
+            if (Tn < g.n_tiles) {
+                const i64 rel_n = relb + (i64)K1F_STAGES * d_rel;
+                const i64 ar = rel_n - need_pad;
+                const i64 a2 = ar - ((ar + par) & 1);
+                const int cnt = (int)(rel_n + (i64)S * down - a2);
+                const int cnt2 = cnt + (cnt & 1);
+                if (a2 >= 0 && a2 + cnt2 <= a.n_in) {
+                    if (lane == 0) {
+                        const unsigned bar = smem_u32(&bars[st]);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        mbar_expect_tx(bar, (unsigned)cnt2 * 8u);
+                        bulk_g2s(smem_u32(stage0 + (size_t)st * K1F_STAGE_ELEMS), a.x + a2, (unsigned)cnt2 * 8u, bar);
+                    }
+                } else {
+                    produce(Tn, st);
+                }
+            }
+        }
         relb += d_rel; ob += d_ob; pbase += d_ph;
         st = (st + 1 == K1F_STAGES) ? 0 : st + 1;
     }
