@@ -191,6 +191,21 @@ int64_t pysdr_psd_launch_count(const pysdr_psd *p);
 #define PYSDR_PSD_FLIP 2
 int pysdr_psd_configure(pysdr_psd *p, int32_t sub, const int32_t *sub_off, int32_t flags);
 
+/* Transform lengths that are not a power of two (or exceed 16384) — the reference's RF panel uses chunk 32818 /
+ * NFFT 65636 (Plotting.py:370-375) — go through Bluestein's chirp-z identity on a 2^17-point four-step FFT (czt.cu).
+ * Tables come from the host in float64-derived complex64: wc[n] = w[n]*conj(b[n]) (chunk entries), bspec = FFT_M of
+ * the wrapped chirp b[m] = exp(j*pi*m^2/nfft) divided by M, laid out [512][256] in the transforms' position order
+ * (pysdr_fft_pos_to_freq gives the bin of a position).  Same frame / averaging / dB / fftshift contract as
+ * pysdr_psd_lines.  Requires nfft + chunk - 1 <= 131072. */
+typedef struct pysdr_czt pysdr_czt;
+int pysdr_fft_pos_to_freq(int nfft, int pos);
+int pysdr_czt_create(int32_t chunk_size, int32_t nfft, int32_t hop, const float *window_host,
+                     const float *wc_host, const float *bspec_host, pysdr_czt **out);
+int pysdr_czt_destroy(pysdr_czt *p);
+int pysdr_czt_lines(pysdr_czt *p, const void *d_x, int64_t n, int is_complex, int32_t navg, int dB,
+                    float *d_out, int64_t *n_lines, void *stream);
+int64_t pysdr_czt_launch_count(const pysdr_czt *p);
+
 /* ---- a12: three_box_plot waterfall compute (reference Plotting.py:536-548,583-587,618-626,689-695)
  * d_wf float32[nfft][ncols] state; shift-in one line, optional roll by nbins, background =
  * median(mean(wf[:, -cnt:],1)) -> *d_bkgnd, image = max(wf-bkgnd, max(wf-bkgnd)-pan_dr) -> d_img. */

@@ -77,6 +77,11 @@ SIGNATURES = {
     "pysdr_psd_lines": (c_int, [c_vp, c_vp, c_i64, c_int, ctypes.c_int32, c_int, c_vp, ctypes.POINTER(c_i64), c_vp]),
     "pysdr_psd_launch_count": (c_i64, [c_vp]),
     "pysdr_waterfall_rgba": (c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_float, c_vp, c_vp, c_vp]),
+    "pysdr_fft_pos_to_freq": (c_int, [c_int, c_int]),
+    "pysdr_czt_create": (c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)]),
+    "pysdr_czt_destroy": (c_int, [c_vp]),
+    "pysdr_czt_lines": (c_int, [c_vp, c_vp, c_i64, c_int, ctypes.c_int32, c_int, c_vp, ctypes.POINTER(c_i64), c_vp]),
+    "pysdr_czt_launch_count": (c_i64, [c_vp]),
     "pysdr_psd_configure": (c_int, [c_vp, ctypes.c_int32, c_vp, ctypes.c_int32]),
     "pysdr_waterfall_push": (c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_vp, ctypes.c_int32,
                                      ctypes.c_int32, ctypes.c_float, c_vp, c_vp, c_vp, c_vp]),

@@ -214,6 +214,23 @@ class _PView:
 
 
 # ---------------------------------------------------------------------------------------------------
+def _czt_tables(lib, win, chunk, nfft, M):
+    """Bluestein tables for czt.cu (float64 on the host, stored complex64): wc[n] = w[n] conj(b[n]) and the spectrum of
+    the wrapped chirp b[m] = exp(j pi m^2 / nfft), m in [-(chunk-1), nfft-1], divided by M, in [512][256] position order."""
+    def chirp(m):
+        m = np.asarray(m, np.int64)
+        return np.exp(1j * np.pi * ((m * m) % (2 * nfft)).astype(np.float64) / nfft)
+    wc = (np.asarray(win, np.float64) * np.conj(chirp(np.arange(chunk)))).astype(np.complex64)
+    m = np.arange(-(chunk - 1), nfft)
+    bpad = np.zeros(M, np.complex128)
+    bpad[m % M] = chirp(m)
+    B = np.fft.fft(bpad) / M
+    k1 = np.array([lib.pysdr_fft_pos_to_freq(512, p) for p in range(512)], np.int64)
+    k2 = np.array([lib.pysdr_fft_pos_to_freq(256, q) for q in range(256)], np.int64)
+    bspec = B[k1[:, None] + 512 * k2[None, :]].astype(np.complex64)
+    return np.ascontiguousarray(wc), np.ascontiguousarray(bspec)
+
+
 class spectrum:
     """``dsp.spectrum(fs, chunk_size, NFFT, overlap, TAG=)`` (reference Plotting.py:376-377); attributes
     ``NFFT frq frq2 df fs chunk_size new_samps`` (Plotting.py:467,594,690; gui.py:1259,1289-1290,1369)."""
@@ -232,19 +249,28 @@ class spectrum:
         self.frq = (np.arange(self.NFFT) - self.NFFT // 2) * self.df
         self.frq2 = self.frq
         self.device = _dev()
-        if self.NFFT & (self.NFFT - 1):
-            raise PysdrError("spectrum: NFFT=%d is not a power of two (the reference's 65636-point RF panel, "
-                             "Plotting.py:370-375, is not served yet)" % self.NFFT)
         h = ctypes.c_void_p()
-        check(self.lib.pysdr_psd_create(self.chunk_size, self.NFFT, max(1, self.new_samps),
-                                        self.win.ctypes.data_as(ctypes.c_void_p), ctypes.byref(h)))
+        self.czt = bool(self.NFFT & (self.NFFT - 1)) or self.NFFT > 16384 or self.NFFT < 64
+        if self.czt:
+            # e.g. the reference's RF panel: chunk 32818, NFFT 65636 = 4*61*269 (Plotting.py:370-375) -> chirp-z (czt.cu)
+            M = 131072
+            if self.NFFT + self.chunk_size - 1 > M:
+                raise PysdrError("spectrum: NFFT=%d with chunk_size=%d exceeds the 2^17-point chirp-z transform"
+                                 % (self.NFFT, self.chunk_size))
+            wc, bspec = _czt_tables(self.lib, self.win, self.chunk_size, self.NFFT, M)
+            check(self.lib.pysdr_czt_create(self.chunk_size, self.NFFT, max(1, self.new_samps),
+                                            self.win.ctypes.data_as(ctypes.c_void_p), wc.ctypes.data_as(ctypes.c_void_p),
+                                            bspec.ctypes.data_as(ctypes.c_void_p), ctypes.byref(h)))
+        else:
+            check(self.lib.pysdr_psd_create(self.chunk_size, self.NFFT, max(1, self.new_samps),
+                                            self.win.ctypes.data_as(ctypes.c_void_p), ctypes.byref(h)))
         self.h = h
         self.buf = torch.zeros(self.chunk_size, dtype=torch.complex64, device=self.device)
 
     def __del__(self):
         try:
             if getattr(self, "h", None):
-                self.lib.pysdr_psd_destroy(self.h)
+                (self.lib.pysdr_czt_destroy if self.czt else self.lib.pysdr_psd_destroy)(self.h)
                 self.h = None
         except Exception:
             pass
@@ -260,8 +286,9 @@ class spectrum:
         nl = nfr // navg
         out = torch.empty((max(nl, 1), self.NFFT), dtype=torch.float32, device=self.device)
         got = ctypes.c_int64(0)
-        check(self.lib.pysdr_psd_lines(self.h, ctypes.c_void_p(x.data_ptr()), n, 1, int(navg), 1 if dB else 0,
-                                       ctypes.c_void_p(out.data_ptr()), ctypes.byref(got), _stream_ptr()))
+        fn = self.lib.pysdr_czt_lines if self.czt else self.lib.pysdr_psd_lines
+        check(fn(self.h, ctypes.c_void_p(x.data_ptr()), n, 1, int(navg), 1 if dB else 0,
+                 ctypes.c_void_p(out.data_ptr()), ctypes.byref(got), _stream_ptr()))
         return out[:got.value]
 
     def periodogram(self, y, dB=True):

@@ -82,8 +82,8 @@ def test_error_codes_are_loud():
     with pytest.raises(PysdrError, match="WFM"):
         bank.process(torch.zeros(P.IN_CHUNK_SIZE, dtype=torch.complex64, device="cuda"))
     import pysdr_b200.sig_proc as dsp
-    with pytest.raises(PysdrError, match="power of two"):
-        dsp.spectrum(8000., 32818, 65636, 0.)                                      # Plotting.py:370-375 geometry
+    with pytest.raises(PysdrError, match="chirp-z"):
+        dsp.spectrum(8000., 70000, 140000, 0.)                                     # beyond the 2^17-point chirp-z transform
     sp = dsp.spectrum(48., 4096, 8192, 0.5)
     assert len(sp.psd_est(np.zeros(100, np.complex64), True)) == 0                 # shorter than one frame -> []
     rx = dsp.Receiver(make_both(2.048, [1000], ['USB'])[0], 1e5, 0, '1')
@@ -414,3 +414,27 @@ def test_replay_streamer_equals_resident_processing():
     for i, no in enumerate(n_seg):
         assert np.array_equal(st.h_iq[i, 0, :no].numpy(), iq[0][pos:pos + no].cpu().numpy())     # K1 bit-exact
         pos += no
+
+
+@pytest.mark.parametrize("chunk,nfft,overlap", [(32818, 65636, 0.0), (1000, 3000, 0.5), (32768, 65536, 0.5), (30, 45, 0.0)])
+def test_spectrum_non_power_of_two_nfft_chirp_z(chunk, nfft, overlap):
+    """The reference's RF panel geometry (Plotting.py:370-375: chunk 32818, NFFT 65636 = 4*61*269) and other lengths the
+    radix-16 transforms do not cover, through Bluestein's identity on the 2^17-point four-step FFT; oracle = numpy fft."""
+    import pysdr_b200.sig_proc as dsp
+    sp = dsp.spectrum(8000., chunk, nfft, overlap)
+    so = odsp.spectrum(8000., chunk, nfft, overlap)
+    assert sp.czt and np.array_equal(sp.frq, so.frq)
+    hop = max(1, int(chunk * (1 - overlap)))
+    n = chunk + 5 * hop + 7
+    t = np.arange(n)
+    x = (_noise(n, 12, 0.02).astype(np.complex128) + 0.3 * np.exp(2j * np.pi * 0.1234 * t)
+         + 0.05 * np.exp(-2j * np.pi * 0.37 * t)).astype(np.complex64)
+    lin, ref = sp.psd_est(x, False), so.psd_est(x, False)
+    assert lin.shape == ref.shape == (nfft,)
+    assert_parity(lin, ref, "czt psd %d/%d" % (chunk, nfft), rel_tol=1e-4, snr_min=80)
+    wf, wref = sp.waterfall(x, 2, False), so.waterfall(x, 2, False)
+    assert wf.shape == wref.shape == (3, nfft)
+    assert_parity(wf, wref, "czt waterfall", rel_tol=1e-4, snr_min=80)
+    one, oref = sp.periodogram(x[:chunk], True), so.periodogram(x[:chunk], True)
+    top = oref > oref.max() - 60
+    assert np.max(np.abs(one - oref)[top]) < 5e-3                                  # dB, within 60 dB of the peak
