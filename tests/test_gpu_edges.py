@@ -438,3 +438,34 @@ def test_spectrum_non_power_of_two_nfft_chirp_z(chunk, nfft, overlap):
     one, oref = sp.periodogram(x[:chunk], True), so.periodogram(x[:chunk], True)
     top = oref > oref.max() - 60
     assert np.max(np.abs(one - oref)[top]) < 5e-3                                  # dB, within 60 dB of the peak
+
+
+def test_replay_from_capture_file_through_streamer(tmp_path):
+    """-replay end to end: capture file -> pinned read -> rates from the file header (receiver.py:808-822) ->
+    streaming executive -> demod file; against the oracle loop on the same samples."""
+    from pysdr_b200.fileio import sdr_fileio, open_replay
+    from pysdr_b200.receiver import ReplayStreamer
+    Pw, _ = make_both(2.048, [1000], ['USB'], af_bw_khz=[2])
+    Pw.SAVE_DIR = str(tmp_path)
+    C = Pw.IN_CHUNK_SIZE
+    x = _noise(6 * C, 14, 0.05)
+    w = sdr_fileio('raw_iq', 'w', Pw, 2, 'RAW_IQ')
+    w.save_data(x); w.close()
+    P, Po = make_both(8, [1000], ['USB'], af_bw_khz=[2])         # started with another rate: the file decides
+    open_replay(P, w.fname)
+    assert P.IN_CHUNK_SIZE == C and P.SRATE == 2.048e6
+    st = ReplayStreamer(P, seg_chunks=4)
+    hx = P.sdr.read_data(pinned=True)
+    assert hx.is_pinned() and hx.numel() == 6 * C
+    st.run(hx)
+    got = st.audio(0)
+    from pysdr_b200.receiver import receiver_offsets
+    Po2 = rxo.make_P(2.048e6, [1000e3], 'USB', foffset=100e3, af_bw=2e3)
+    # FOFFSET stays as quantised for the start-up rate (params.py:472 runs before the file is opened, receiver.py:811)
+    orx = odsp.Receiver(Po2, receiver_offsets(P)[0], 0, '1', fast=True)
+    ref = np.concatenate([orx.demod_data(x[c * C:(c + 1) * C]) for c in range(6)])
+    assert_parity(got, ref, "replayed file", rel_tol=2e-4, snr_min=74)
+    P.SAVE_DIR = str(tmp_path)
+    d = sdr_fileio('demod', 'w', P, 1, 'USB')
+    d.save_data(got); d.close()
+    assert np.array_equal(sdr_fileio(d.fname, 'r', None).read_data(), got)

@@ -150,3 +150,32 @@ def test_jet_colormap_reproduces_reference_table():
     assert list(J[0]) == [0, 0, 143, 255] and list(J[7]) == [0, 0, 255, 255] and list(J[8]) == [0, 16, 255, 255]
     lut = lookup_table(J, 256)
     assert lut.shape == (256, 4) and np.array_equal(lut[0], J[0]) and np.array_equal(lut[-1], J[-1])
+
+
+def test_capture_file_roundtrip_and_replay_setup(tmp_path):
+    """sdr_fileio surface (reference receiver.py:295-297,526,810-813; pySDR.py:118-123) and the in-tree header hints
+    hdr(1) = fs, hdr(4) = nchan (sigs/nfm.m:50-55)."""
+    from pysdr_b200.fileio import sdr_fileio, open_replay
+    P, _ = make_both(2.048, [14074.123], ['USB'])
+    P.SAVE_DIR = str(tmp_path)
+    w = sdr_fileio('raw_iq', 'w', P, 2, 'RAW_IQ')
+    assert w.fname is None                                       # nothing on disk until the first save_data
+    rng = np.random.default_rng(1)
+    x = (rng.normal(size=5000) + 1j * rng.normal(size=5000)).astype(np.complex64)
+    w.save_data(x[:3000]); w.save_data(x[3000:], VERBOSITY=0); w.close()
+    assert re.match(r".*raw_iq_\d{8}_\d{6}\.dat$", w.fname)
+    r = sdr_fileio(w.fname, 'r', None)
+    assert r.hdr[0] == r.srate == P.SRATE and int(r.hdr[3]) == r.nchan == 2 and r.tag == 'RAW_IQ'
+    assert abs(r.fc - 14074.123e3) < 0.5
+    assert np.array_equal(r.read_data(), x)
+    d = sdr_fileio('demod', 'w', P, 1, 'USB')
+    d.save_data(x.real[:100]); d.close()
+    rd = sdr_fileio(d.fname, 'r', None)
+    assert rd.nchan == 1 and rd.srate == P.FS_OUT and np.array_equal(rd.read_data(), x.real[:100])
+    P2, _ = make_both(8, [1000], ['USB'])                        # replay: rates follow the file (receiver.py:811-820)
+    open_replay(P2, w.fname)
+    assert (P2.SRATE, P2.UP, P2.DOWN, P2.FS_OUT, P2.IN_CHUNK_SIZE) == (2.048e6, 3, 128, 48000, 43690)
+    with open(tmp_path / "junk.dat", "wb") as f:
+        f.write(b"\0" * 200)
+    with pytest.raises(ValueError):
+        sdr_fileio(str(tmp_path / "junk.dat"), 'r', None)
