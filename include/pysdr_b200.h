@@ -49,6 +49,9 @@ double pysdr_phase_inc_to_freq(uint64_t inc, double fs_hz);
 /* x[i] *= exp(-j*2*pi*(acc0 + i*inc)/2^64), in place or out of place; complex64 device pointers. */
 int pysdr_quad_mixer(const void *d_x, void *d_y, int64_t n, uint64_t acc0, uint64_t inc, void *stream);
 
+/* CS16 sources (reference receiver.py:614-617): complex64 out[i] = scale*(in[2i] + j in[2i+1]), scale = 1/2048 there.
+ * d_in: device int16[2n], d_out: device complex64[n]. */
+int pysdr_cs16_to_cf32(const void *d_in, void *d_out, int64_t n, double scale, void *stream);
 /* rx.auto_mute(x) building block (reference receiver.py:238-245): *d_out = mean(|x|^2), float32 device. */
 int pysdr_mean_power(const void *d_x, int64_t n, float *d_out, void *stream);
 

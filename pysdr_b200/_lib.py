@@ -36,6 +36,7 @@ SIGNATURES = {
     "pysdr_freq_to_phase_inc": (c_u64, [c_dbl, c_dbl]),
     "pysdr_phase_inc_to_freq": (c_dbl, [c_u64, c_dbl]),
     "pysdr_quad_mixer": (c_int, [c_vp, c_vp, c_i64, c_u64, c_u64, c_vp]),
+    "pysdr_cs16_to_cf32": (c_int, [c_vp, c_vp, c_i64, c_dbl, c_vp]),
     "pysdr_mean_power": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "pysdr_fir_valid": (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_vp, c_vp]),
     "pysdr_bank_create": (c_int, [ctypes.POINTER(BankConfig), ctypes.POINTER(c_vp)]),

@@ -56,6 +56,44 @@ extern "C" int pysdr_quad_mixer(const void *d_x, void *d_y, int64_t n, uint64_t 
     return PYSDR_OK;
 }
 
+// CS16 -> CF32 (reference receiver.py:614-617: xxx = sc*xx[0::2] + 1j*sc*xx[1::2], sc = 1/2048).  Done on the device
+// so that int16 sources cross PCIe at 4 bytes per sample instead of 8.  One 16-byte load = 4 complex samples.
+__global__ void cs16_to_cf32_kernel(const short *__restrict__ in, float2 *__restrict__ out, i64 n, float scale) {
+    const i64 n4 = n >> 2;
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const bool aligned = (((unsigned long long)in & 15ull) == 0) && (((unsigned long long)out & 15ull) == 0);
+    if (aligned) {
+        for (; i < n4; i += stride) {
+            const int4 v = ((const int4 *)in)[i];
+            const int w[4] = {v.x, v.y, v.z, v.w};
+            float4 o[2];
+            float *of = (float *)o;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                of[2 * k] = (float)(short)(w[k] & 0xffff) * scale;
+                of[2 * k + 1] = (float)(short)(w[k] >> 16) * scale;
+            }
+            ((float4 *)out)[2 * i] = o[0];
+            ((float4 *)out)[2 * i + 1] = o[1];
+        }
+        i = (n4 << 2) + (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    } else {
+        i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    }
+    for (; i < n; i += stride) out[i] = make_float2((float)in[2 * i] * scale, (float)in[2 * i + 1] * scale);
+}
+
+extern "C" int pysdr_cs16_to_cf32(const void *d_in, void *d_out, int64_t n, double scale, void *stream) {
+    if (n <= 0) return PYSDR_OK;
+    if (!d_in || !d_out) { pysdr_set_error("cs16_to_cf32: null pointer"); return PYSDR_ERR_ARG; }
+    i64 blocks = ((n >> 2) + 255) / 256 + 1;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cs16_to_cf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const short *)d_in, (float2 *)d_out, n, (float)scale);
+    LAUNCH_CHECK();
+    return PYSDR_OK;
+}
+
 // mean |x|^2 of a chunk (auto-mute detector); single CTA, deterministic tree
 __global__ void __launch_bounds__(1024) mean_power_kernel(const float2 *__restrict__ x, i64 n, float *__restrict__ out) {
     __shared__ double sm[32];

@@ -10,10 +10,13 @@ Reference semantics kept:
   * audio gain                  receiver.py:197-200   af_gain = 10**AF_GAIN - 1, muted -> 0
   * duration                    receiver.py:764
 """
+import ctypes
+
 import numpy as np
 import torch
 
 from . import design
+from ._lib import check
 from .bank import ReceiverBank
 
 
@@ -87,13 +90,23 @@ class ReplayStreamer:
     (per-block semantics are defined on absolute block indices); MP_SCHEME 3's broadcast + barrier collapses to one
     process per GPU."""
 
-    def __init__(self, P, seg_chunks=64, device=None, want_iq=False):
+    CS16_SCALE = 1.0 / 2048.0                                   # reference receiver.py:614
+
+    def __init__(self, P, seg_chunks=64, device=None, want_iq=False, fmt='cf32'):
+        """fmt 'cf32': the host capture is complex64 (replay files, SOAPY_SDR_CF32).  fmt 'cs16': interleaved int16 I/Q
+        as SDR hardware delivers it (reference receiver.py:609-617); it crosses PCIe at 4 bytes per sample and is
+        scaled by 1/2048 to complex64 on the device."""
+        if fmt not in ('cf32', 'cs16'):
+            raise ValueError("fmt must be 'cf32' or 'cs16'")
+        self.fmt = fmt
         self.P = P
         self.C = int(P.IN_CHUNK_SIZE)
         self.seg_chunks = int(seg_chunks)
         self.bank = ReceiverBank(P, receiver_offsets(P), max_in=self.seg_chunks * self.C, device=device)
         dev = self.bank.device
         self.dbuf = [torch.empty(self.seg_chunks * self.C, dtype=torch.complex64, device=dev) for _ in range(2)]
+        self.dbuf16 = [torch.empty(2 * self.seg_chunks * self.C, dtype=torch.int16, device=dev) for _ in range(2)] \
+            if fmt == 'cs16' else None
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.freed = [torch.cuda.Event() for _ in range(2)]
@@ -103,14 +116,18 @@ class ReplayStreamer:
 
     def pin(self, raw):
         """Pinned copy of a host capture (numpy complex64 or CPU tensor)."""
-        t = torch.from_numpy(np.ascontiguousarray(raw, np.complex64)) if isinstance(raw, np.ndarray) else raw
-        return t if t.is_pinned() else t.pin_memory()
+        if isinstance(raw, np.ndarray):
+            raw = torch.from_numpy(np.ascontiguousarray(raw, np.int16 if self.fmt == 'cs16' else np.complex64))
+        return raw if raw.is_pinned() else raw.pin_memory()
 
     def run(self, hx, start_sample=0):
         """hx: pinned CPU complex64 tensor holding whole chunks.  Returns (h_am, n_out_per_segment): pinned float32
         [n_segments, n_rx, n_out_max] (complex receivers: interleaved re/im in 2*n_out floats)."""
         C, sc, bank = self.C, self.seg_chunks, self.bank
-        n_chunks = hx.numel() // C
+        cs16 = self.fmt == 'cs16'
+        if cs16 and hx.dtype != torch.int16 or not cs16 and hx.dtype != torch.complex64:
+            raise ValueError("capture dtype %s does not match fmt %r" % (hx.dtype, self.fmt))
+        n_chunks = (hx.numel() // 2 if cs16 else hx.numel()) // C
         segs = [(s, min(n_chunks, s + sc)) for s in range(0, n_chunks, sc)]
         n_out_max = 2 * ((int(self.P.UP) * sc * C) // int(self.P.DOWN) + 2)
         if self.h_am is None or self.h_am.shape[0] < len(segs):
@@ -128,9 +145,16 @@ class ReplayStreamer:
             with torch.cuda.stream(cp):
                 if i >= 2:
                     cp.wait_event(self.freed[k])
-                self.dbuf[k][:(b - a) * C].copy_(hx[a * C:b * C], non_blocking=True)
+                if cs16:
+                    self.dbuf16[k][:2 * (b - a) * C].copy_(hx[2 * a * C:2 * b * C], non_blocking=True)
+                else:
+                    self.dbuf[k][:(b - a) * C].copy_(hx[a * C:b * C], non_blocking=True)
                 self.ready[k].record(cp)
             cs.wait_event(self.ready[k])
+            if cs16:
+                check(bank.lib.pysdr_cs16_to_cf32(ctypes.c_void_p(self.dbuf16[k].data_ptr()),
+                                                  ctypes.c_void_p(self.dbuf[k].data_ptr()), (b - a) * C, self.CS16_SCALE,
+                                                  ctypes.c_void_p(cs.cuda_stream)))
             bank.process(self.dbuf[k][:(b - a) * C], want_dc=False)
             self.freed[k].record(cs)
             no = bank.n_out

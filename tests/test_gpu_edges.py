@@ -469,3 +469,23 @@ def test_replay_from_capture_file_through_streamer(tmp_path):
     d = sdr_fileio('demod', 'w', P, 1, 'USB')
     d.save_data(got); d.close()
     assert np.array_equal(sdr_fileio(d.fname, 'r', None).read_data(), got)
+
+
+def test_cs16_source_streams_at_half_the_pcie_bytes():
+    """CS16 capture (reference receiver.py:609-617: sc = 1/2048) converted on the device == the same samples fed as
+    complex64; the conversion is exact in float32."""
+    from pysdr_b200.receiver import ReplayStreamer
+    P, _ = make_both(2.048, [1000, 1030], ['USB', 'AM'], af_bw_khz=[2, 5])
+    C = P.IN_CHUNK_SIZE
+    rng = np.random.default_rng(3)
+    raw = rng.integers(-2048, 2048, size=2 * 7 * C + 2, dtype=np.int16)[:2 * 7 * C]
+    x = (raw[0::2].astype(np.float64) / 2048.0 + 1j * raw[1::2].astype(np.float64) / 2048.0).astype(np.complex64)
+    a = ReplayStreamer(P, seg_chunks=3, want_iq=True)
+    a.run(a.pin(x))
+    b = ReplayStreamer(P, seg_chunks=3, want_iq=True, fmt='cs16')
+    b.run(b.pin(raw))
+    for r in range(2):
+        assert np.array_equal(a.audio(r), b.audio(r))
+    assert torch.equal(a.h_iq[:3], b.h_iq[:3])
+    with pytest.raises(ValueError):
+        b.run(a.pin(x))
