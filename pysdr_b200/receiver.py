@@ -160,9 +160,10 @@ class ReplayStreamer:
             no = bank.n_out
             self.n_out_seg.append(no)
             w = 2 * no if any_cplx else no                      # complex receivers (IQ/RTTY) use 2 floats per sample
-            self.h_am[i, :, :w].copy_(bank._am[:, :w], non_blocking=True)
-            if self.want_iq:
-                self.h_iq[i, :, :no].copy_(bank._iq[:, :no], non_blocking=True)
+            for r in range(bank.n_rx):                          # row by row: contiguous copies stay asynchronous (a strided
+                self.h_am[i, r, :w].copy_(bank._am[r, :w], non_blocking=True)   # 2-D device-to-host copy_ blocks the host)
+                if self.want_iq:
+                    self.h_iq[i, r, :no].copy_(bank._iq[r, :no], non_blocking=True)
         cs.synchronize()
         return self.h_am, self.n_out_seg
 
