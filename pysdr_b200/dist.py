@@ -91,3 +91,36 @@ class ShardedCapture:
         am, iq, dc = b.process_back(prev_peaks=prev, want_dc=want_dc, skip_blocks=w)   # whose own peaks are not valid)
         k = self.skip_out
         return [a[k:] for a in am], [a[k:] for a in iq], [a[k:] for a in dc]
+
+
+# ---- the other natural axis (SURVEY.md 8e axis 1): shard by receiver, no data-path collective -----------------------
+def receiver_shard(n_rx, rank, world):
+    """Receiver indices owned by `rank`: contiguous, sizes differing by at most one (what MP_SCHEME 3 does with one
+    process per receiver, reference receiver.py:726-739, generalised to world ranks)."""
+    base, extra = divmod(int(n_rx), int(world))
+    lo = rank * base + min(rank, extra)
+    return list(range(lo, lo + base + (1 if rank < extra else 0)))
+
+
+def gather_audio(local, n_rx, rank, world, group=None):
+    """Optional convenience: collect every receiver's audio on all ranks.  local: dict {irx: 1-D float32 tensor of equal
+    length} for the receivers of receiver_shard(n_rx, rank, world).  Returns a [n_rx, n] tensor.  (The data path itself
+    needs no collective: each rank can equally well write its own receivers' files.)"""
+    per = -(-int(n_rx) // int(world))
+    n = next(iter(local.values())).numel() if local else 0
+    dev = next(iter(local.values())).device if local else torch.device("cpu")
+    nt = torch.tensor([n], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(nt, op=dist.ReduceOp.MAX, group=group)
+    n = int(nt.item())
+    mine = torch.zeros((per, n), dtype=torch.float32, device=dev)
+    for j, irx in enumerate(receiver_shard(n_rx, rank, world)):
+        mine[j].copy_(local[irx])
+    if world == 1:
+        return mine[:n_rx]
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    rows = []
+    for r in range(world):
+        rows.extend(parts[r][j] for j in range(len(receiver_shard(n_rx, r, world))))
+    return torch.stack(rows)

@@ -119,3 +119,49 @@ def test_shard_plan_geometry():
     # 1002 baseband samples of AF memory need ceil(1002*500/3)=167000 inputs < one 170666-sample chunk
     Pw = rxo.make_P(0.25e6, [1e6], 'USB', foffset=20e3)               # 24/125: chunk 5333 inputs -> 1024 outputs
     assert shard_plan(Pw, 1, 2, 10)['warm_chunks'] == 1
+
+
+def _rx_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pysdr_b200.dist import gather_audio, receiver_shard
+        P = rxo.make_P(2.048e6, [1000e3, 1040e3, 1075e3], ['USB', 'AM', 'CW'], foffset=100e3, af_bw=[2e3, 5e3, 500.], nfilt=101)
+        x = _capture(P, 3)
+        offs = [P.FOFFSET + f - P.FC[0] for f in P.FC]
+        mine = receiver_shard(3, rank, world)
+        local = {}
+        for irx in mine:
+            rx = odsp.Receiver(P, offs[irx], irx, str(irx + 1))
+            C = P.IN_CHUNK_SIZE
+            local[irx] = torch.from_numpy(np.concatenate([rx.demod_data(x[c * C:(c + 1) * C]) for c in range(3)]).astype(np.float32))
+        allrx = gather_audio(local, 3, rank, world)
+        q.put((rank, mine, allrx.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_receiver_shard_needs_no_exchange():
+    from pysdr_b200.dist import receiver_shard
+    assert [receiver_shard(3, r, 2) for r in range(2)] == [[0, 1], [2]]
+    assert [receiver_shard(4, r, 8) for r in range(8)] == [[0], [1], [2], [3], [], [], [], []]
+    assert sum((receiver_shard(1024, r, 8) for r in range(8)), []) == list(range(1024))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rx_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1] == [0, 1] and res[1][1] == [2]
+    assert np.array_equal(res[0][2], res[1][2]) and res[0][2].shape[0] == 3
+    P = rxo.make_P(2.048e6, [1000e3, 1040e3, 1075e3], ['USB', 'AM', 'CW'], foffset=100e3, af_bw=[2e3, 5e3, 500.], nfilt=101)
+    x = _capture(P, 3)
+    rxo.create_receivers(P)
+    C = P.IN_CHUNK_SIZE
+    for irx in range(3):
+        ref = np.concatenate([P.rx[irx].demod_data(x[c * C:(c + 1) * C]) for c in range(3)]).astype(np.float32)
+        assert np.array_equal(res[0][2][irx], ref)
