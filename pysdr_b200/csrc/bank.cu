@@ -220,16 +220,8 @@ af_fir_kernel(const void *__restrict__ src_v, const float2 *__restrict__ taps, i
     }
 }
 
-// Output index range [lo,hi) (relative to this call) of AGC/DC block b (relative to this call).
-__device__ __forceinline__ void block_range(i64 b, i64 B0, i64 in_chunk, int up, int down, i64 m0, i64 n_out,
-                                            i64 &lo, i64 &hi) {
-    const i64 s = ((i64)up * (B0 + b) * in_chunk + down - 1) / down - m0;
-    const i64 e = ((i64)up * (B0 + b + 1) * in_chunk + down - 1) / down - m0;
-    lo = s < 0 ? 0 : s;
-    hi = e > n_out ? n_out : e;
-}
-
-// Warp-uniform block range: lanes 0/1 do the two 64-bit divisions, the rest of the warp takes the result by shuffle.
+// Output index range [lo,hi) (relative to this call) of AGC/DC block b (relative to this call), warp-uniform: lanes 0/1
+// do the two 64-bit divisions, the rest of the warp takes the result by shuffle.
 __device__ __forceinline__ void block_range_warp(i64 b, i64 B0, i64 in_chunk, int up, int down, i64 m0, i64 n_out,
                                                  i64 &lo, i64 &hi) {
     const int lane = threadIdx.x & 31;

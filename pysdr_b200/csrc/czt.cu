@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(CZT_THREADS) czt_cols_fwd(const void *__restri
         s[c * PITCH + FFT_PAD(n1)] = v;
     }
     __syncthreads();
-    fft_smem<CZT_N1, false>(s + (tid >> 5) * PITCH, tid & 31, nullptr);             // warp f owns column f of the tile
+    fft_smem<CZT_N1, false>(s + (tid >> 5) * PITCH, tid & 31);             // warp f owns column f of the tile
     float2 *Tf = T + (size_t)blockIdx.y * CZT_M;
     for (int i = 0; i < CZT_N1 / (CZT_THREADS / CZT_COLS); ++i) {
         const int p = r0 + i * (CZT_THREADS / CZT_COLS);
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(CZT_THREADS) czt_rows(const float2 *__restrict
 #pragma unroll
     for (int i = 0; i < CZT_N2 / 32; ++i) sw[FFT_PAD(lane + 32 * i)] = row[lane + 32 * i];
     __syncthreads();
-    fft_smem<CZT_N2, false>(sw, lane, nullptr);
+    fft_smem<CZT_N2, false>(sw, lane);
     const float2 *bp = bspec + (size_t)p * CZT_N2;
 #pragma unroll
     for (int i = 0; i < CZT_N2 / 32; ++i) {
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(CZT_THREADS) czt_rows(const float2 *__restrict
         sw[FFT_PAD(q)] = cmul(sw[FFT_PAD(q)], __ldg(bp + q));
     }
     __syncthreads();
-    fft_smem<CZT_N2, true>(sw, lane, nullptr);
+    fft_smem<CZT_N2, true>(sw, lane);
     float2 *orow = U + (size_t)blockIdx.y * CZT_M + (size_t)p * CZT_N2;
 #pragma unroll
     for (int i = 0; i < CZT_N2 / 32; ++i) orow[lane + 32 * i] = sw[FFT_PAD(lane + 32 * i)];
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(CZT_THREADS) czt_cols_inv(const float2 *__rest
         s[c * PITCH + FFT_PAD(p)] = cmul(Uf[(size_t)p * CZT_N2 + n2], make_float2(cs, sn));
     }
     __syncthreads();
-    fft_smem<CZT_N1, true>(s + (tid >> 5) * PITCH, tid & 31, nullptr);
+    fft_smem<CZT_N1, true>(s + (tid >> 5) * PITCH, tid & 31);
     float *Pf = P + (size_t)blockIdx.y * nfft;
     for (int i = 0; i < CZT_N1 / (CZT_THREADS / CZT_COLS); ++i) {
         const int n1 = r0 + i * (CZT_THREADS / CZT_COLS);

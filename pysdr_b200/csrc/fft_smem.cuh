@@ -93,7 +93,7 @@ __device__ __forceinline__ void twiddle_powers(float2 w1, float2 *w) {
 
 // One pass over all blocks of length NI (NI = remaining transform length at this pass), radix R.
 template <int N, int NI, int R, int T, bool INV>
-__device__ __forceinline__ void fft_pass(float2 *s, int tid, const float2 *__restrict__ tw) {
+__device__ __forceinline__ void fft_pass(float2 *s, int tid) {
     constexpr int STRIDE = NI / R;
 #pragma unroll
     for (int u0 = 0; u0 < N / R; u0 += T) {
@@ -107,9 +107,7 @@ __device__ __forceinline__ void fft_pass(float2 *s, int tid, const float2 *__res
         float2 w[R];
         if constexpr (STRIDE > 1) {
             // W_NI^(k*m), k = 1..R-1: one accurate sincospi + a depth-4 product tree.  (A table of W_N^j gathered
-            // with 15 uncoalesced loads per butterfly was measured 35 % slower on B200; `tw` is kept for callers
-            // that want exact twiddles in other layouts.)
-            (void)tw;
+            // with 15 uncoalesced loads per butterfly was measured 35 % slower on B200.)
             float sn, cs;
             sincospif(-2.0f * (float)m / (float)NI, &sn, &cs);
             twiddle_powers<R>(make_float2(cs, sn), w);
@@ -147,20 +145,20 @@ struct FftPlan {
 
 // forward (INV=false) or inverse (INV=true) transform of the N points in s (padded layout), T = FftPlan<N>::THREADS
 template <int N, bool INV>
-__device__ __forceinline__ void fft_smem(float2 *s, int tid, const float2 *__restrict__ tw) {
+__device__ __forceinline__ void fft_smem(float2 *s, int tid) {
     using P = FftPlan<N>;
     constexpr int T = P::THREADS;
     constexpr int N1 = N / P::R0;                           // length after the odd first pass
     if constexpr (!INV) {
-        if constexpr (P::R0 > 1) fft_pass<N, N, P::R0, T, false>(s, tid, tw);
-        if constexpr (P::N16 >= 1) fft_pass<N, N1, 16, T, false>(s, tid, tw);
-        if constexpr (P::N16 >= 2) fft_pass<N, N1 / 16, 16, T, false>(s, tid, tw);
-        if constexpr (P::N16 >= 3) fft_pass<N, N1 / 256, 16, T, false>(s, tid, tw);
+        if constexpr (P::R0 > 1) fft_pass<N, N, P::R0, T, false>(s, tid);
+        if constexpr (P::N16 >= 1) fft_pass<N, N1, 16, T, false>(s, tid);
+        if constexpr (P::N16 >= 2) fft_pass<N, N1 / 16, 16, T, false>(s, tid);
+        if constexpr (P::N16 >= 3) fft_pass<N, N1 / 256, 16, T, false>(s, tid);
     } else {
-        if constexpr (P::N16 >= 3) fft_pass<N, N1 / 256, 16, T, true>(s, tid, tw);
-        if constexpr (P::N16 >= 2) fft_pass<N, N1 / 16, 16, T, true>(s, tid, tw);
-        if constexpr (P::N16 >= 1) fft_pass<N, N1, 16, T, true>(s, tid, tw);
-        if constexpr (P::R0 > 1) fft_pass<N, N, P::R0, T, true>(s, tid, tw);
+        if constexpr (P::N16 >= 3) fft_pass<N, N1 / 256, 16, T, true>(s, tid);
+        if constexpr (P::N16 >= 2) fft_pass<N, N1 / 16, 16, T, true>(s, tid);
+        if constexpr (P::N16 >= 1) fft_pass<N, N1, 16, T, true>(s, tid);
+        if constexpr (P::R0 > 1) fft_pass<N, N, P::R0, T, true>(s, tid);
     }
 }
 
@@ -186,4 +184,3 @@ __host__ __device__ __forceinline__ int fft_pos_to_freq(int p) {
 }
 
 // Device table of W_N^j = exp(-2*pi*i*j/N), j = 0..N-1 (lazily built per device, float64-exact, cached).
-const float2 *fft_twiddles(int N);

@@ -13,13 +13,13 @@
 
 template <int N>
 __global__ void __launch_bounds__(FftPlan<N>::THREADS)
-taps_fft_kernel(const float2 *__restrict__ taps, int L, float2 *__restrict__ Hpos, const float2 *__restrict__ tw) {
+taps_fft_kernel(const float2 *__restrict__ taps, int L, float2 *__restrict__ Hpos) {
     extern __shared__ __align__(16) float2 s[];
     constexpr int T = FftPlan<N>::THREADS;
     const int tid = threadIdx.x;
     for (int e = tid; e < N; e += T) s[FFT_PAD(e)] = (e < L) ? taps[e] : make_float2(0.f, 0.f);
     __syncthreads();
-    fft_smem<N, false>(s, tid, tw);
+    fft_smem<N, false>(s, tid);
     const float sc = 1.0f / (float)N;                                     // fold the inverse transform's 1/N
     for (int p = tid; p < N; p += T) {
         const float2 v = s[FFT_PAD(p)];
@@ -66,7 +66,7 @@ __device__ __forceinline__ float2 k2_detect(const float2 *raw, int e, int mode, 
 
 template <int N>
 __global__ void __launch_bounds__(FftPlan<N>::THREADS)
-af_fftconv_kernel(const FftConvArgs a, const float2 *__restrict__ tw) {
+af_fftconv_kernel(const FftConvArgs a) {
     extern __shared__ __align__(16) float2 s[];
     constexpr int T = FftPlan<N>::THREADS;
     constexpr int PER = N / T;
@@ -104,7 +104,7 @@ af_fftconv_kernel(const FftConvArgs a, const float2 *__restrict__ tw) {
         for (int i = 0; i < PER; ++i) s[FFT_PAD(tid + i * T)] = u[i];
     }
     __syncthreads();
-    fft_smem<N, false>(s, tid, tw);
+    fft_smem<N, false>(s, tid);
 
     float2 *sw = s;                                                       // buffer the inverse transform runs in
     if (pair) {
@@ -143,7 +143,7 @@ af_fftconv_kernel(const FftConvArgs a, const float2 *__restrict__ tw) {
         }
     }
     __syncthreads();
-    fft_smem<N, true>(sw, tid, tw);
+    fft_smem<N, true>(sw, tid);
 
     // ---- store the valid outputs of this block (32-bit loop, pointers hoisted) -----------------------------------
     const i64 left = a.n_out - k0;
@@ -189,9 +189,7 @@ template <int N>
 static int taps_fft_launch(const float2 *d_taps, int L, float2 *d_H, cudaStream_t st) {
     const size_t smem = sizeof(float2) * FFT_SMEM_ELEMS(N);
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(taps_fft_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const float2 *tw = fft_twiddles(N);
-    if (!tw) { pysdr_set_error("fft twiddle table allocation failed"); return PYSDR_ERR_CUDA; }
-    taps_fft_kernel<N><<<1, FftPlan<N>::THREADS, smem, st>>>(d_taps, L, d_H, tw);
+    taps_fft_kernel<N><<<1, FftPlan<N>::THREADS, smem, st>>>(d_taps, L, d_H);
     LAUNCH_CHECK();
     return PYSDR_OK;
 }
@@ -229,9 +227,7 @@ static int fftconv_launch_n(const FftConvArgs &a0, int n_rx, cudaStream_t st) {
     if (n_units == 0) return PYSDR_OK;
     const int V = N - (a.L - 1);
     dim3 grid((unsigned)((a.n_out + V - 1) / V), (unsigned)n_units);
-    const float2 *tw = fft_twiddles(N);
-    if (!tw) { pysdr_set_error("fft twiddle table allocation failed"); return PYSDR_ERR_CUDA; }
-    af_fftconv_kernel<N><<<grid, FftPlan<N>::THREADS, smem, st>>>(a, tw);
+    af_fftconv_kernel<N><<<grid, FftPlan<N>::THREADS, smem, st>>>(a);
     LAUNCH_CHECK();
     return PYSDR_OK;
 }

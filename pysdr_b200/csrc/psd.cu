@@ -28,7 +28,7 @@ struct PsdSteps { int sub; int off[8]; };
 template <int N, bool CPLX>
 __global__ void __launch_bounds__(FftPlan<N>::THREADS)
 psd_frames_kernel(const void *__restrict__ xv, const float *__restrict__ win, int chunk, int hop, const PsdSteps steps, int navg,
-                  int n_split, float *__restrict__ part, const float2 *__restrict__ tw) {
+                  int n_split, float *__restrict__ part) {
     extern __shared__ __align__(16) float2 s[];
     constexpr int T = FftPlan<N>::THREADS;
     constexpr int PER = (N + T - 1) / T;
@@ -61,7 +61,7 @@ psd_frames_kernel(const void *__restrict__ xv, const float *__restrict__ win, in
             }
         }
         __syncthreads();
-        fft_smem<N, false>(s, tid, tw);
+        fft_smem<N, false>(s, tid);
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             const int p = tid + i * T;
@@ -152,16 +152,14 @@ static int psd_launch(pysdr_psd *p, const void *d_x, int is_complex, int navg, i
         CUDA_TRY(cudaFuncSetAttribute(psd_frames_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(psd_frames_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    const float2 *tw = fft_twiddles(N);
-    if (!tw) { pysdr_set_error("fft twiddle table allocation failed"); return PYSDR_ERR_CUDA; }
     dim3 grid((unsigned)n_split, (unsigned)n_lines);
     PsdSteps steps;
     steps.sub = p->sub;
     for (int i = 0; i < 8; ++i) steps.off[i] = p->sub_off[i];
     if (is_complex)
-        psd_frames_kernel<N, true><<<grid, FftPlan<N>::THREADS, smem, st>>>(d_x, p->d_win, p->chunk, p->hop, steps, navg, n_split, p->d_part, tw);
+        psd_frames_kernel<N, true><<<grid, FftPlan<N>::THREADS, smem, st>>>(d_x, p->d_win, p->chunk, p->hop, steps, navg, n_split, p->d_part);
     else
-        psd_frames_kernel<N, false><<<grid, FftPlan<N>::THREADS, smem, st>>>(d_x, p->d_win, p->chunk, p->hop, steps, navg, n_split, p->d_part, tw);
+        psd_frames_kernel<N, false><<<grid, FftPlan<N>::THREADS, smem, st>>>(d_x, p->d_win, p->chunk, p->hop, steps, navg, n_split, p->d_part);
     LAUNCH_CHECK();
     const float scale = (p->flags & PYSDR_PSD_RAW) ? 1.0f / (float)navg : (float)(1.0 / ((double)navg * p->wsum2));
     dim3 g2((unsigned)((N + 255) / 256), (unsigned)n_lines);
