@@ -27,6 +27,8 @@ def shard_plan(P, rank, world, chunks_per_rank):
         warm_in = math.ceil(hist_out * int(P.DOWN) / int(P.UP))         # inputs that produce >= hist_out outputs
         warm_chunks = max(1, math.ceil(warm_in / C))
         halo = need
+        if warm_chunks * C >= start:                                    # the warm-up reaches back to the stream start:
+            warm_chunks, halo = start // C, 0                           # x[<0] = 0, exactly what seek(0) gives
     lead = warm_chunks * C + halo                                       # samples to read before `start`
     return dict(start=start, n=chunks_per_rank * C, warm_chunks=warm_chunks, halo=halo, lead=lead,
                 first_sample=start - lead, n_blocks=chunks_per_rank)
@@ -81,7 +83,7 @@ class ShardedCapture:
         w = p['warm_chunks']
         if w:
             b.seek(p['start'] - w * C)
-            b.process_front(xbuf[p['halo']:], self.peaks_ext, halo_in_place=True)
+            b.process_front(xbuf[p['halo']:], self.peaks_ext, halo_in_place=p['halo'] > 0)
             self.own.copy_(self.peaks_ext[:, w:])
         else:
             b.seek(0)

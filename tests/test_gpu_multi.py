@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 FCS = [-500, 700, 1400, 3100]
 MODES = ['AM', 'NFM', 'USB', 'CW']
-CPR = 4                                   # chunks per rank
+CPRS = [4, 1]                             # chunks per rank; 1: rank 1's warm-up starts at the very first sample
 
 
 def _P():
@@ -23,7 +23,7 @@ def _P():
                            ['-foffset', '100', '-af_bw', '5', '10', '2', '0.5'])
 
 
-def _worker(rank, world, port, outdir):
+def _worker(rank, world, port, outdir, CPR):
     import torch.distributed as dist
     from pysdr_b200.bank import ReceiverBank
     from pysdr_b200.dist import ShardedCapture
@@ -51,7 +51,8 @@ def _worker(rank, world, port, outdir):
         dist.destroy_process_group()
 
 
-def test_two_gpu_time_shard_equals_single_gpu(tmp_path):
+@pytest.mark.parametrize("CPR", CPRS)
+def test_two_gpu_time_shard_equals_single_gpu(tmp_path, CPR):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -60,7 +61,7 @@ def test_two_gpu_time_shard_equals_single_gpu(tmp_path):
     from pysdr_b200.synth import synth_iq
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     world = 2
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), CPR), nprocs=world, join=True)
     P = _P()
     offs = receiver_offsets(P)
     C = P.IN_CHUNK_SIZE
