@@ -509,13 +509,15 @@ class _WfmChain:
         vid.SRATE, vid.UP, vid.DOWN, vid.FS_OUT = P.SRATE, 1, 1, int(P.SRATE)
         vid.IN_CHUNK_SIZE, vid.FILT_LEN, vid.VIDEO_BW = P.IN_CHUNK_SIZE, P.FILT_LEN, P.VIDEO_BW
         vid.MODE, vid.AF_BW, vid.AF_FILTER_NUM, vid.BFO, vid.VIDEO_FILTER_NUM = 'RAW', 0, 0, 0, None
-        self.vbank = ReceiverBank(vid, [rx._bank.fo[0]], max_in=int(P.IN_CHUNK_SIZE))
+        # P.WFM_MAX_CHUNKS (default 1 = the reference's chunk-at-a-time calls) lets a resident capture go through in one call
+        self.max_in = int(P.IN_CHUNK_SIZE) * max(1, int(getattr(P, 'WFM_MAX_CHUNKS', 1)))
+        self.vbank = ReceiverBank(vid, [rx._bank.fo[0]], max_in=self.max_in)
         check(self.lib.pysdr_bank_set_k1_only(self.vbank.h, 1))
         self.filter_bank = design.wfm_video_bank(P.SRATE, P.FILT_LEN, design.VIDEO_BWs, P.VIDEO_BW)
         self.set_video(self.filter_bank[design.video_index(P)])
         dev = self.vbank.device
         self.prev2 = torch.zeros(2, dtype=torch.complex64, device=dev)
-        self.fm = torch.empty(int(P.IN_CHUNK_SIZE), dtype=torch.complex64, device=dev)
+        self.fm = torch.empty(self.max_in, dtype=torch.complex64, device=dev)
         self.stage2(stereo)
 
     def stage2(self, stereo):
@@ -528,10 +530,10 @@ class _WfmChain:
         if self.stereo:
             res.MODE = ['IQ', 'IQ', 'IQ']
             res.AF_FILTER_NUM = [0, 0, design.AF_BWs.index(self.PILOT_AF)]
-            self.rbank = ReceiverBank(res, [0.0, 38e3, 19e3], max_in=int(P.IN_CHUNK_SIZE))
+            self.rbank = ReceiverBank(res, [0.0, 38e3, 19e3], max_in=self.max_in)
             check(self.lib.pysdr_bank_set_stereo(self.rbank.h, 1, float(getattr(P, 'WFM_PILOT_MIN', 0.0))))
         else:
-            self.rbank = ReceiverBank(res, [0.0], max_in=int(P.IN_CHUNK_SIZE))
+            self.rbank = ReceiverBank(res, [0.0], max_in=self.max_in)
         self._res_key = None
         self.deemph = None
 
@@ -540,9 +542,18 @@ class _WfmChain:
         self.vbank.set_dec_taps(0, self.h)
 
     def demod(self, x):
-        P, rx = self.rx.P, self.rx
-        n = len(x)
+        """Host chunk in, host audio out (what rx.demod_data returns in WFM / WFM2 mode)."""
         xd = torch.from_numpy(np.ascontiguousarray(x, np.complex64)).to(self.vbank.device)
+        out, iq = self.demod_dev(xd)
+        if self.stereo:
+            a = out[0].cpu().numpy() + 1j * out[1].cpu().numpy()
+            return a.astype(np.complex64), iq.cpu().numpy()
+        return out[0].cpu().numpy(), iq.cpu().numpy()
+
+    def demod_dev(self, xd):
+        """Device samples (whole chunks, at most max_in) -> ([audio] or [L, R], baseband iq), device tensors."""
+        P, rx = self.rx.P, self.rx
+        n = xd.numel()
         _, y, _ = self.vbank.process(xd, want_dc=False)
         fm = self.fm[:n]
         check(self.lib.pysdr_fm_disc(ctypes.c_void_p(y[0].data_ptr()), n, ctypes.c_void_p(self.prev2.data_ptr()),
@@ -563,12 +574,11 @@ class _WfmChain:
             lr = [self.rbank._am[r, :n_out] for r in (0, 1)]    # float32 L, R rows after the common AGC
             if tau > 0:
                 lr = [self.deemph[r].run_dev(lr[r].contiguous()) for r in (0, 1)]
-            a = lr[0].cpu().numpy() + 1j * lr[1].cpu().numpy()
-            return a.astype(np.complex64), iq[0].cpu().numpy()
+            return lr, iq[0]
         a = am[0]
         if tau > 0:
             a = self.deemph[0].run_dev(a.contiguous())
-        return a.cpu().numpy(), iq[0].cpu().numpy()
+        return [a], iq[0]
 
 
 class _WfmVideo:
