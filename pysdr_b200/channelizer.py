@@ -55,3 +55,26 @@ class ChannelBank:
 def raster_offsets(n_ch, spacing_hz, centre_hz=0.0):
     """n_ch offsets on a uniform raster centred on centre_hz (config 5: 1024 channels, 9.6 kHz apart)."""
     return [centre_hz + spacing_hz * (k - (n_ch - 1) / 2.0) for k in range(n_ch)]
+
+
+class ShardedChannelBank:
+    """Config 5's multi-GPU shape: the capture is split in time across ranks, every rank runs all channel groups on its
+    shard, and the AGC carry of ALL channels travels in ONE all-gather of [n_ch, n_blocks] block peaks."""
+
+    def __init__(self, cb, rank, world, chunks_per_rank):
+        from .dist import ShardedCapture
+        self.cb, self.rank, self.world = cb, rank, world
+        self.shards = [ShardedCapture(b, b.P, rank, world, chunks_per_rank) for b in cb.banks]
+        self.plan = self.shards[0].plan
+
+    def step(self, xbuf):
+        """xbuf: device samples [first_sample, start+n) of this rank's shard.  Returns (am, iq) lists over channels."""
+        from .dist import exchange_agc_peaks
+        own = torch.cat([sh.front(xbuf) for sh in self.shards])          # [n_ch, n_blocks]
+        prev = exchange_agc_peaks(own, self.rank, self.world)            # one collective for every channel
+        am, iq = [], []
+        for sh, (g0, g1) in zip(self.shards, self.cb.slices):
+            a, q, _ = sh.back(None if prev is None else prev[g0:g1].contiguous())
+            am.extend(a)
+            iq.extend(q)
+        return am, iq

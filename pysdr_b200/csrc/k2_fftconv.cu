@@ -82,6 +82,8 @@ af_fftconv_kernel(const FftConvArgs a) {
     const float2 *C = a.C + (size_t)rx * a.c_stride;                      // C[k+2] <-> src[k]
     float *out = a.out + (size_t)rx * 2 * a.a_stride;
     float2 *s2 = s + FFT_SMEM_ELEMS(N);                                   // second buffer (N = 4096 launches only)
+    __shared__ float s_max[2][FftPlan<N>::THREADS / 32];
+    int pair_exp = 0;                                                     // b rides the transform scaled by 2^pair_exp
 
     // ---- stage raw samples (async), detect from shared memory, lay out for the FFT ---------------------------------
     k2_stage_raw<N, T>(s, C, k0, avail + 2, tid);
@@ -99,7 +101,34 @@ af_fftconv_kernel(const FftConvArgs a) {
             u[i] = k2_detect(s, e, mode, ok);
             if (pair) u[i].y = k2_detect(s2, e, modeb, ok).x;             // two real detector outputs: u = det_a + j det_b
         }
+        if (pair) {
+            // The two signals share one transform, so its rounding error (~1e-7 of the LARGER one) lands on both.  Bring
+            // them to the same binade first: b is scaled by an exact power of two (undone at the store), which keeps
+            // e.g. the discriminator output of a carrier-less NFM channel (1e-6) accurate next to an AM envelope (1e-2).
+            float ma = 0.f, mb = 0.f;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) { ma = fmaxf(ma, fabsf(u[i].x)); mb = fmaxf(mb, fabsf(u[i].y)); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+                mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+            }
+            if ((tid & 31) == 0) { s_max[0][tid >> 5] = ma; s_max[1][tid >> 5] = mb; }
+        }
         __syncthreads();
+        if (pair) {
+            float ma = 0.f, mb = 0.f;
+#pragma unroll
+            for (int w = 0; w < T / 32; ++w) { ma = fmaxf(ma, s_max[0][w]); mb = fmaxf(mb, s_max[1][w]); }
+            if (ma > 0.f && mb > 0.f && isfinite(ma) && isfinite(mb)) {
+                int e = ilogbf(ma) - ilogbf(mb);
+                e = e < -60 ? -60 : (e > 60 ? 60 : e);
+                pair_exp = e;
+                const float sb = scalbnf(1.0f, e);
+#pragma unroll
+                for (int i = 0; i < PER; ++i) u[i].y *= sb;
+            }
+        }
 #pragma unroll
         for (int i = 0; i < PER; ++i) s[FFT_PAD(tid + i * T)] = u[i];
     }
@@ -152,11 +181,12 @@ af_fftconv_kernel(const FftConvArgs a) {
     float *o0 = out + k0;
     if (pair) {
         float *o1 = a.out + (size_t)rxb * 2 * a.a_stride + k0;
+        const float unscale = scalbnf(1.0f, -pair_exp);
 #pragma unroll 4
         for (int j = tid; j < lim; j += T) {
             const float2 c = sv[FFT_PAD(j + L - 1)];
             o0[j] = c.x;
-            o1[j] = c.y;
+            o1[j] = c.y * unscale;
         }
     } else if (mode == PYSDR_MODE_IQ) {
         float2 *oc = (float2 *)out + k0;

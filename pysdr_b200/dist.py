@@ -75,9 +75,9 @@ class ShardedCapture:
         if bank.max_in < self.plan['n'] + w * C:
             raise ValueError("bank.max_in must cover the shard plus its %d warm-up chunk(s)" % w)
 
-    def step(self, xbuf, want_dc=False):
-        """xbuf: device tensor holding samples [first_sample, start+n) of the capture.
-        Returns (am, iq, am_dc) views of this rank's shard."""
+    def front(self, xbuf):
+        """K1 + audio-rate filters + block peaks of this shard (and its warm-up).  xbuf: device tensor holding samples
+        [first_sample, start+n) of the capture.  Leaves this rank's own block peaks in self.own."""
         p, b = self.plan, self.bank
         C = int(self.P.IN_CHUNK_SIZE)
         w = p['warm_chunks']
@@ -89,10 +89,19 @@ class ShardedCapture:
             b.seek(0)
             b.process_front(xbuf[p['lead']:], self.peaks_ext)
             self.own = self.peaks_ext
-        prev = exchange_agc_peaks(self.own, self.rank, self.world)  # peaks of ALL earlier blocks (incl. the warm-up ones,
-        am, iq, dc = b.process_back(prev_peaks=prev, want_dc=want_dc, skip_blocks=w)   # whose own peaks are not valid)
+        return self.own
+
+    def back(self, prev, want_dc=False):
+        """AGC replay over the peaks of ALL earlier blocks (prev, from exchange_agc_peaks; the warm-up blocks' own peaks
+        are not valid and are skipped) and gain application.  Returns (am, iq, am_dc) views of this rank's shard."""
+        am, iq, dc = self.bank.process_back(prev_peaks=prev, want_dc=want_dc, skip_blocks=self.plan['warm_chunks'])
         k = self.skip_out
         return [a[k:] for a in am], [a[k:] for a in iq], [a[k:] for a in dc]
+
+    def step(self, xbuf, want_dc=False):
+        own = self.front(xbuf)
+        prev = exchange_agc_peaks(own, self.rank, self.world)           # the one collective of the path
+        return self.back(prev, want_dc=want_dc)
 
 
 # ---- the other natural axis (SURVEY.md 8e axis 1): shard by receiver, no data-path collective -----------------------

@@ -489,3 +489,22 @@ def test_cs16_source_streams_at_half_the_pcie_bytes():
     assert torch.equal(a.h_iq[:3], b.h_iq[:3])
     with pytest.raises(ValueError):
         b.run(a.pin(x))
+
+
+def test_paired_fft_keeps_a_weak_signal_accurate_next_to_a_strong_one():
+    """AM and NFM receivers share one complex FFT in the AF filter (k2_fftconv.cu).  A carrier-less NFM channel (its
+    discriminator output ~1e-7) must not inherit the rounding error of a strong AM envelope (~0.3): the pair is brought
+    to the same binade by an exact power-of-two scale.  Without it this case fails the gate by two orders of magnitude."""
+    P, Po = make_both(8, [1000, 1400], ['AM', 'NFM'], af_bw_khz=[5, 10])
+    C = P.IN_CHUNK_SIZE
+    n = np.arange(3 * C)
+    from pysdr_b200.receiver import receiver_offsets
+    offs = receiver_offsets(P)
+    x = (0.3 * (1 + 0.5 * np.sin(2 * np.pi * 1e3 * n / P.SRATE)) * np.exp(2j * np.pi * offs[0] * n / P.SRATE)
+         + _noise(len(n), 31, 3e-4)).astype(np.complex64)
+    bank = _bank(P, 3 * C)
+    am, _, _ = bank.process(torch.from_numpy(x).cuda(), want_dc=False)
+    rxo.create_receivers(Po)
+    for r in range(2):
+        ref = np.concatenate([Po.rx[r].demod_data(x[c * C:(c + 1) * C]) for c in range(3)])
+        assert_parity(am[r].cpu().numpy(), ref, "rx%d" % r)

@@ -78,3 +78,60 @@ def test_two_gpu_time_shard_equals_single_gpu(tmp_path, CPR):
         assert got_am.shape == ref_am[r].shape
         np.testing.assert_array_equal(got_iq, ref_iq[r])                         # K1 is shard-invariant bit for bit
         assert_parity(got_am, ref_am[r], "sharded vs single rx%d" % r, rel_tol=2e-5, snr_min=90)
+
+
+def _chan_worker(rank, world, port, outdir):
+    import torch.distributed as dist
+    from pysdr_b200.channelizer import ChannelBank, ShardedChannelBank, raster_offsets
+    from pysdr_b200.params import RUN_TIME_PARAMS
+    from pysdr_b200.synth import synth_iq
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        P = RUN_TIME_PARAMS(['-fs', '10', '-fc', '7000', '-mode', 'USB', '-af_bw', '2'])
+        offs, modes, afs = _chan_cfg()
+        C = P.IN_CHUNK_SIZE
+        cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=5 * C, device=dev)
+        sh = ShardedChannelBank(cb, rank, world, 3)
+        pl = sh.plan
+        xbuf = synth_iq(pl['lead'] + pl['n'], P.SRATE, offs[:4], modes[:4], seed=78, device=dev, n0=pl['first_sample'], block=1 << 16)
+        am, iq = sh.step(xbuf)
+        torch.cuda.synchronize()
+        np.savez(os.path.join(outdir, "chan%d.npz" % rank), **{"am%d" % r: am[r].cpu().numpy() for r in range(len(offs))})
+    finally:
+        dist.destroy_process_group()
+
+
+def _chan_cfg():
+    from pysdr_b200.channelizer import raster_offsets
+    n_ch = 20
+    offs = raster_offsets(n_ch, 9600.0, 150e3)
+    modes = [['AM', 'NFM', 'USB', 'CW'][k % 4] for k in range(n_ch)]
+    afs = [[5e3, 10e3, 2e3, 500.][k % 4] for k in range(n_ch)]
+    return offs, modes, afs
+
+
+def test_two_gpu_many_channel_time_shard(tmp_path):
+    """Config 5's shape at test size: 20 channels (3 groups) on a 10 MS/s stream, time-sharded over 2 ranks with one
+    all-gather of every channel's AGC peaks, equals the single-GPU single-stream result."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from pysdr_b200.channelizer import ChannelBank
+    from pysdr_b200.params import RUN_TIME_PARAMS
+    from pysdr_b200.synth import synth_iq
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_chan_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    P = RUN_TIME_PARAMS(['-fs', '10', '-fc', '7000', '-mode', 'USB', '-af_bw', '2'])
+    offs, modes, afs = _chan_cfg()
+    C = P.IN_CHUNK_SIZE
+    x = synth_iq(6 * C, P.SRATE, offs[:4], modes[:4], seed=78, device="cuda:0", block=1 << 16)
+    cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=6 * C, device="cuda:0")
+    am, _ = cb.process(x)
+    parts = [np.load(os.path.join(str(tmp_path), "chan%d.npz" % r)) for r in range(2)]
+    for r in range(len(offs)):
+        got = np.concatenate([p["am%d" % r] for p in parts])
+        assert_parity(got, am[r].cpu().numpy(), "channel %d" % r, rel_tol=2e-5, snr_min=90)
