@@ -1,13 +1,10 @@
 #!/usr/bin/env python
 """Secondary measurement: BASELINE.json configs[0] — the reference's own CPU-runnable case: 10 s of 2.048 MS/s complex64
-IQ through ONE USB receiver to 48 kHz audio (3/128, FILT_LEN 1001), on the device and against the oracle port on the
-host (one core)."""
+IQ through ONE USB receiver to 48 kHz audio (3/128, FILT_LEN 1001), resident on the device.  (CPU figures come from
+bench.py's cpu_baseline / --impl reference legs, the only places that may time the oracle.)"""
 import json
 import os
 import sys
-import time
-
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -17,8 +14,6 @@ sys.path.insert(0, ROOT)
 def main():
     import __graft_entry__ as ge
     ge.build()
-    from oracle import receiver_oracle as rxo            # CPU baseline only
-    from oracle import sig_proc_oracle as odsp
     from pysdr_b200.bank import ReceiverBank
     from pysdr_b200.params import RUN_TIME_PARAMS
     from pysdr_b200.receiver import receiver_offsets
@@ -41,20 +36,11 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / k
-    # CPU: the oracle port, chunk loop as in the reference, bounded sample (1 s of signal)
-    Po = rxo.make_P(P.SRATE, [1000e3], 'USB', foffset=100e3, af_bw=2e3)
-    orx = odsp.Receiver(Po, offs[0], 0, '1', dtype=np.complex64, fast=True)
-    xh = x[:47 * C].cpu().numpy()
-    t0 = time.perf_counter()
-    for c in range(47):
-        orx.demod_data(xh[c * C:(c + 1) * C])
-    cpu_s = time.perf_counter() - t0
     lp = (int(P.FILT_LEN) + int(P.UP) - 1) // int(P.UP)
     print(json.dumps({"workload": "cfg1: 1 RX USB, 2.048 MS/s -> 48 kHz (3/128), %d samples (%.2f s)" % (n, n / P.SRATE),
                       "ms_per_pass": ms, "Msamples_per_s": n / ms / 1e3, "realtime_factor": (n / P.SRATE) / (ms / 1e3),
                       "k1_variant": bank.k1_variant, "k1_TFLOP_per_s(8 flop/tap)": 8.0 * lp * bank.n_out / ms / 1e9,
-                      "hbm_algorithmic_GBps": 8.094 * n / ms / 1e6,
-                      "cpu_oracle_port_1core_Msamples_per_s": 47 * C / cpu_s / 1e6, "cpu_sample": "47 chunks (1.0 s of signal)"}))
+                      "hbm_algorithmic_GBps": 8.094 * n / ms / 1e6}))
 
 
 if __name__ == "__main__":
