@@ -36,6 +36,30 @@ def af_gain(P, irx=0):
     return pow(10., P.AF_GAIN) - 1
 
 
+def audio_out(P, am):
+    """What reference receiver.py:153-225 pushes to the audio players for one chunk (compute part only; the players and
+    their ring buffers are out of scope).  am: list of per-receiver audio of this chunk.  Returns one payload per player:
+    AUDIO_SCHEME 2 (:158-188) routes two mono receivers to one player as ``am1*g1 + 1j*am2*g2`` with the partner
+    irx + (NUM_RX+1)//2; otherwise (:190-225) every receiver has its own player and gets ``am*gain`` (0 when muted or
+    auto-muted).  The gain is the slider law 10**AF_GAIN - 1 (:173,200)."""
+    n_rx = int(P.NUM_RX)
+    g = pow(10., P.AF_GAIN) - 1
+    if getattr(P, 'AUDIO_SCHEME', 1) == 2:
+        n2 = int((n_rx + 1) / 2)
+        out = []
+        for irx in range(n2):
+            a1 = np.asarray(am[irx]).real
+            g1 = 0. if P.MUTED[irx] else g
+            if irx + n2 < n_rx:
+                a2 = np.asarray(am[irx + n2]).real
+                g2 = 0. if P.MUTED[irx + n2] else g
+            else:
+                a2, g2 = 0, 0.
+            out.append(a1 * g1 + 1j * a2 * g2)
+        return out
+    return [np.asarray(am[irx]) * af_gain(P, irx) for irx in range(n_rx)]
+
+
 class SDR_EXECUTIVE:
     """Replay-mode executive (reference receiver.py:408-782, MP_SCHEME 1 data plane)."""
 

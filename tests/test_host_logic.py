@@ -179,3 +179,21 @@ def test_capture_file_roundtrip_and_replay_setup(tmp_path):
         f.write(b"\0" * 200)
     with pytest.raises(ValueError):
         sdr_fileio(str(tmp_path / "junk.dat"), 'r', None)
+
+
+def test_audio_out_routing_schemes():
+    """reference receiver.py:153-225: slider gain law, mute, and AUDIO_SCHEME 2's two-receivers-per-player packing."""
+    from pysdr_b200.receiver import audio_out
+    P, _ = make_both(8, [1000, 1100, 1200], ['USB', 'AM', 'CW'])
+    am = [np.full(4, 1.0, np.float32), np.full(4, 2.0, np.float32), np.full(4, 3.0, np.float32)]
+    g = 10 ** P.AF_GAIN - 1
+    out = audio_out(P, am)
+    assert len(out) == 3 and all(np.allclose(out[r], am[r] * g) for r in range(3))
+    P.MUTED[1] = True
+    assert np.all(audio_out(P, am)[1] == 0)
+    P.AUDIO_SCHEME = 2                                           # players: (rx0 + j rx2), (rx1 + j 0)
+    out = audio_out(P, am)
+    assert len(out) == 2
+    assert np.allclose(out[0], 1.0 * g + 1j * 3.0 * g) and np.allclose(out[1], 0.0)
+    P.MUTED[1] = False
+    assert np.allclose(audio_out(P, am)[1], 2.0 * g + 0j)
