@@ -323,7 +323,9 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
             // Interior tiles (almost all): the refill is one aligned bulk copy whose address follows from the running
             // tile offset — no 64-bit multiplies and no edge loop on the warp that is already the last one
             // (0.859 -> 0.842 ms at cfg2).  Measured and rejected here: an extra cp.async.bulk.prefetch.L2 one, two or
-            // four tiles ahead (0.865 ms), and consuming the arrival count one task later (0.965 ms).
+            // four tiles ahead (0.865 ms), consuming the arrival count one task later (0.965 ms), and an "empty" mbarrier
+            // with a rotating refill warp instead of the atomic counter (0.864 ms): anything that delays the refill by
+            // even a fraction of a tile costs more than the atomic's latency.
             const i64 Tn = T + (i64)K1F_STAGES * Tstep;
             if (Tn < g.n_tiles) {
                 const i64 rel_n = relb + (i64)K1F_STAGES * d_rel;
