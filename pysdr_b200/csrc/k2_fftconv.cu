@@ -65,7 +65,7 @@ __device__ __forceinline__ float2 k2_detect(const float2 *raw, int e, int mode, 
 }
 
 template <int N>
-__global__ void __launch_bounds__(FftPlan<N>::THREADS)
+__global__ void __launch_bounds__(FftPlan<N>::THREADS, (N == 4096 ? 3 : 1))
 af_fftconv_kernel(const FftConvArgs a) {
     extern __shared__ __align__(16) float2 s[];
     constexpr int T = FftPlan<N>::THREADS;
