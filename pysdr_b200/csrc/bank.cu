@@ -467,24 +467,6 @@ __global__ void copy_f32_kernel(const float *__restrict__ s, float *__restrict__
     for (; i < n; i += stride) d[i] = s[i];
 }
 
-// K2f / input memory roll: dst[0..len) = src[0..len) where the ranges may overlap (single CTA per row).
-__global__ void __launch_bounds__(1024) roll_kernel(float2 *base, i64 row_stride, i64 src_off, int len) {
-    float2 *row = base + (size_t)blockIdx.x * row_stride;
-    float2 tmp[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int e = threadIdx.x + k * 1024;
-        if (e < len) tmp[k] = row[src_off + e];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int e = threadIdx.x + k * 1024;
-        if (e < len) row[e] = tmp[k];
-    }
-}
-
-// new input memory: hist'[k] = sample (n_in - need + k) of the stream [hist | x]
 __global__ void hist_update_kernel(float2 *hist, const float2 *__restrict__ hist_src, const float2 *__restrict__ x,
                                    int need, i64 n_in) {
     // single CTA; read everything first (hist may alias hist_src)
@@ -502,6 +484,64 @@ __global__ void hist_update_kernel(float2 *hist, const float2 *__restrict__ hist
     for (int k = 0; k < 4; ++k) {
         const int e = threadIdx.x + k * 1024;
         if (e < need) hist[e] = tmp[k];
+    }
+}
+
+// End-of-call state update in ONE launch: blocks 0..n_rx-1 roll the complex memories C[r][0..hc) <- C[r][n_out..n_out+hc),
+// block n_rx moves the raw input memory on (the last `need` samples of [hist | x]).
+__global__ void __launch_bounds__(1024) state_update_kernel(float2 *C, i64 c_stride, i64 n_out, int hc, int n_rx, float2 *hist,
+                                                            const float2 *__restrict__ hist_src, const float2 *__restrict__ x,
+                                                            int need, i64 n_in) {
+    float2 tmp[4];
+    if ((int)blockIdx.x < n_rx) {
+        float2 *row = C + (size_t)blockIdx.x * c_stride;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = threadIdx.x + k * 1024;
+            if (e < hc) tmp[k] = row[n_out + e];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = threadIdx.x + k * 1024;
+            if (e < hc) row[e] = tmp[k];
+        }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = threadIdx.x + k * 1024;
+        if (e < need) {
+            const i64 idx = n_in - need + e;                 // relative to x[0]
+            tmp[k] = idx >= 0 ? x[idx] : hist_src[need + idx];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = threadIdx.x + k * 1024;
+        if (e < need) hist[e] = tmp[k];
+    }
+}
+
+// seek(): every carried state back to "nothing before this sample" in ONE launch: blocks 0..n_rx-1 clear the complex
+// memories, block n_rx clears the raw input memory and the PLL states and (at the stream origin) resets the AGCs.
+__global__ void __launch_bounds__(256) seek_reset_kernel(float2 *C, i64 c_stride, int hc, int n_rx, float2 *hist, int n_hist,
+                                                         double2 *pll, AgcState *agc, int reset_agc) {
+    const float2 z = make_float2(0.f, 0.f);
+    if ((int)blockIdx.x < n_rx) {
+        float2 *row = C + (size_t)blockIdx.x * c_stride;
+        for (int e = threadIdx.x; e < hc; e += blockDim.x) row[e] = z;
+        return;
+    }
+    for (int e = threadIdx.x; e < n_hist; e += blockDim.x) hist[e] = z;
+    if (threadIdx.x < PYSDR_MAX_RX) {
+        const int r = threadIdx.x;
+        pll[r] = make_double2(0.0, 0.0);
+        if (reset_agc) {
+            for (int i = 0; i < PYSDR_AGC_NB; ++i) agc[r].ring[i] = 0.0;
+            agc[r].k = 0; agc[r].gain = 1.0; agc[r].maxbuf = 0.0; agc[r].err = 0.0;
+        }
     }
 }
 
@@ -1016,14 +1056,12 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
     if (rc) return rc;
     if ((rc = mark())) return rc;
 
-    // input memory for the next call
-    if (b->need > 0) {
-        hist_update_kernel<<<1, 1024, 0, st>>>(b->d_hist, a.hist, a.x, b->need, n_in);
-        LAUNCH_CHECK();
-        b->launches++;
-    }
-
-    if (n_out == 0 || b->k1_only) {          // ragged tail too short to emit a sample (only the input memory moves),
+    if (n_out == 0 || b->k1_only) {
+        if (b->need > 0) {                   // input memory for the next call (the audio-rate path does it in state_update)
+            hist_update_kernel<<<1, 1024, 0, st>>>(b->d_hist, a.hist, a.x, b->need, n_in);
+            LAUNCH_CHECK();
+            b->launches++;
+        }          // ragged tail too short to emit a sample (only the input memory moves),
                                              // or a K1-only bank (WFM video stage): no audio-rate stages
         b->pend_n_out = 0; b->pend_m0 = m0; b->pend_B0 = B0; b->pend_blocks = n_blocks;
         b->pend_peaks = d_peaks;
@@ -1120,8 +1158,9 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
         LAUNCH_CHECK();
         b->launches++;
     }
-    // roll the complex memory: C[0..hc) <- C[n_out .. n_out+hc)
-    roll_kernel<<<c.n_rx, 1024, 0, st>>>(b->d_C, b->c_stride, n_out, b->hc);
+    // carried memories for the next call: complex memory C[0..hc) <- C[n_out .. n_out+hc) and the raw input memory
+    state_update_kernel<<<c.n_rx + 1, 1024, 0, st>>>(b->d_C, b->c_stride, n_out, b->hc, c.n_rx, b->d_hist, a.hist, a.x, b->need,
+                                                     n_in);
     LAUNCH_CHECK();
     b->launches++;
 
@@ -1247,13 +1286,6 @@ extern "C" int pysdr_bank_process(pysdr_bank *b, const void *d_iq, int64_t n_in,
     return pysdr_bank_process_back(b, nullptr, 0, 0, d_am, d_am_dc, out_stride, stream);
 }
 
-__global__ void agc_reset_kernel(AgcState *s, int n) {
-    const int r = threadIdx.x;
-    if (r >= n) return;
-    for (int i = 0; i < PYSDR_AGC_NB; ++i) s[r].ring[i] = 0.0;
-    s[r].k = 0; s[r].gain = 1.0; s[r].maxbuf = 0.0; s[r].err = 0.0;
-}
-
 extern "C" int pysdr_bank_seek(pysdr_bank *b, int64_t n0_abs, void *stream) {
     if (!b || n0_abs < 0 || n0_abs % b->cfg.in_chunk != 0) {
         pysdr_set_error("seek: position must be a non-negative multiple of IN_CHUNK_SIZE");
@@ -1262,15 +1294,11 @@ extern "C" int pysdr_bank_seek(pysdr_bank *b, int64_t n0_abs, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     b->n0 = n0_abs;
     b->pending = false;
-    CUDA_TRY(cudaMemsetAsync(b->d_hist, 0, sizeof(float2) * (size_t)(b->need + 8), st));
-    CUDA_TRY(cudaMemsetAsync(b->d_pll, 0, sizeof(double2) * PYSDR_MAX_RX, st));
-    CUDA_TRY(cudaMemset2DAsync(b->d_C, sizeof(float2) * (size_t)b->c_stride, 0, sizeof(float2) * (size_t)b->hc,
-                               (size_t)b->cfg.n_rx, st));
-    if (n0_abs == 0) {                       // back at the stream origin: a fresh set of receivers
-        agc_reset_kernel<<<1, 32, 0, st>>>(b->d_agc, PYSDR_MAX_RX);
-        LAUNCH_CHECK();
-        b->launches++;
-    }
+    // one launch; at the stream origin (n0 = 0) the AGCs restart too: a fresh set of receivers
+    seek_reset_kernel<<<b->cfg.n_rx + 1, 256, 0, st>>>(b->d_C, b->c_stride, b->hc, b->cfg.n_rx, b->d_hist, b->need + 8, b->d_pll,
+                                                       b->d_agc, n0_abs == 0 ? 1 : 0);
+    LAUNCH_CHECK();
+    b->launches++;
     return PYSDR_OK;
 }
 
