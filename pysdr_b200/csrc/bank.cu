@@ -295,7 +295,7 @@ struct AgcScanArgs {
 // so the recurrence over blocks — this call's own blocks and, in time-sharded runs, the replay of all EARLIER
 // shards' blocks — is an ordered parallel scan in float64 (re-association changes gains at the 1e-16 level,
 // far below the float32 gain that is applied).  One CTA per receiver.
-#define AGC_TILE 2048
+#define AGC_TILE 3072                 /* one tile covers the 2812 blocks of the 60 s capture (36.9 KB of shared memory) */
 #define AGC_THREADS 256
 
 struct AgcFn { double A, C, D; };
