@@ -245,12 +245,23 @@ block_peak_kernel(const float *__restrict__ a, i64 a_row, float *__restrict__ pe
     i64 lo, hi;
     block_range_warp(blk, B0, in_chunk, up, down, m0, n_out, lo, hi);
     float mx = 0.f;
-    for (i64 i = lo + lane; i < hi; i += 32 * 8) {
-        float v[8];
+    // scalar head up to the first 16-byte boundary, 16-byte body (8 loads = 128 B in flight per lane), scalar tail
+    const i64 head = ((4 - (i64)(((unsigned long long)(a + lo) >> 2) & 3ull)) & 3);
+    const i64 b0 = (lo + head < hi) ? lo + head : hi;
+    const i64 n4 = (hi - b0) >> 2;
+    if (lo + lane < b0) mx = fabsf(a[lo + lane]);
+    const float4 *a4 = (const float4 *)(a + b0);
+    for (i64 i = lane; i < n4; i += 32 * 8) {
+        float4 v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = (i + 32 * u < hi) ? a[i + 32 * u] : 0.f;
+        for (int u = 0; u < 8; ++u) v[u] = (i + 32 * u < n4) ? a4[i + 32 * u] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) mx = fmaxf(mx, fabsf(v[u]));
+        for (int u = 0; u < 8; ++u)
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[u].x), fabsf(v[u].y))), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
+    }
+    {
+        const i64 t = b0 + (n4 << 2) + lane;
+        if (t < hi) mx = fmaxf(mx, fabsf(a[t]));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -444,6 +455,26 @@ agc_apply_kernel(const float *__restrict__ a, i64 a_row, const float *__restrict
     block_range_warp(blk, B0, in_chunk, up, down, m0, n_out, lo, hi);
     const float g = gains[(size_t)blockIdx.y * g_row + blk];
     float sum = 0.f;
+    if (!am_dc && ((((unsigned long long)(a + lo)) ^ ((unsigned long long)(am + lo))) & 15ull) == 0) {
+        // audio only, source and destination equally aligned: scalar head, 16-byte body, scalar tail
+        const i64 head = ((4 - (i64)(((unsigned long long)(a + lo) >> 2) & 3ull)) & 3);
+        const i64 b0 = (lo + head < hi) ? lo + head : hi;
+        const i64 n4 = (hi - b0) >> 2;
+        if (lo + lane < b0) am[lo + lane] = a[lo + lane] * g;
+        const float4 *a4 = (const float4 *)(a + b0);
+        float4 *o4 = (float4 *)(am + b0);
+        for (i64 i = lane; i < n4; i += 32 * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (i + 32 * u < n4) v[u] = a4[i + 32 * u];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (i + 32 * u < n4) o4[i + 32 * u] = make_float4(v[u].x * g, v[u].y * g, v[u].z * g, v[u].w * g);
+        }
+        const i64 t = b0 + (n4 << 2) + lane;
+        if (t < hi) am[t] = a[t] * g;
+        return;
+    }
     for (i64 i = lo + lane; i < hi; i += 32 * 8) {
         float v[8];
 #pragma unroll
