@@ -161,6 +161,11 @@ int pysdr_bank_set_timing(pysdr_bank *b, int on);
 int pysdr_bank_get_timing(pysdr_bank *b, double out4[4], void *stream);
 /* # of kernels launched by this handle so far (bench.py's gpu_launches). */
 int64_t pysdr_bank_launch_count(const pysdr_bank *b);
+/* The bank's complex memory: row r = [hist_len carried baseband samples | the n_out samples of the last call], complex64,
+ * rows row_stride apart.  The new-sample part of a row IS rx.iq of the last call (valid until the next one), so a host
+ * that passes d_iq_bb = NULL to process / process_front reads rx.iq from here without a second copy being written —
+ * except for receivers in PYSDR_MODE_AMSYNC, whose new samples are de-rotated in place by the carrier loop. */
+int pysdr_bank_c_memory(pysdr_bank *b, void **d_ptr, int64_t *row_stride, int32_t *hist_len);
 
 /* ---- a13: scipy.signal.lfilter(b,a,x,zi) with carried state (reference sigs/iir.py:90-105) ----
  * float64 direct-form-II-transposed, evaluated as a block-parallel linear scan.

@@ -23,6 +23,14 @@ def _f32_ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+class _DeviceMemory:
+    """float32 device memory owned by the library, exposed to torch without a copy (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
 class ReceiverBank:
     """n_rx receivers on one stream.
 
@@ -60,7 +68,13 @@ class ReceiverBank:
             self.set_freq(r, freqs[r])
             self.set_dec_taps(r, self.filter_bank[vidx])
         # output buffers (owned here, handed to the library per call)
-        self._iq = torch.empty((self.n_rx, self.max_out), dtype=torch.complex64, device=self.device)
+        self._iq = None                                       # separate rx.iq copy: allocated only if AM-Synch needs it
+        # rx.iq is read straight from the bank's complex memory (K1's output) — no second copy is written
+        ptr, stride, hc = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int32()
+        check(self.lib.pysdr_bank_c_memory(self.h, ctypes.byref(ptr), ctypes.byref(stride), ctypes.byref(hc)))
+        self._hc = hc.value
+        mem = _DeviceMemory(ptr.value, self.n_rx * stride.value * 2)
+        self._cmem = torch.view_as_complex(torch.as_tensor(mem, device=self.device).view(self.n_rx, stride.value, 2))
         self._am = torch.empty((self.n_rx, 2 * self.max_out), dtype=torch.float32, device=self.device)
         self._am_dc = torch.empty((self.n_rx, 2 * self.max_out), dtype=torch.float32, device=self.device)
         self.n_out = 0
@@ -197,7 +211,7 @@ class ReceiverBank:
         self.sync_demod()
         n_out = ctypes.c_int64(0)
         check(self.lib.pysdr_bank_process(self.h, ctypes.c_void_p(x.data_ptr()), x.numel(), 1 if halo_in_place else 0,
-                                          ctypes.c_void_p(self._iq.data_ptr()), ctypes.c_void_p(self._am.data_ptr()),
+                                          self._iq_copy_ptr(), ctypes.c_void_p(self._am.data_ptr()),
                                           ctypes.c_void_p(self._am_dc.data_ptr()) if want_dc else None,
                                           self.max_out, ctypes.byref(n_out), _stream_ptr()))
         self.n_out = n_out.value
@@ -208,7 +222,7 @@ class ReceiverBank:
         self.sync_demod()
         n_out = ctypes.c_int64(0)
         check(self.lib.pysdr_bank_process_front(self.h, ctypes.c_void_p(x.data_ptr()), x.numel(),
-                                                1 if halo_in_place else 0, ctypes.c_void_p(self._iq.data_ptr()),
+                                                1 if halo_in_place else 0, self._iq_copy_ptr(),
                                                 self.max_out, ctypes.c_void_p(peaks.data_ptr()), ctypes.byref(n_out),
                                                 _stream_ptr()))
         self.n_out = n_out.value
@@ -235,8 +249,25 @@ class ReceiverBank:
             else:
                 am.append(self._am[r, :n])
                 dc.append(self._am_dc[r, :n])
-            iq.append(self._iq[r, :n])
+            iq.append(self.iq_row(r, n))
         return am, iq, dc
+
+    def _iq_copy_ptr(self):
+        """Device pointer for a separate rx.iq copy, or None when rx.iq can be read from the complex memory (every mode
+        but AM-Synch, whose carrier loop de-rotates that memory in place)."""
+        self._iq_separate = any(self._mode_of(r) == 'AM-Synch' for r in range(self.n_rx))
+        if not self._iq_separate:
+            return None
+        if self._iq is None:
+            self._iq = torch.empty((self.n_rx, self.max_out), dtype=torch.complex64, device=self.device)
+        return ctypes.c_void_p(self._iq.data_ptr())
+
+    def iq_row(self, r, n=None):
+        """rx.iq of receiver r from the last call (device view, valid until the next call)."""
+        n = self.n_out if n is None else n
+        if getattr(self, '_iq_separate', False):
+            return self._iq[r, :n]
+        return self._cmem[r, self._hc:self._hc + n]
 
     def process_host(self, x_np, want_dc=True):
         """Host buffers in, host buffers out (the reference-facing call): H2D, kernels, D2H."""
@@ -260,7 +291,7 @@ class ReceiverBank:
         for r in range(self.n_rx):
             w = 2 * no if cplx[r] else no
             self._h_am[r, :w].copy_(self._am[r, :w], non_blocking=True)
-            self._h_iq[r, :no].copy_(self._iq[r, :no], non_blocking=True)
+            self._h_iq[r, :no].copy_(self.iq_row(r, no), non_blocking=True)
             if want_dc:
                 self._h_dc[r, :w].copy_(self._am_dc[r, :w], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()

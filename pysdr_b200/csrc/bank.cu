@@ -966,6 +966,14 @@ extern "C" int pysdr_bank_k1_variant(const pysdr_bank *b) {
 }
 extern "C" int64_t pysdr_bank_launch_count(const pysdr_bank *b) { return b ? b->launches : -1; }
 
+extern "C" int pysdr_bank_c_memory(pysdr_bank *b, void **d_ptr, int64_t *row_stride, int32_t *hist_len) {
+    if (!b || !d_ptr || !row_stride || !hist_len) { pysdr_set_error("c_memory: bad arguments"); return PYSDR_ERR_ARG; }
+    *d_ptr = b->d_C;
+    *row_stride = b->c_stride;
+    *hist_len = b->hc;
+    return PYSDR_OK;
+}
+
 // folded taps: G[rx][p][j] = h[p + j*up] * exp(+j*2*pi*frac(inc*j / 2^64)), zero padded to lp_pad
 static int upload_folded_taps(pysdr_bank *b, cudaStream_t st) {
     const pysdr_bank_config &c = b->cfg;

@@ -187,7 +187,7 @@ class ReplayStreamer:
             for r in range(bank.n_rx):                          # row by row: contiguous copies stay asynchronous (a strided
                 self.h_am[i, r, :w].copy_(bank._am[r, :w], non_blocking=True)   # 2-D device-to-host copy_ blocks the host)
                 if self.want_iq:
-                    self.h_iq[i, r, :no].copy_(bank._iq[r, :no], non_blocking=True)
+                    self.h_iq[i, r, :no].copy_(bank.iq_row(r, no), non_blocking=True)
         cs.synchronize()
         return self.h_am, self.n_out_seg
 
