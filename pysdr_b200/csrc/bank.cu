@@ -232,12 +232,57 @@ __device__ __forceinline__ void block_range_warp(i64 b, i64 B0, i64 in_chunk, in
     hi = e > n_out ? n_out : e;
 }
 
+// End-of-call state update: work item r < n_rx rolls complex memory C[r][0..hc) <- C[r][n_out..n_out+hc), work item n_rx
+// moves the raw input memory on (the last `need` samples of [hist | x]).  Any block size; memories are <= 4096 samples.
+struct StateArgs {
+    float2 *C; i64 c_stride, n_out; int hc, n_rx;
+    float2 *hist; const float2 *hist_src, *x; int need; i64 n_in;
+    int enabled;
+};
+__device__ __forceinline__ void state_update_item(const StateArgs &sa, int item) {
+    float2 tmp[16];
+    const int T = blockDim.x;
+    if (item < sa.n_rx) {
+        float2 *row = sa.C + (size_t)item * sa.c_stride;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int e = threadIdx.x + k * T;
+            if (e < sa.hc) tmp[k] = row[sa.n_out + e];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int e = threadIdx.x + k * T;
+            if (e < sa.hc) row[e] = tmp[k];
+        }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int e = threadIdx.x + k * T;
+        if (e < sa.need) {
+            const i64 idx = sa.n_in - sa.need + e;           // relative to x[0]
+            tmp[k] = idx >= 0 ? sa.x[idx] : sa.hist_src[sa.need + idx];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int e = threadIdx.x + k * T;
+        if (e < sa.need) sa.hist[e] = tmp[k];
+    }
+}
+
 // K2c: peak of |a| per block.  One warp per block (a block is ~OUT_CHUNK_SIZE = 1024 samples), 8 blocks per CTA,
 // 8 loads in flight per lane.  grid (ceil(n_blocks/8), n_rx).
 #define BLK_WARPS 8
 __global__ void __launch_bounds__(32 * BLK_WARPS)
 block_peak_kernel(const float *__restrict__ a, i64 a_row, float *__restrict__ peaks, i64 peaks_row, i64 n_blocks, i64 B0,
-                  i64 in_chunk, int up, int down, i64 m0, i64 n_out) {
+                  i64 in_chunk, int up, int down, i64 m0, i64 n_out, int n_rows, const StateArgs sa) {
+    if ((int)blockIdx.y == n_rows) {         // extra grid row: the end-of-call state update rides this launch
+        if ((int)blockIdx.x <= sa.n_rx) state_update_item(sa, blockIdx.x);
+        return;
+    }
     const int lane = threadIdx.x & 31;
     const i64 blk = (i64)blockIdx.x * BLK_WARPS + (threadIdx.x >> 5);
     if (blk >= n_blocks) return;
@@ -502,43 +547,6 @@ __global__ void hist_update_kernel(float2 *hist, const float2 *__restrict__ hist
                                    int need, i64 n_in) {
     // single CTA; read everything first (hist may alias hist_src)
     float2 tmp[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int e = threadIdx.x + k * 1024;
-        if (e < need) {
-            const i64 idx = n_in - need + e;                 // relative to x[0]
-            tmp[k] = idx >= 0 ? x[idx] : hist_src[need + idx];
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int e = threadIdx.x + k * 1024;
-        if (e < need) hist[e] = tmp[k];
-    }
-}
-
-// End-of-call state update in ONE launch: blocks 0..n_rx-1 roll the complex memories C[r][0..hc) <- C[r][n_out..n_out+hc),
-// block n_rx moves the raw input memory on (the last `need` samples of [hist | x]).
-__global__ void __launch_bounds__(1024) state_update_kernel(float2 *C, i64 c_stride, i64 n_out, int hc, int n_rx, float2 *hist,
-                                                            const float2 *__restrict__ hist_src, const float2 *__restrict__ x,
-                                                            int need, i64 n_in) {
-    float2 tmp[4];
-    if ((int)blockIdx.x < n_rx) {
-        float2 *row = C + (size_t)blockIdx.x * c_stride;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int e = threadIdx.x + k * 1024;
-            if (e < hc) tmp[k] = row[n_out + e];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int e = threadIdx.x + k * 1024;
-            if (e < hc) row[e] = tmp[k];
-        }
-        return;
-    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int e = threadIdx.x + k * 1024;
@@ -1186,9 +1194,16 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
         b->launches += 3;
     }
     {
-        dim3 grid((unsigned)((n_blocks + BLK_WARPS - 1) / BLK_WARPS), (unsigned)c.n_rx);   // IQ-mode rows produce unused values
+        // block peaks (IQ-mode rows produce unused values) + one extra grid row that carries the end-of-call state update:
+        // complex memory C[0..hc) <- C[n_out .. n_out+hc) and the raw input memory, for the next call
+        StateArgs sa;
+        sa.C = b->d_C; sa.c_stride = b->c_stride; sa.n_out = n_out; sa.hc = b->hc; sa.n_rx = c.n_rx;
+        sa.hist = b->d_hist; sa.hist_src = a.hist; sa.x = a.x; sa.need = b->need; sa.n_in = n_in; sa.enabled = 1;
+        unsigned gx = (unsigned)((n_blocks + BLK_WARPS - 1) / BLK_WARPS);
+        if (gx < (unsigned)c.n_rx + 1) gx = (unsigned)c.n_rx + 1;
+        dim3 grid(gx, (unsigned)c.n_rx + 1);
         block_peak_kernel<<<grid, 32 * BLK_WARPS, 0, st>>>((const float *)b->d_a, 2 * b->a_stride, d_peaks, n_blocks, n_blocks, B0,
-                                                            c.in_chunk, c.up, c.down, m0, n_out);
+                                                            c.in_chunk, c.up, c.down, m0, n_out, c.n_rx, sa);
         LAUNCH_CHECK();
         b->launches++;
     }
@@ -1197,11 +1212,6 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
         LAUNCH_CHECK();
         b->launches++;
     }
-    // carried memories for the next call: complex memory C[0..hc) <- C[n_out .. n_out+hc) and the raw input memory
-    state_update_kernel<<<c.n_rx + 1, 1024, 0, st>>>(b->d_C, b->c_stride, n_out, b->hc, c.n_rx, b->d_hist, a.hist, a.x, b->need,
-                                                     n_in);
-    LAUNCH_CHECK();
-    b->launches++;
 
     if ((rc = mark())) return rc;
     b->pend_n_out = n_out; b->pend_m0 = m0; b->pend_B0 = B0; b->pend_blocks = n_blocks;
