@@ -147,8 +147,8 @@ int pysdr_bank_set_state(pysdr_bank *b, const void *host_blob, int64_t size, voi
 /* Which K1 variant the next process() will use: 0 generic, 1 tap-stationary fast path. */
 int pysdr_bank_k1_variant(const pysdr_bank *b);
 int pysdr_bank_force_generic(pysdr_bank *b, int on);
-/* K1-only bank (WFM video stage: LO + FIR at the RF rate, UP = DOWN = 1): process() stops after K1 and only d_iq_bb
- * is produced. */
+/* K1-only bank (WFM video stage: LO + FIR at the RF rate, UP = DOWN = 1): process() stops after K1; its output is the
+ * new-sample part of the complex memory (pysdr_bank_c_memory) and, when given, d_iq_bb. */
 int pysdr_bank_set_k1_only(pysdr_bank *b, int on);
 /* 3-point FM discriminator at any rate (reference sigs/nfm.m:123-127) with two carried samples:
  * out[n] = (Im(conj(y[n-1]) * (y[n] - y[n-2])), 0) as complex64; d_prev2: complex64[2] in/out. */
