@@ -197,3 +197,31 @@ def test_audio_out_routing_schemes():
     assert np.allclose(out[0], 1.0 * g + 1j * 3.0 * g) and np.allclose(out[1], 0.0)
     P.MUTED[1] = False
     assert np.allclose(audio_out(P, am)[1], 2.0 * g + 0j)
+
+
+def test_chirp_z_tables_reproduce_numpy_fft_for_the_rf_panel_length():
+    """Host side of czt.cu without a GPU: the Bluestein tables (float64 chirp, wrapped chirp spectrum in the kernels'
+    [512][256] position order) run through a numpy emulation of the four-step transform must give |FFT_65636|^2 —
+    the reference's RF panel length (Plotting.py:370-375)."""
+    from pysdr_b200 import _lib
+    from pysdr_b200.sig_proc import _czt_tables
+    lib = _lib.load()
+    chunk, nfft, M = 32818, 65636, 131072
+    win = np.hanning(chunk).astype(np.float32)
+    wc, bspec = _czt_tables(lib, win, chunk, nfft, M)
+    assert wc.shape == (chunk,) and bspec.shape == (512, 256) and bspec.dtype == np.complex64
+    k1 = np.array([lib.pysdr_fft_pos_to_freq(512, p) for p in range(512)])
+    k2 = np.array([lib.pysdr_fft_pos_to_freq(256, q) for q in range(256)])
+    assert sorted(k1) == list(range(512)) and sorted(k2) == list(range(256))          # permutations
+    rng = np.random.default_rng(5)
+    x = (rng.normal(size=chunk) + 1j * rng.normal(size=chunk)).astype(np.complex64)
+    a = np.zeros(M, np.complex128)
+    a[:chunk] = x.astype(np.complex128) * wc.astype(np.complex128)
+    A = np.fft.fft(a)                                                                  # spectrum in natural order ...
+    S = A[k1[:, None] + 512 * k2[None, :]]                                             # ... as the kernels hold it
+    Y = np.zeros(M, np.complex128)
+    Y[(k1[:, None] + 512 * k2[None, :]).ravel()] = (S * bspec.astype(np.complex128)).ravel()
+    y = np.fft.ifft(Y) * M                                                             # bspec carries the 1/M
+    got = np.abs(y[:nfft]) ** 2
+    ref = np.abs(np.fft.fft(x.astype(np.complex128) * win, nfft)) ** 2
+    assert np.max(np.abs(got - ref)) <= 2e-5 * ref.max()                               # complex64 tables
