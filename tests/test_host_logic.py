@@ -225,3 +225,22 @@ def test_chirp_z_tables_reproduce_numpy_fft_for_the_rf_panel_length():
     got = np.abs(y[:nfft]) ** 2
     ref = np.abs(np.fft.fft(x.astype(np.complex128) * win, nfft)) ** 2
     assert np.max(np.abs(got - ref)) <= 2e-5 * ref.max()                               # complex64 tables
+
+
+def test_wola_identity_for_uniform_channel_rasters():
+    """Design aid for config 5's next step (tools/wola_prototype.py): on a uniform raster the per-channel fused mix +
+    polyphase FIR equals one shared windowing pass + one 3125-point inverse DFT per output instant."""
+    import importlib.util
+    from scipy import signal
+    spec = importlib.util.spec_from_file_location("wola", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "wola_prototype.py"))
+    wp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(wp)
+    rng = np.random.default_rng(1)
+    fs, up, down = 10e6, 3, 625
+    h = signal.firwin(1001, 5e3, window='hamming', fs=fs * up) * up
+    x = rng.normal(size=30000) + 1j * rng.normal(size=30000)
+    ms = [37, 38, 39, 120]
+    d = wp.direct(x, h, up, down, fs, -3.0e6, 9600.0, 24, ms)
+    w, (a, nd) = wp.wola(x, h, up, down, fs, -3.0e6, 9600.0, 24, ms)
+    assert (a, nd) == (3, 3125)
+    assert np.max(np.abs(d - w)) <= 1e-10 * np.max(np.abs(d))
