@@ -468,16 +468,15 @@ __global__ void __launch_bounds__(AGC_THREADS) agc_scan_kernel(AgcScanArgs p) {
         t0 += len;
     }
     __syncthreads();
-    if (tid == 0) {
-        st.gain = s_g; st.err = s_err; st.maxbuf = s_mb;
-        for (int j = 0; j < 8; ++j) {                                      // ring <- the last 8 peaks seen
-            const i64 e = n_total - 1 - j;
-            if (e < 0) break;
-            st.ring[(int)((k0 + e) % 8)] = (double)(e < n_prev ? prev[e] : own[e - n_prev]);
-        }
-        st.k = k0 + n_total;
-        p.state[rx] = st;
+    if (tid < 8) {                                                         // ring <- the last 8 peaks seen (one lane each)
+        const i64 e = n_total - 1 - tid;
+        if (e >= 0) st.ring[(int)((k0 + e) & 7)] = (double)(e < n_prev ? prev[e] : own[e - n_prev]);
     }
+    if (tid == 8) { st.gain = s_g; st.err = s_err; st.maxbuf = s_mb; st.k = k0 + n_total; }
+    __syncthreads();
+    static_assert(sizeof(AgcState) % 8 == 0, "AgcState is copied in 8-byte words");
+    if (tid < (int)(sizeof(AgcState) / 8))
+        ((unsigned long long *)&p.state[rx])[tid] = ((const unsigned long long *)&st)[tid];
 }
 
 // K2e: am = a*gain ; am_dc = am - mean_block(am) for AM/USB.  grid (n_blocks, n_rx); IQ rows are skipped.
