@@ -166,6 +166,23 @@ int64_t pysdr_bank_launch_count(const pysdr_bank *b);
  * that passes d_iq_bb = NULL to process / process_front reads rx.iq from here without a second copy being written —
  * except for receivers in PYSDR_MODE_AMSYNC, whose new samples are de-rotated in place by the carrier loop. */
 int pysdr_bank_c_memory(pysdr_bank *b, void **d_ptr, int64_t *row_stride, int32_t *hist_len);
+/* Many-channel operation (wola.cu): the bank's complex memory can live in caller-owned device memory (n_rx rows,
+ * row_stride >= the bank's own stride, zero-initialised, not freed by the bank), and K1 can be left to the caller, who then
+ * writes the new baseband samples of every row at [hist_len, hist_len + n_out) on the same stream before process(). */
+int pysdr_bank_adopt_c_memory(pysdr_bank *b, void *d_ptr, int64_t row_stride);
+int pysdr_bank_set_k1_external(pysdr_bank *b, int on);
+
+/* Many channels on a uniform raster (BASELINE config 5; beyond the reference's MAX_RX): baseband IQ of n_ch channel
+ * receivers whose offsets are f0 + c*df with df/fs = a/3125 in lowest terms, from ONE windowing pass and ONE 3125-point
+ * inverse DFT per output instant (wola.cu) — same indexing contract and arithmetic definition as the per-receiver K1:
+ *   out[c][i] = e^{-j th_c(n_m)} sum_j G0[p_m][j] e^{+j 2 pi (a c) j/3125} x[n_m - j],  m = m0 + i, n_m = (m*down)/up, p_m = (m*down)%up
+ * d_x[0] is absolute sample n0, n_in samples; the n_before samples preceding it are at d_hist (NULL: in place, directly in
+ * front of d_x); anything earlier reads as zero.
+ * d_g0: complex64[up][lp] folded taps of channel 0 (lp <= 625); d_pos[c] = base-5 digit reversal of (a*c) mod 3125;
+ * d_inc[c]: 64-bit LO phase increment of channel c (phase 0 at absolute sample 0); d_out: complex64[n_ch][out_stride]. */
+int pysdr_wola_channelize(const void *d_x, const void *d_hist, int64_t n0, int64_t n_before, int64_t n_in, int64_t m0, int64_t n_out,
+                          int32_t up, int32_t down, int32_t lp, const void *d_g0, int32_t n_ch, const int32_t *d_pos,
+                          const uint64_t *d_inc, void *d_out, int64_t out_stride, void *stream);
 
 /* ---- a13: scipy.signal.lfilter(b,a,x,zi) with carried state (reference sigs/iir.py:90-105) ----
  * float64 direct-form-II-transposed, evaluated as a block-parallel linear scan.

@@ -68,6 +68,8 @@ SIGNATURES = {
     "pysdr_bank_set_k1_only": (c_int, [c_vp, c_int]),
     "pysdr_fm_disc": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "pysdr_bank_force_direct_fir": (c_int, [c_vp, c_int]),
+    "pysdr_bank_adopt_c_memory": (c_int, [c_vp, c_vp, c_i64]),
+    "pysdr_bank_set_k1_external": (c_int, [c_vp, c_int]),
     "pysdr_bank_c_memory": (c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), ctypes.POINTER(ctypes.c_int32)]),
     "pysdr_bank_launch_count": (c_i64, [c_vp]),
     "pysdr_lfilter_set_mode": (c_int, [c_int]),
@@ -84,6 +86,8 @@ SIGNATURES = {
     "pysdr_czt_destroy": (c_int, [c_vp]),
     "pysdr_czt_lines": (c_int, [c_vp, c_vp, c_i64, c_int, ctypes.c_int32, c_int, c_vp, ctypes.POINTER(c_i64), c_vp]),
     "pysdr_czt_launch_count": (c_i64, [c_vp]),
+    "pysdr_wola_channelize": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                      c_vp, ctypes.c_int32, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "pysdr_psd_configure": (c_int, [c_vp, ctypes.c_int32, c_vp, ctypes.c_int32]),
     "pysdr_waterfall_push": (c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_vp, ctypes.c_int32,
                                      ctypes.c_int32, ctypes.c_float, c_vp, c_vp, c_vp, c_vp]),

@@ -600,6 +600,8 @@ struct pysdr_bank {
     bool h_dirty[PYSDR_MAX_RX];             // AF taps changed: their position-order FFT must be refreshed
     bool force_direct_fir;                  // testing: use the direct-form AF FIR instead of the FFT path
     bool k1_only;                           // WFM video stage: stop after K1
+    bool k1_external;                       // the caller fills C[r][hc .. hc+n_out) itself (raster channelizer, wola.cu)
+    bool c_external;                        // d_C was adopted from the caller (not freed here)
     float2 *d_H;                            // [n_rx][Nfft] FFT of AF taps (position order, 1/N folded in)
     float2 *d_hist, *d_g, *d_C, *d_af;
     float2 *d_a;                            // pre-AGC audio, rows of a_stride float2 (IQ mode fills complex)
@@ -694,6 +696,7 @@ extern "C" int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out)
     b->force_generic = false;
     b->force_direct_fir = false;
     b->k1_only = false;
+    b->k1_external = false; b->c_external = false;
     b->stereo = false; b->pilot_min = 0.f;
     b->timing = false;
     b->launches = 0;
@@ -721,7 +724,8 @@ extern "C" int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out)
 extern "C" int pysdr_bank_destroy(pysdr_bank *b) {
     if (!b) return PYSDR_OK;
     cudaFree(b->d_H);
-    cudaFree(b->d_hist); cudaFree(b->d_g); cudaFree(b->d_C); cudaFree(b->d_af); cudaFree(b->d_R);
+    if (!b->c_external) cudaFree(b->d_C);
+    cudaFree(b->d_hist); cudaFree(b->d_g); cudaFree(b->d_af); cudaFree(b->d_R);
     cudaFree(b->d_a); cudaFree(b->d_peaks); cudaFree(b->d_gains); cudaFree(b->d_agc); cudaFree(b->d_pll);
     delete b;
     return PYSDR_OK;
@@ -847,6 +851,24 @@ extern "C" int pysdr_bank_force_direct_fir(pysdr_bank *b, int on) {
     b->force_direct_fir = on != 0;
     return PYSDR_OK;
 }
+extern "C" int pysdr_bank_adopt_c_memory(pysdr_bank *b, void *d_ptr, int64_t row_stride) {
+    if (!b || !d_ptr || row_stride < b->c_stride || (row_stride & 1)) {
+        pysdr_set_error("adopt_c_memory: need an even row stride >= %lld complex64 elements", b ? (long long)b->c_stride : 0LL);
+        return PYSDR_ERR_ARG;
+    }
+    if (!b->c_external) cudaFree(b->d_C);
+    b->d_C = (float2 *)d_ptr;
+    b->c_stride = row_stride;
+    b->c_external = true;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_set_k1_external(pysdr_bank *b, int on) {
+    if (!b) { pysdr_set_error("null bank"); return PYSDR_ERR_ARG; }
+    b->k1_external = on != 0;
+    return PYSDR_OK;
+}
+
 extern "C" int pysdr_bank_set_k1_only(pysdr_bank *b, int on) {
     if (!b) return PYSDR_ERR_ARG;
     b->k1_only = on != 0;
@@ -1092,7 +1114,9 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
         return PYSDR_OK;
     };
     if ((rc = mark())) return rc;
-    if (!b->force_generic && k1_fast_supported(c.up, c.down, b->lp, c.n_rx)) {
+    if (b->k1_external) {
+        rc = PYSDR_OK;                       // C[r][hc .. hc+n_out) was written by the caller on this stream
+    } else if (!b->force_generic && k1_fast_supported(c.up, c.down, b->lp, c.n_rx)) {
         rc = k1_launch_fast(a, st);
         b->launches += k1_fast_groups(b->lp, c.n_rx);
     } else {

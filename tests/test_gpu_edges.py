@@ -508,3 +508,69 @@ def test_paired_fft_keeps_a_weak_signal_accurate_next_to_a_strong_one():
     for r in range(2):
         ref = np.concatenate([Po.rx[r].demod_data(x[c * C:(c + 1) * C]) for c in range(3)])
         assert_parity(am[r].cpu().numpy(), ref, "rx%d" % r)
+
+
+def test_raster_channelizer_equals_per_channel_k1():
+    """wola.cu: 96 channels on the 9.6 kHz raster of config 5 (3/3125 of 10 MS/s) from one windowing pass + one 3125-point
+    inverse DFT per output instant == the per-receiver K1 of ChannelBank (and the oracle's resampler), two calls with
+    carried history, ragged second call."""
+    from pysdr_b200.channelizer import ChannelBank, RasterChannelizer
+    P, Po = make_both(10, [7000], ['IQ'])
+    n_ch, f0, df = 96, -450e3, 9600.0
+    C = P.IN_CHUNK_SIZE
+    n1, n2 = 2 * C, C + 12345
+    x = _noise(n1 + n2, 41, 0.05)
+    t = np.arange(len(x))
+    x = (x + 0.2 * np.exp(2j * np.pi * (f0 + 17 * df + 300.0) * t / P.SRATE)).astype(np.complex64)
+    rc = RasterChannelizer(P, f0, df, n_ch)
+    xd = torch.from_numpy(x).cuda()
+    y1 = rc.process(xd[:n1], n0=0, n_before=0)
+    keep = rc.lp - 1
+    y2 = rc.process(xd[n1 - keep:], n0=n1, n_before=keep)
+    got = torch.cat((y1, y2), dim=1).cpu().numpy()
+    assert got.shape == (n_ch, odsp.n_out_total(n1 + n2, P.UP, P.DOWN))
+    cb = ChannelBank(P, rc.offsets, 'IQ', max_in=n1 + n2)
+    _, iq = cb.process(xd[:3 * C])                                # whole chunks only for the bank
+    k = cb.n_out
+    for c in (0, 1, 17, 50, 95):
+        assert_parity(got[c, :k], iq[c].cpu().numpy(), "wola vs K1, channel %d" % c, rel_tol=2e-5, snr_min=90)
+    for c in (17, 95):
+        dec = odsp.decimator(Po.SRATE, Po.UP, Po.DOWN, Po.FILT_LEN, odsp.VIDEO_BWs, Po.VIDEO_BW)
+        dec.h = dec.filter_bank[odsp._video_index(Po)]
+        lo = odsp.signal_generator(rc.offsets[c], Po.IN_CHUNK_SIZE, Po.SRATE, True)
+        ref = dec.resamp_fast(x, lo)
+        assert_parity(got[c], ref, "wola vs oracle, channel %d" % c, rel_tol=2e-5, snr_min=90)
+
+
+def test_many_channel_bank_raster_mode_two_blocks():
+    """Config 5 with the raster channelizer in front: ONE wola.cu pass per block writes every channel's baseband into the
+    groups' shared complex memory, the groups run only their audio-rate stages; two blocks (carried input history, AF
+    memories, AGC), every channel against its own oracle receiver."""
+    from pysdr_b200.channelizer import ChannelBank, raster_offsets
+    P, Po = make_both(10, [7000], ['USB'], af_bw_khz=[2])
+    n_ch, C = 20, P.IN_CHUNK_SIZE
+    offs = raster_offsets(n_ch, 9600.0, 150e3)
+    modes = [['AM', 'NFM', 'USB', 'CW', 'LSB'][k % 5] for k in range(n_ch)]
+    afs = [[5e3, 10e3, 2e3, 500., 3e3][k % 5] for k in range(n_ch)]
+    n = np.arange(3 * C)
+    x = _noise(len(n), 78, 0.01).astype(np.complex128)
+    for k, f in enumerate(offs):
+        x = x + 0.02 * (1 + 0.5 * np.sin(2 * np.pi * (300.0 + 40 * k) * n / P.SRATE)) * np.exp(2j * np.pi * (f + 700.0) * n / P.SRATE)
+    x = x.astype(np.complex64)
+    cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=2 * C, raster=(offs[0], 9600.0))
+    xd = torch.from_numpy(x).cuda()
+    outs, iqs = [], []
+    for a, b in ((0, 2 * C), (2 * C, 3 * C)):
+        am, iq = cb.process(xd[a:b])
+        outs.append([v.cpu().numpy().copy() for v in am])
+        iqs.append([v.cpu().numpy().copy() for v in iq])
+    for k in range(n_ch):
+        Pk = rxo.make_P(P.SRATE, [7000e3], modes[k], foffset=100e3, af_bw=afs[k], bfo=700.0)
+        orx = odsp.Receiver(Pk, offs[k], 0, str(k), fast=True)
+        ref, refq = [], []
+        for c in range(3):
+            ref.append(np.array(orx.demod_data(x[c * C:(c + 1) * C])))
+            refq.append(orx.iq.copy())
+        got = np.concatenate([o[k] for o in outs])
+        assert_parity(np.concatenate([q[k] for q in iqs]), np.concatenate(refq), "iq channel %d" % k, rel_tol=2e-5, snr_min=90)
+        assert_parity(got, np.concatenate(ref), "channel %d (%s)" % (k, modes[k]), rel_tol=2e-4, snr_min=74)

@@ -52,6 +52,41 @@ def main():
     n_out = cb.n_out
     flops = 8.0 * lp * n_out * args.channels
     sec = n / P.SRATE
+    # the same channels' baseband IQ through the raster channelizer (wola.cu): K1 only
+    from pysdr_b200.channelizer import RasterChannelizer
+    rc = RasterChannelizer(P, offs[0], 9600.0, args.channels)
+    for _ in range(args.warmup):
+        rc.process(x)
+    torch.cuda.synchronize()
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
+    for _ in range(args.steps):
+        yw = rc.process(x)
+    w1.record()
+    torch.cuda.synchronize()
+    ms_w = w0.elapsed_time(w1) / args.steps
+    wola = {"ms_per_block_k1_only": ms_w, "Msamples_per_s": n / ms_w / 1e3, "realtime_factor": sec / (ms_w / 1e3),
+            "hbm_algorithmic_GBps(8 B in + 8 B per channel-output)": (8.0 * n + 8.0 * yw.numel()) / ms_w / 1e6}
+    print(json.dumps({"wola_k1": wola}))
+    del rc, yw
+    # whole chain with the raster channelizer in front of the groups' audio-rate stages
+    cbr = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=n, raster=(offs[0], 9600.0))
+    for _ in range(args.warmup):
+        cbr._n0 = 0
+        cbr.process(x)
+    torch.cuda.synchronize()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(args.steps):
+        cbr._n0 = 0
+        cbr.process(x)
+    r1.record()
+    torch.cuda.synchronize()
+    ms_r = r0.elapsed_time(r1) / args.steps
+    print(json.dumps({"raster_mode_whole_chain": {"ms_per_block": ms_r, "Msamples_per_s": n / ms_r / 1e3,
+                                                  "realtime_factor": sec / (ms_r / 1e3),
+                                                  "one_hour_capture_s_on_1_gpu": 3600.0 / (sec / (ms_r / 1e3))}}))
+    del cbr
     print(json.dumps({"workload": "cfg5 geometry: %d channels, 9.6 kHz raster, 10 MS/s, 3/625, %.2f s blocks (%d chunks), modes AM/NFM/USB/CW"
                                   % (args.channels, sec, args.block_chunks),
                       "ms_per_block": ms, "wall_ms_per_block": wall * 1e3, "Msamples_per_s": n / ms / 1e3,
