@@ -72,12 +72,39 @@ class ChannelBank:
             else:
                 self._x_hist.copy_(torch.cat((self._x_hist[x.numel():], x)))
             self._n0 += x.numel()
-        for b in self.banks:
-            a, q, _ = b.process(x, want_dc=want_dc)
-            am.extend(a)
-            iq.extend(q)
-        self.n_out = self.banks[0].n_out
-        return am, iq
+        if want_dc or self.raster is None:
+            for b in self.banks:
+                a, q, _ = b.process(x, want_dc=want_dc)
+                am.extend(a)
+                iq.extend(q)
+            self.n_out = self.banks[0].n_out
+            return am, iq
+        # raster mode, audio only: the groups are driven with prepared arguments (one ctypes call each: the host loop over
+        # 128 groups is otherwise the bottleneck once K1 is a single launch) and the views are built once per output length
+        import ctypes
+        from ._lib import check
+        if getattr(self, '_fast_args', None) is None:
+            for b in self.banks:
+                b._check_input(x)
+                b.sync_demod()
+                b._iq_copy_ptr()
+            self._fast_args = [(b.lib.pysdr_bank_process, b.h, ctypes.c_void_p(b._am.data_ptr()), b.max_out) for b in self.banks]
+            self._views_for = None
+        xp, n_in = ctypes.c_void_p(x.data_ptr()), x.numel()
+        n_out = ctypes.c_int64(0)
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        for fn, h, am_p, max_out in self._fast_args:
+            check(fn(h, xp, n_in, 0, None, am_p, None, max_out, ctypes.byref(n_out), st))
+        self.n_out = n_out.value
+        if self._views_for != self.n_out:
+            self._views = ([], [])
+            for b in self.banks:
+                b.n_out = self.n_out
+                a, q, _ = b.views()
+                self._views[0].extend(a)
+                self._views[1].extend(q)
+            self._views_for = self.n_out
+        return self._views
 
     def launch_count(self):
         return sum(b.lib.pysdr_bank_launch_count(b.h) for b in self.banks)
