@@ -128,6 +128,12 @@ class ShardedChannelBank:
     def step(self, xbuf):
         """xbuf: device samples [first_sample, start+n) of this rank's shard.  Returns (am, iq) lists over channels."""
         from .dist import exchange_agc_peaks
+        cb = self.cb
+        if cb.raster is not None:                                        # K1 of every channel for shard + warm-up in one pass
+            p = self.plan
+            C = int(cb.P.IN_CHUNK_SIZE)
+            n0 = p['start'] - p['warm_chunks'] * C
+            cb.raster.process(xbuf[p['halo']:], n0=n0, hist=xbuf[:p['halo']], out=cb._C, out_col=cb._hc)
         own = torch.cat([sh.front(xbuf) for sh in self.shards])          # [n_ch, n_blocks]
         prev = exchange_agc_peaks(own, self.rank, self.world)            # one collective for every channel
         am, iq = [], []

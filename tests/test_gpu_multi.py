@@ -80,7 +80,7 @@ def test_two_gpu_time_shard_equals_single_gpu(tmp_path, CPR):
         assert_parity(got_am, ref_am[r], "sharded vs single rx%d" % r, rel_tol=2e-5, snr_min=90)
 
 
-def _chan_worker(rank, world, port, outdir):
+def _chan_worker(rank, world, port, outdir, raster):
     import torch.distributed as dist
     from pysdr_b200.channelizer import ChannelBank, ShardedChannelBank, raster_offsets
     from pysdr_b200.params import RUN_TIME_PARAMS
@@ -94,7 +94,8 @@ def _chan_worker(rank, world, port, outdir):
         P = RUN_TIME_PARAMS(['-fs', '10', '-fc', '7000', '-mode', 'USB', '-af_bw', '2'])
         offs, modes, afs = _chan_cfg()
         C = P.IN_CHUNK_SIZE
-        cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=5 * C, device=dev)
+        cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=5 * C, device=dev,
+                         raster=(offs[0], 9600.0) if raster else None)
         sh = ShardedChannelBank(cb, rank, world, 3)
         pl = sh.plan
         xbuf = synth_iq(pl['lead'] + pl['n'], P.SRATE, offs[:4], modes[:4], seed=78, device=dev, n0=pl['first_sample'], block=1 << 16)
@@ -114,7 +115,8 @@ def _chan_cfg():
     return offs, modes, afs
 
 
-def test_two_gpu_many_channel_time_shard(tmp_path):
+@pytest.mark.parametrize("raster", [False, True])
+def test_two_gpu_many_channel_time_shard(tmp_path, raster):
     """Config 5's shape at test size: 20 channels (3 groups) on a 10 MS/s stream, time-sharded over 2 ranks with one
     all-gather of every channel's AGC peaks, equals the single-GPU single-stream result."""
     if torch.cuda.device_count() < 2:
@@ -124,7 +126,7 @@ def test_two_gpu_many_channel_time_shard(tmp_path):
     from pysdr_b200.params import RUN_TIME_PARAMS
     from pysdr_b200.synth import synth_iq
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_chan_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_chan_worker, args=(2, port, str(tmp_path), raster), nprocs=2, join=True)
     P = RUN_TIME_PARAMS(['-fs', '10', '-fc', '7000', '-mode', 'USB', '-af_bw', '2'])
     offs, modes, afs = _chan_cfg()
     C = P.IN_CHUNK_SIZE
