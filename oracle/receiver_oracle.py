@@ -113,10 +113,47 @@ def af_gain(P, irx=0):
     return pow(10., P.AF_GAIN) - 1
 
 
-def run_replay(P, raw, collect=('am', 'iq', 'am_dc')):
+def audio_payloads(P):
+    """What reference receiver.py:153-225 pushes to each player for the chunk just demodulated: AUDIO_SCHEME 2 packs
+    receiver i and its partner i + (NUM_RX+1)//2 as ``am1*g1 + 1j*am2*g2`` (:158-188, mute only — auto-mute is not
+    looked at in this branch); otherwise one player per receiver gets ``am*gain`` with gain 0 when muted or auto-muted."""
+    g = pow(10., P.AF_GAIN) - 1
+    if getattr(P, 'AUDIO_SCHEME', 1) == 2:
+        n2 = int((P.NUM_RX + 1) / 2)
+        out = []
+        for irx in range(n2):
+            a1 = P.rx[irx].am.real
+            g1 = 0. if P.MUTED[irx] else g
+            j = irx + n2
+            if j < P.NUM_RX:
+                a2, g2 = P.rx[j].am.real, (0. if P.MUTED[j] else g)
+            else:
+                a2, g2 = 0, 0.
+            out.append(a1 * g1 + 1j * a2 * g2)
+        return out
+    return [P.rx[irx].am * af_gain(P, irx) for irx in range(P.NUM_RX)]
+
+
+def mode_freq_change(P):
+    """reference receiver.py:634-650: a pending mode change takes effect between chunks; 'FM' means 'NFM'; receiver 0's
+    AGC and carrier PLL restart."""
+    if getattr(P, 'MODE_CHANGE', False):
+        if P.NEW_MODE == 'FM':
+            P.NEW_MODE = 'NFM'
+        if P.MODE != P.NEW_MODE:
+            P.MODE = P.NEW_MODE
+            P.rx[0].agc.reset()
+            P.rx[0].demod.am_pll.reset()
+        P.MODE_CHANGE = False
+
+
+def run_replay(P, raw, collect=('am', 'iq', 'am_dc'), on_iteration=None):
     """Replay loop, reference receiver.py:684-782 + read_chunk :538-559 (MP_SCHEME 1, no pre-mixer).
-    Returns dict of per-RX lists of per-chunk arrays, and the number of loop iterations."""
+    Returns dict of per-RX lists of per-chunk arrays, and the number of loop iterations.  on_iteration(k) runs at the
+    end of iteration k (where the reference saves the raw chunk, :755-758); 'audio' collects the player payloads."""
     out = {k: [[] for _ in range(P.NUM_RX)] for k in collect}
+    if 'auto_muted' in out:
+        out['auto_muted'] = []
     praw = 0
     x = np.zeros(P.IN_CHUNK_SIZE, np.complex64)                 # receiver.py:445
     dt = float(P.IN_CHUNK_SIZE) / P.SRATE
@@ -132,6 +169,7 @@ def run_replay(P, raw, collect=('am', 'iq', 'am_dc')):
             praw += P.IN_CHUNK_SIZE
         else:
             P.RX_DONE = True                                    # ... and the stale x is processed again
+        mode_freq_change(P)
         for irx in range(P.NUM_RX):
             am_dc = demodulate_data(P, x, irx)
             if 'am' in out:
@@ -140,5 +178,12 @@ def run_replay(P, raw, collect=('am', 'iq', 'am_dc')):
                 out['iq'][irx].append(P.rx[irx].iq.copy())
             if 'am_dc' in out:
                 out['am_dc'][irx].append(np.asarray(am_dc))
+        if 'audio' in out:
+            for i, a in enumerate(audio_payloads(P)):
+                out['audio'][i].append(np.asarray(a))
+        if 'auto_muted' in out:
+            out['auto_muted'].append(bool(P.AUTO_MUTED))
+        if on_iteration is not None:
+            on_iteration(iters)
         P.RX_DONE = P.RX_DONE or t >= P.DURATION
     return out, iters

@@ -78,6 +78,13 @@ class ReceiverBank:
         self._am = torch.empty((self.n_rx, 2 * self.max_out), dtype=torch.float32, device=self.device)
         self._am_dc = torch.empty((self.n_rx, 2 * self.max_out), dtype=torch.float32, device=self.device)
         self.n_out = 0
+        self._s1 = None
+
+    def scratch1(self):
+        """One float32 of device scratch (chunk power of the auto-mute detector)."""
+        if self._s1 is None:
+            self._s1 = torch.zeros(1, dtype=torch.float32, device=self.device)
+        return self._s1
 
     def __del__(self):
         try:

@@ -119,15 +119,21 @@ class sdr_fileio:
 SDR_FILEIO = sdr_fileio            # reference sigs/iq.py:59 spells it in capitals
 
 
-def open_replay(P, fname):
-    """Replay set-up of reference receiver.py:808-822: rates and chunk size follow the file's own sample rate."""
+def open_replay(P, fname, literal=False):
+    """Replay set-up of reference receiver.py:808-822: rates and chunk size follow the file's own sample rate.
+
+    Baseband captures are already at the audio rate, so FS_OUT = SRATE for them.  The reference tests this with
+    ``if P.REPLAY.find('baseband_iq'):`` (receiver.py:815) — str.find's truthiness, which is true for every name that does
+    NOT start with 'baseband_iq' (-1) and false only when the name starts with it (0).  literal=True reproduces exactly
+    that (what SDR_EXECUTIVE.create_SDR does, pinned by tests/golden/ref_callers.npz); the default implements the evident
+    intent ('baseband_iq' in the file name)."""
     from . import design
     P.REPLAY = fname
     P.sdr = sdr_fileio(fname, 'r', P)
     P.SRATE = P.sdr.srate
     P.REPLAY_FC = P.sdr.fc
     P.FC[0] = P.sdr.fc
-    if 'baseband_iq' in os.path.basename(fname):                 # receiver.py:815-816
+    if (fname.find('baseband_iq') if literal else 'baseband_iq' in os.path.basename(fname)):   # receiver.py:815-816
         P.FS_OUT = P.SRATE
     P.UP, P.DOWN = design.up_dn(P.SRATE, P.FS_OUT)
     P.FS_OUT = int(P.SRATE * P.UP / P.DOWN)

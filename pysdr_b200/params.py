@@ -20,7 +20,7 @@ class RUN_TIME_PARAMS:
         ap.add_argument('-mode', help='Demod mode(s)', type=str, default=['AM'], nargs='*', choices=MODES)
         ap.add_argument('-fs', help='RF sampling rate (MHz)', type=float, default=0)
         ap.add_argument('-fsout', help='Audio sampling rate (KHz)', type=float, default=48)
-        ap.add_argument('-foffset', help='Tuning offset (KHz)', type=float, default=0)
+        ap.add_argument('-foffset', help='Tuning offset (KHz)', type=float, default=100)     # params.py:80-81
         ap.add_argument('-vid_bw', help='Video bandwidth (KHz)', type=float, default=0)
         ap.add_argument('-af_bw', help='Audio bandwidth(s) (KHz)', type=float, default=[0], nargs='*')
         ap.add_argument('-nfilt', help='Decimation filter length', type=int, default=1001)
@@ -32,6 +32,9 @@ class RUN_TIME_PARAMS:
         ap.add_argument('-pan_dr', help='Waterfall dynamic range (dB)', type=float, default=60)
         ap.add_argument('-pan_bw', help='Pan bandwidth (KHz)', type=float, default=0)
         ap.add_argument('-src', type=int, default=[-1], nargs='*')
+        ap.add_argument('-audio', help='Audio scheme for routing RXs', type=int, default=1)   # params.py:71-72
+        ap.add_argument('-delay', help='Audio buffer delay', type=int, default=16)            # params.py:73-74
+        ap.add_argument('-mute', action='store_true')
         args = ap.parse_args(argv if argv is not None else [])
         for k, v in overrides.items():
             setattr(args, k, v)
@@ -41,8 +44,8 @@ class RUN_TIME_PARAMS:
         self.AF_FILTER_NUM = None                             # params.py:202
         self.VIDEO_FILTER_NUM = None
         self.audio_playback = False                           # params.py:203
-        self.SDR_TYPE = 'rtlsdr' if args.rtl else 'sdrplay'
-        self.REPLAY_MODE = args.replay is not None
+        self.REPLAY_MODE = bool(args.replay)
+        self.SDR_TYPE = 'replay' if self.REPLAY_MODE else ('rtlsdr' if args.rtl else 'sdrplay')   # utils.py:462-471
         self.REPLAY = args.replay[0] if args.replay else None
 
         fs = args.fs                                          # params.py:218-236: snap to the device's rate table
@@ -68,6 +71,15 @@ class RUN_TIME_PARAMS:
         mode = list(args.mode) if isinstance(args.mode, (list, tuple)) else [args.mode]
         self.MODE = mode[0] if len(mode) == 1 else (mode + [mode[-1]] * self.NUM_RX)[:self.NUM_RX]
         self.FOFFSET = args.foffset * 1e3
+        self.AUDIO_SCHEME = args.audio                        # params.py:287
+        if self.AUDIO_SCHEME == 1:                            # params.py:296-303
+            self.NUM_PLAYERS = int(self.NUM_RX)
+        elif self.AUDIO_SCHEME == 2:
+            self.NUM_PLAYERS = int((self.NUM_RX + 1) / 2)
+        else:
+            raise SystemExit('ERROR - Invalid audio playback scheme')
+        self.LOOPBACK = False
+        self.AUX_AUDIO = False
         src = np.atleast_1d(np.array(args.src) * 1)           # params.py:289-294
         while len(src) < self.NUM_RX:
             src = np.append(src, [-1])
@@ -111,7 +123,7 @@ class RUN_TIME_PARAMS:
         self.NEW_MODE = self.MODE
         self.FREQ_CHANGE = False
         self.AF_GAIN = 0.5                                    # params.py:425
-        self.MUTED = MAX_RX * [False]
+        self.MUTED = MAX_RX * [args.mute]                     # params.py:431
         self.OUT_CHUNK_SIZE = 1024                            # params.py:440
         self.IN_CHUNK_SIZE = int(self.OUT_CHUNK_SIZE * self.DOWN / float(self.UP) + 0 * 0.5)   # params.py:444
         self.ENABLE_AUTO_MUTE = args.auto_mute
@@ -119,7 +131,11 @@ class RUN_TIME_PARAMS:
         self.MUTE_CHUNKS = int(self.MUTE_TIME * self.FS_OUT / self.OUT_CHUNK_SIZE)             # params.py:449
         self.AUTO_MUTED = False
         self.RB_SIZE = design.rb_size(self.NUM_RX, self.FS_OUT, self.SDR_TYPE, self.OUT_CHUNK_SIZE)  # :456-468
+        self.DELAY = min(32, max(1, args.delay)) * self.OUT_CHUNK_SIZE                         # params.py:457
         design.adjust_foffset(self)                           # params.py:472
+        self.SHUT_DOWN = False
+        self.raw_iq_io = self.baseband_iq_io = self.demod_io = None
+        self.gui = None
         self.RX_DONE = False
         self.nchunks = 0
         self.Stopper = None

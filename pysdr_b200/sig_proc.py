@@ -56,17 +56,19 @@ class signal_generator:
 
 # ---------------------------------------------------------------------------------------------------
 class _Lo:
+    """``rx.lo`` (reference receiver.py:112,352, gui.py:1928,1938).  `_rx._bank` / `_rx._slot` name the bank row."""
+
     def __init__(self, rx):
         self._rx = rx
 
     @property
     def fo(self):
-        return self._rx._bank.fo[0]
+        return self._rx._bank.fo[self._rx._slot]
 
     def change_freq(self, f):
         if self._rx._wfm is not None:
             self._rx._wfm.vbank.set_freq(0, f)
-        return self._rx._bank.set_freq(0, f)
+        return self._rx._bank.set_freq(self._rx._slot, f)
 
 
 class _Dec:
@@ -83,7 +85,7 @@ class _Dec:
 
     @h.setter
     def h(self, taps):
-        self._rx._bank.set_dec_taps(0, taps)          # takes effect at the next chunk boundary
+        self._rx._bank.set_dec_taps(self._rx._slot, taps)          # takes effect at the next chunk boundary
         self._h = np.asarray(taps, np.float32)
 
 
@@ -94,15 +96,15 @@ class _Pll:
         self._rx = rx
 
     def reset(self):                                     # reference receiver.py:649
-        self._rx._bank.pll_reset(0)
+        self._rx._bank.pll_reset(self._rx._slot)
 
     @property
     def phi(self):
-        return self._rx._bank.pll_get(0)['phi']
+        return self._rx._bank.pll_get(self._rx._slot)['phi']
 
     @property
     def w(self):
-        return self._rx._bank.pll_get(0)['w']
+        return self._rx._bank.pll_get(self._rx._slot)['w']
 
 
 class _Holder:
@@ -126,10 +128,10 @@ class _Agc:
         self._rx = rx
 
     def reset(self):
-        self._rx._bank.agc_reset(0)
+        self._rx._bank.agc_reset(self._rx._slot)
 
     def _get(self, k):
-        return self._rx._bank.agc_get(0)[k]
+        return self._rx._bank.agc_get(self._rx._slot)[k]
 
     agc = property(lambda s: s._get('agc'))
     gain = property(lambda s: s._get('gain'))
@@ -152,6 +154,7 @@ class Receiver:
         self.irx = irx
         self.name = name
         self.sub = 0
+        self._slot = 0                                         # row of this receiver in its (one-row) bank
         self._view = _PView(P, irx)
         self._bank = ReceiverBank(self._view, [frq], max_in=int(P.IN_CHUNK_SIZE), video_bws=video_bws, af_bws=af_bws)
         self.lo = _Lo(self)
