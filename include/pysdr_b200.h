@@ -134,6 +134,21 @@ int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t n_in, int 
                              void *stream);
 int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, int64_t skip_blocks,
                             float *d_am, float *d_am_dc, int64_t out_stride, void *stream);
+/* O(1) AGC carry between time shards (replaces the all-gather of every block peak).  The per-block update
+ * gain <- min(w_b, beta w_b + (1-beta) gain) is closed under composition, and w_b depends on the last 8 peaks only, so a
+ * shard of n >= 8 blocks is summarised by PYSDR_AGC_SUMMARY_LEN doubles per receiver:
+ *     [0..2]  (A, C, D): gain_out = min(A, C + D gain_in) over the shard's blocks 7 .. n-1 (own peaks only)
+ *     [3..9]  the shard's first 7 block peaks (their w_b needs the previous shard's last peaks)
+ *     [10..17] the shard's last 8 block peaks (the peak buffer it hands on), oldest first
+ *     [18]    n
+ * agc_summary: after process_front; writes d_summary[n_rx][LEN] (device) for this call's blocks skip_blocks .. n-1.
+ * agc_enter:   sets the AGC state the NEXT process_back(NULL, 0, skip, ...) continues from, by running the summaries of
+ *              the n_before earlier shards (d_summaries[n_before][n_rx][LEN], device, in stream order) from the reset
+ *              state: 7 plain updates + one composed step per shard.  n_before = 0 gives the reset state. */
+#define PYSDR_AGC_SUMMARY_LEN 19
+int pysdr_bank_agc_summary(pysdr_bank *b, int64_t skip_blocks, double *d_summary, void *stream);
+int pysdr_bank_agc_enter(pysdr_bank *b, const double *d_summaries, int n_before, void *stream);
+
 /* Move the stream position without processing (time shards): n0 must be a multiple of in_chunk.
  * LO/BFO accumulators follow; filter memories are cleared; n0 == 0 also resets the AGC (stream restart).
  * Asynchronous on `stream`. */
@@ -166,6 +181,11 @@ int64_t pysdr_bank_launch_count(const pysdr_bank *b);
  * that passes d_iq_bb = NULL to process / process_front reads rx.iq from here without a second copy being written —
  * except for receivers in PYSDR_MODE_AMSYNC, whose new samples are de-rotated in place by the carrier loop. */
 int pysdr_bank_c_memory(pysdr_bank *b, void **d_ptr, int64_t *row_stride, int32_t *hist_len);
+/* AGC trace of the last process / process_back call (what reference watchdog.py:298-302 prints, per block instead of
+ * per tick): host_peaks / host_gains receive [n_rx][*n_blocks] float32 — the per-IN_CHUNK_SIZE-block peak of the pre-AGC
+ * audio and the gain applied to that block.  capacity = floats per row the caller provides.  Synchronises `stream`. */
+int pysdr_bank_agc_trace(pysdr_bank *b, float *host_peaks, float *host_gains, int64_t capacity, int64_t *n_blocks,
+                         void *stream);
 /* Many-channel operation (wola.cu): the bank's complex memory can live in caller-owned device memory (n_rx rows,
  * row_stride >= the bank's own stride, zero-initialised, not freed by the bank), and K1 can be left to the caller, who then
  * writes the new baseband samples of every row at [hist_len, hist_len + n_out) on the same stream before process(). */

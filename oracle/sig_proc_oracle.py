@@ -525,7 +525,7 @@ class agc:
             self.gain = want
         else:
             self.gain = self.beta * want + (1.0 - self.beta) * self.gain
-        self.agc = self.gain
+        self.agc = want                      # the gain the loop asks for; .gain is what it applies
         return self.gain
 
     def run(self, a):

@@ -72,6 +72,9 @@ SIGNATURES = {
     "pysdr_bank_set_k1_external": (c_int, [c_vp, c_int]),
     "pysdr_bank_c_memory": (c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), ctypes.POINTER(ctypes.c_int32)]),
     "pysdr_bank_launch_count": (c_i64, [c_vp]),
+    "pysdr_bank_agc_summary": (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "pysdr_bank_agc_enter": (c_int, [c_vp, c_vp, c_int, c_vp]),
+    "pysdr_bank_agc_trace": (c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),
     "pysdr_lfilter_set_mode": (c_int, [c_int]),
     "pysdr_lfilter": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
     "pysdr_abs_f32": (c_int, [c_vp, c_vp, c_i64, c_vp]),

@@ -161,6 +161,17 @@ class ReceiverBank:
         check(self.lib.pysdr_bank_agc_get(self.h, rx, out, _stream_ptr()))
         return dict(agc=out[0], gain=out[1], maxbuf=out[2], ref=out[3], err=out[4])
 
+    def agc_trace(self, max_blocks=None):
+        """(peaks, gains) of the last call: float32 [n_rx, n_blocks] — per-block peak of the pre-AGC audio and applied gain."""
+        cap = int(max_blocks if max_blocks is not None else self.max_in // int(self.P.IN_CHUNK_SIZE) + 2)
+        pk = np.zeros((self.n_rx, cap), np.float32)
+        gn = np.zeros((self.n_rx, cap), np.float32)
+        nb = ctypes.c_int64(0)
+        check(self.lib.pysdr_bank_agc_trace(self.h, pk.ctypes.data_as(ctypes.c_void_p), gn.ctypes.data_as(ctypes.c_void_p),
+                                            cap, ctypes.byref(nb), _stream_ptr()))
+        n = nb.value
+        return pk.reshape(-1)[:self.n_rx * n].reshape(self.n_rx, n), gn.reshape(-1)[:self.n_rx * n].reshape(self.n_rx, n)
+
     def reset(self):
         check(self.lib.pysdr_bank_reset(self.h))
 

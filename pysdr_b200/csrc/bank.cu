@@ -22,6 +22,22 @@ void pysdr_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 extern "C" const char *pysdr_last_error(void) { return g_err; }
+
+int pysdr_device(void) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+    return d;
+}
+int pysdr_sm_count(void) {
+    static int cached[64] = {0};
+    const int d = pysdr_device() & 63;
+    if (cached[d] <= 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || n <= 0) n = 148;
+        cached[d] = n;
+    }
+    return cached[d];
+}
 extern "C" int pysdr_version(void) { return 100; }
 
 extern "C" uint64_t pysdr_freq_to_phase_inc(double f, double fs) {
@@ -49,7 +65,7 @@ extern "C" int pysdr_quad_mixer(const void *d_x, void *d_y, int64_t n, uint64_t 
                                 void *stream) {
     if (n <= 0) return PYSDR_OK;
     i64 blocks = (n + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks > (i64)pysdr_sm_count() * 32) blocks = (i64)pysdr_sm_count() * 32;
     quad_mixer_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float2 *)d_x, (float2 *)d_y,
                                                                         n, acc0, inc);
     LAUNCH_CHECK();
@@ -88,7 +104,7 @@ extern "C" int pysdr_cs16_to_cf32(const void *d_in, void *d_out, int64_t n, doub
     if (n <= 0) return PYSDR_OK;
     if (!d_in || !d_out) { pysdr_set_error("cs16_to_cf32: null pointer"); return PYSDR_ERR_ARG; }
     i64 blocks = ((n >> 2) + 255) / 256 + 1;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (i64)pysdr_sm_count() * 16) blocks = (i64)pysdr_sm_count() * 16;
     cs16_to_cf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const short *)d_in, (float2 *)d_out, n, (float)scale);
     LAUNCH_CHECK();
     return PYSDR_OK;
@@ -479,6 +495,67 @@ __global__ void __launch_bounds__(AGC_THREADS) agc_scan_kernel(AgcScanArgs p) {
         ((unsigned long long *)&p.state[rx])[tid] = ((const unsigned long long *)&st)[tid];
 }
 
+// ---- O(1) AGC carry between time shards (include/pysdr_b200.h: pysdr_bank_agc_summary / _enter) -----------------------
+// One CTA per receiver: ordered reduction (composition is associative, not commutative) of the block functions of
+// blocks 7 .. n-1; every w_b there depends on the shard's own peaks only.
+#define SUM_THREADS 256
+__global__ void __launch_bounds__(SUM_THREADS) agc_summary_kernel(const AgcState *__restrict__ state, const float *__restrict__ peaks,
+                                                                  i64 peaks_stride, i64 skip, i64 n_blocks, double *__restrict__ out) {
+    const int rx = blockIdx.x, tid = threadIdx.x;
+    const float *own = peaks + (size_t)rx * peaks_stride + skip;
+    const i64 n = n_blocks - skip;
+    double *o = out + (size_t)rx * PYSDR_AGC_SUMMARY_LEN;
+    const double ref = state[rx].ref, beta = state[rx].beta, D = 1.0 - beta;
+    __shared__ AgcFn s_fn[SUM_THREADS];
+    // thread t owns the contiguous run [lo, hi) of blocks 7 .. n-1
+    const i64 m = n > 7 ? n - 7 : 0;
+    const i64 per = (m + SUM_THREADS - 1) / SUM_THREADS;
+    const i64 lo = 7 + (i64)tid * per, hi = (lo + per < n) ? lo + per : n;
+    AgcFn f; f.A = 1.0e300; f.C = 0.0; f.D = 1.0;
+    for (i64 b = lo; b < hi; ++b) {
+        float mb = own[b];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) mb = fmaxf(mb, own[b - j]);
+        const double w = fmin(ref / fmax((double)mb, 1.0e-9), 1.0e4);
+        AgcFn g; g.A = w; g.C = beta * w; g.D = D;
+        f = agc_compose(f, g);
+    }
+    s_fn[tid] = f;
+    __syncthreads();
+    for (int o2 = 1; o2 < SUM_THREADS; o2 <<= 1) {          // ordered tree: element t absorbs its RIGHT neighbour run
+        if ((tid & (2 * o2 - 1)) == 0) s_fn[tid] = agc_compose(s_fn[tid], s_fn[tid + o2]);
+        __syncthreads();
+    }
+    if (tid == 0) { o[0] = s_fn[0].A; o[1] = s_fn[0].C; o[2] = s_fn[0].D; o[18] = (double)n; }
+    if (tid < 7) o[3 + tid] = tid < n ? (double)own[tid] : 0.0;
+    if (tid < 8) { const i64 e = n - 8 + tid; o[10 + tid] = e >= 0 ? (double)own[e] : 0.0; }
+}
+
+__global__ void agc_enter_kernel(AgcState *__restrict__ state, const double *__restrict__ sums, int n_before, int n_rx) {
+    const int rx = threadIdx.x;
+    if (rx >= n_rx) return;
+    AgcState s = state[rx];
+    for (int i = 0; i < PYSDR_AGC_NB; ++i) s.ring[i] = 0.0;
+    s.k = 0; s.gain = 1.0; s.maxbuf = 0.0; s.err = 0.0;
+    for (int q = 0; q < n_before; ++q) {
+        const double *o = sums + ((size_t)q * n_rx + rx) * PYSDR_AGC_SUMMARY_LEN;
+        const i64 n = (i64)o[18];
+        const int head = n < 7 ? (int)n : 7;
+        for (int j = 0; j < head; ++j) agc_update(s, o[3 + j]);
+        if (n > 7) {
+            const double g_in = s.gain;
+            s.gain = fmin(o[0], fma(o[2], g_in, o[1]));
+            for (int t = 0; t < 8; ++t) s.ring[(int)((s.k + (n - 7) - 1 - t) & 7)] = o[17 - t];
+            s.k += n - 7;
+            double mb = 0.0;
+            for (int i = 0; i < PYSDR_AGC_NB; ++i) mb = fmax(mb, s.ring[i]);
+            s.maxbuf = mb;
+            s.err = fmin(s.ref / fmax(mb, 1.0e-9), 1.0e4) - s.gain;
+        }
+    }
+    state[rx] = s;
+}
+
 // K2e: am = a*gain ; am_dc = am - mean_block(am) for AM/USB.  grid (n_blocks, n_rx); IQ rows are skipped.
 struct ApplyKinds { int kind[PYSDR_MAX_RX]; };     // 0 skip (IQ), 1 real, 2 real + per-block DC removal
 __global__ void __launch_bounds__(32 * BLK_WARPS)
@@ -498,7 +575,6 @@ agc_apply_kernel(const float *__restrict__ a, i64 a_row, const float *__restrict
     i64 lo, hi;
     block_range_warp(blk, B0, in_chunk, up, down, m0, n_out, lo, hi);
     const float g = gains[(size_t)blockIdx.y * g_row + blk];
-    float sum = 0.f;
     if (!am_dc && ((((unsigned long long)(a + lo)) ^ ((unsigned long long)(am + lo))) & 15ull) == 0) {
         // audio only, source and destination equally aligned: scalar head, 16-byte body, scalar tail
         const i64 head = ((4 - (i64)(((unsigned long long)(a + lo) >> 2) & 3ull)) & 3);
@@ -519,6 +595,7 @@ agc_apply_kernel(const float *__restrict__ a, i64 a_row, const float *__restrict
         if (t < hi) am[t] = a[t] * g;
         return;
     }
+    double sum = 0.0;                                   // block mean in float64 (the subtraction below cancels the carrier)
     for (i64 i = lo + lane; i < hi; i += 32 * 8) {
         float v[8];
 #pragma unroll
@@ -526,13 +603,13 @@ agc_apply_kernel(const float *__restrict__ a, i64 a_row, const float *__restrict
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             if (i + 32 * u < hi) am[i + 32 * u] = v[u];
-            sum += v[u];
+            sum += (double)v[u];
         }
     }
     if (!am_dc) return;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = (hi > lo && dc_remove) ? sum / (float)(hi - lo) : 0.f;
+    const float mean = (hi > lo && dc_remove) ? (float)(sum / (double)(hi - lo)) : 0.f;
     for (i64 i = lo + lane; i < hi; i += 32) am_dc[i] = a[i] * g - mean;
 }
 
@@ -833,7 +910,25 @@ extern "C" int pysdr_bank_agc_get(pysdr_bank *b, int rx, double out5[5], void *s
     AgcState s;
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     CUDA_TRY(cudaMemcpy(&s, b->d_agc + rx, sizeof(s), cudaMemcpyDeviceToHost));
-    out5[0] = s.gain; out5[1] = s.gain; out5[2] = s.maxbuf; out5[3] = s.ref; out5[4] = s.err;
+    // rx.agc.agc (reference watchdog.py:298) = the gain the loop WANTS for the current peak buffer (ref / maxbuf, clamped),
+    // rx.agc.gain = the gain it applies after the attack / loop-filter law; err = agc - gain before the last update
+    const double want = fmin(s.ref / fmax(s.maxbuf, 1.0e-9), 1.0e4);
+    out5[0] = s.k > 0 ? want : s.gain; out5[1] = s.gain; out5[2] = s.maxbuf; out5[3] = s.ref; out5[4] = s.err;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_agc_trace(pysdr_bank *b, float *host_peaks, float *host_gains, int64_t capacity, int64_t *n_blocks,
+                                    void *stream) {
+    if (!b || !host_peaks || !host_gains || !n_blocks) { pysdr_set_error("agc_trace: bad arguments"); return PYSDR_ERR_ARG; }
+    const i64 nb = b->pend_blocks;
+    if (b->pending || nb <= 0 || !b->pend_peaks) { pysdr_set_error("agc_trace: no completed process call"); return PYSDR_ERR_STATE; }
+    if (nb > capacity) { pysdr_set_error("agc_trace: %lld blocks exceed capacity %lld", nb, (i64)capacity); return PYSDR_ERR_CAPACITY; }
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    CUDA_TRY(cudaMemcpy2D(host_peaks, sizeof(float) * (size_t)nb, b->pend_peaks, sizeof(float) * (size_t)nb,
+                          sizeof(float) * (size_t)nb, b->cfg.n_rx, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy2D(host_gains, sizeof(float) * (size_t)nb, b->d_gains, sizeof(float) * (size_t)b->max_blocks,
+                          sizeof(float) * (size_t)nb, b->cfg.n_rx, cudaMemcpyDeviceToHost));
+    *n_blocks = nb;
     return PYSDR_OK;
 }
 
@@ -899,7 +994,7 @@ extern "C" int pysdr_fm_disc(const void *d_y, int64_t n, void *d_prev2, void *d_
     if (n == 0) return PYSDR_OK;
     cudaStream_t st = (cudaStream_t)stream;
     i64 blocks = (n + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (i64)pysdr_sm_count() * 16) blocks = (i64)pysdr_sm_count() * 16;
     fm_disc_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float2 *)d_y, n, (const float2 *)d_prev2, (float2 *)d_out);
     LAUNCH_CHECK();
     fm_disc_tail_kernel<<<1, 1, 0, st>>>((const float2 *)d_y, n, (float2 *)d_prev2);
@@ -1077,7 +1172,7 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
     const pysdr_bank_config &c = b->cfg;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_in > c.max_in) { pysdr_set_error("process: n_in=%lld exceeds max_in=%lld", (i64)n_in, (i64)c.max_in); return PYSDR_ERR_CAPACITY; }
-    if (b->n0 % c.in_chunk != 0) {
+    if (!b->k1_only && b->n0 % c.in_chunk != 0) {        // a K1-only bank has no per-block stages: any position
         pysdr_set_error("process: stream position %lld is not on an IN_CHUNK_SIZE=%lld boundary", b->n0, (i64)c.in_chunk);
         return PYSDR_ERR_ALIGN;
     }
@@ -1178,7 +1273,7 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
         const int mode = b->mode[r];
         if (mode == PYSDR_MODE_RAW) {                 // WFM second stage: a = Re{resampler output}
             i64 blocks = (n_out + 255) / 256;
-            if (blocks > 148 * 8) blocks = 148 * 8;
+            if (blocks > (i64)pysdr_sm_count() * 8) blocks = (i64)pysdr_sm_count() * 8;
             real_part_kernel<<<(unsigned)blocks, 256, 0, st>>>(C + b->hc, aout, n_out);
             LAUNCH_CHECK();
             b->launches++;
@@ -1188,7 +1283,7 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
         } else if (mode == PYSDR_MODE_AM || mode == PYSDR_MODE_NFM || mode == PYSDR_MODE_AMSYNC) {
             const i64 nr = (L - 1) + n_out;
             i64 blocks = (nr + 255) / 256;
-            if (blocks > 148 * 8) blocks = 148 * 8;
+            if (blocks > (i64)pysdr_sm_count() * 8) blocks = (i64)pysdr_sm_count() * 8;
             detect_kernel<<<(unsigned)blocks, 256, 0, st>>>(C, R, nr, mode == PYSDR_MODE_NFM, mode == PYSDR_MODE_AMSYNC);
             LAUNCH_CHECK();
             b->launches++;
@@ -1205,7 +1300,7 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
         for (int r = 0; r < 3; ++r)
             if (b->mode[r] != PYSDR_MODE_IQ) { pysdr_set_error("stereo bank: all three rows must be in IQ mode"); return PYSDR_ERR_STATE; }
         i64 blocks = (n_out + 255) / 256;
-        if (blocks > 148 * 8) blocks = 148 * 8;
+        if (blocks > (i64)pysdr_sm_count() * 8) blocks = (i64)pysdr_sm_count() * 8;
         float *Ls = b->d_R, *Rs = b->d_R + b->r_stride;
         stereo_matrix_kernel<<<(unsigned)blocks, 256, 0, st>>>(b->d_a, b->d_a + b->a_stride, b->d_a + 2 * b->a_stride, n_out,
                                                                b->pilot_min, Ls, Rs);
@@ -1292,7 +1387,7 @@ extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks,
         float *amdc = d_am_dc ? d_am_dc + (size_t)r * 2 * out_stride : nullptr;
         if (b->mode[r] == PYSDR_MODE_IQ && !(b->stereo && r < 2)) {
             i64 n = 2 * n_out, blocks = (n + 255) / 256;
-            if (blocks > 148 * 8) blocks = 148 * 8;
+            if (blocks > (i64)pysdr_sm_count() * 8) blocks = (i64)pysdr_sm_count() * 8;
             copy_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(aout, am, n);
             LAUNCH_CHECK();
             b->launches++;
@@ -1321,6 +1416,25 @@ extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks,
         b->evs.push_back(e);
     }
     b->pending = false;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_agc_summary(pysdr_bank *b, int64_t skip_blocks, double *d_summary, void *stream) {
+    if (!b || !d_summary) { pysdr_set_error("agc_summary: bad arguments"); return PYSDR_ERR_ARG; }
+    if (!b->pending || !b->pend_peaks) { pysdr_set_error("agc_summary: call process_front first"); return PYSDR_ERR_STATE; }
+    if (skip_blocks < 0 || skip_blocks >= b->pend_blocks) { pysdr_set_error("agc_summary: bad skip_blocks"); return PYSDR_ERR_ARG; }
+    agc_summary_kernel<<<b->cfg.n_rx, SUM_THREADS, 0, (cudaStream_t)stream>>>(b->d_agc, b->pend_peaks, b->pend_blocks, skip_blocks,
+                                                                              b->pend_blocks, d_summary);
+    LAUNCH_CHECK();
+    b->launches++;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_agc_enter(pysdr_bank *b, const double *d_summaries, int n_before, void *stream) {
+    if (!b || n_before < 0 || (n_before > 0 && !d_summaries)) { pysdr_set_error("agc_enter: bad arguments"); return PYSDR_ERR_ARG; }
+    agc_enter_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(b->d_agc, d_summaries, n_before, b->cfg.n_rx);
+    LAUNCH_CHECK();
+    b->launches++;
     return PYSDR_OK;
 }
 

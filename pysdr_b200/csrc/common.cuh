@@ -14,6 +14,10 @@ typedef unsigned long long u64;
 typedef long long i64;
 
 void pysdr_set_error(const char *fmt, ...);
+// multiprocessor count of the CURRENT device (cudaDevAttrMultiProcessorCount, cached per device; 148 on B200)
+int pysdr_sm_count(void);
+// current device ordinal, or 0 when it cannot be read (used to key per-device one-time set-up)
+int pysdr_device(void);
 
 #define CUDA_TRY(expr)                                                                         \
     do {                                                                                       \

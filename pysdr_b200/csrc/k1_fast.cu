@@ -393,10 +393,11 @@ int k1_fast_supported(int up, int down, int lp, int n_rx) {
 template <int NRXP, int TPL>
 static int launch_one(const K1Args &a, const FastGeom &g, int grid, cudaStream_t st) {
     const size_t smem = 64 + sizeof(float2) * (size_t)K1F_STAGES * K1F_STAGE_ELEMS;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done = 0ull;          // one bit per device: the attribute is per (function, device)
+    const unsigned long long dev_bit = 1ull << (pysdr_device() & 63);
+    if (!(attr_done & dev_bit)) {
         CUDA_TRY(cudaFuncSetAttribute(k1_fast_kernel<NRXP, TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        attr_done |= dev_bit;
     }
     k1_fast_kernel<NRXP, TPL><<<grid, K1F_THREADS, smem, st>>>(a, g);
     LAUNCH_CHECK();
@@ -432,7 +433,7 @@ int k1_launch_fast(const K1Args &a, cudaStream_t st) {
     g.q_first = a.m0 / a.up;
     const i64 q_last = (a.m0 + a.n_out - 1) / a.up;
     g.n_tiles = (q_last - g.q_first) / g.S + 1;
-    int sms = 148;
+    const int sms = pysdr_sm_count();
     int grid = (int)(g.n_tiles < sms ? g.n_tiles : sms);
     for (int rx0 = 0; rx0 < a.n_rx; rx0 += nrxp) {
         g.rx0 = rx0;

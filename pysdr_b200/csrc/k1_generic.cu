@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) k1_generic_kernel(K1Args a) {
 int k1_launch_generic(const K1Args &a, cudaStream_t st) {
     if (a.n_out <= 0) return PYSDR_OK;
     i64 blocks = (a.n_out + 7) / 8;
-    const i64 cap = 148 * 16;
+    const i64 cap = (i64)pysdr_sm_count() * 16;
     if (blocks > cap) blocks = cap;
     k1_generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
     LAUNCH_CHECK();

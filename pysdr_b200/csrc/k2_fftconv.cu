@@ -27,12 +27,14 @@ taps_fft_kernel(const float2 *__restrict__ taps, int L, float2 *__restrict__ Hpo
     }
 }
 
-// Stage raw complex memory C[k0 .. k0+N+2) of one receiver into LINEAR shared memory with cp.async (16-byte copies, no
-// registers held, every copy of the CTA in flight at once); samples at or beyond `valid` are zero.
+// Stage raw complex memory C[k0 .. k0+N+4) of one receiver into LINEAR shared memory with cp.async (16-byte copies, no
+// registers held, every copy of the CTA in flight at once); samples at or beyond `valid` are zero.  k0 must be EVEN
+// (16-byte aligned source): a block whose first sample is odd — every other block when the AF filter length is even,
+// V = N-(L-1) odd — stages from k0-1 and the readers skip one element (N+4 covers N+2 samples plus the shift).
 template <int N, int T>
 __device__ __forceinline__ void k2_stage_raw(float2 *raw, const float2 *__restrict__ C, i64 k0, i64 valid, int tid) {
-    constexpr int CH = (N + 2) / 2;                                       // 16-byte chunks
-    if (k0 + N + 2 <= valid) {                                            // interior block: no bounds checks
+    constexpr int CH = (N + 4) / 2;                                       // 16-byte chunks
+    if (k0 + N + 4 <= valid) {                                            // interior block: no bounds checks
         const float2 *src = C + k0;
 #pragma unroll
         for (int i = 0; i < CH / T; ++i) __pipeline_memcpy_async(raw + 2 * (tid + i * T), src + 2 * (tid + i * T), 16);
@@ -86,8 +88,9 @@ af_fftconv_kernel(const FftConvArgs a) {
     int pair_exp = 0;                                                     // b rides the transform scaled by 2^pair_exp
 
     // ---- stage raw samples (async), detect from shared memory, lay out for the FFT ---------------------------------
-    k2_stage_raw<N, T>(s, C, k0, avail + 2, tid);
-    if (pair) k2_stage_raw<N, T>(s2, a.C + (size_t)rxb * a.c_stride, k0, avail + 2, tid);
+    const int sh = (int)(k0 & 1);                                         // cp.async sources must be 16-byte aligned
+    k2_stage_raw<N, T>(s, C, k0 - sh, avail + 2, tid);
+    if (pair) k2_stage_raw<N, T>(s2, a.C + (size_t)rxb * a.c_stride, k0 - sh, avail + 2, tid);
     __pipeline_commit();
     __pipeline_wait_prior(0);
     __syncthreads();
@@ -98,8 +101,8 @@ af_fftconv_kernel(const FftConvArgs a) {
         for (int i = 0; i < PER; ++i) {
             const int e = tid + i * T;
             const bool ok = k0 + e < avail;
-            u[i] = k2_detect(s, e, mode, ok);
-            if (pair) u[i].y = k2_detect(s2, e, modeb, ok).x;             // two real detector outputs: u = det_a + j det_b
+            u[i] = k2_detect(s + sh, e, mode, ok);
+            if (pair) u[i].y = k2_detect(s2 + sh, e, modeb, ok).x;             // two real detector outputs: u = det_a + j det_b
         }
         if (pair) {
             // The two signals share one transform, so its rounding error (~1e-7 of the LARGER one) lands on both.  Bring

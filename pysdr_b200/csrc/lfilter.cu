@@ -211,7 +211,7 @@ extern "C" int pysdr_abs_f32(const float *d_x, float *d_y, int64_t n, void *stre
     if (!d_x || !d_y || n < 0) { pysdr_set_error("abs_f32: bad arguments"); return PYSDR_ERR_ARG; }
     if (n == 0) return PYSDR_OK;
     i64 blocks = (n + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > (i64)pysdr_sm_count() * 8) blocks = (i64)pysdr_sm_count() * 8;
     abs_f32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_x, d_y, n);
     LAUNCH_CHECK();
     return PYSDR_OK;
@@ -220,7 +220,7 @@ extern "C" int pysdr_ratio_f32(const float *d_a, const float *d_b, float *d_r, f
     if (!d_a || !d_b || !d_r || n < 0) { pysdr_set_error("ratio_f32: bad arguments"); return PYSDR_ERR_ARG; }
     if (n == 0) return PYSDR_OK;
     i64 blocks = (n + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > (i64)pysdr_sm_count() * 8) blocks = (i64)pysdr_sm_count() * 8;
     ratio_f32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_a, d_b, d_r, floor_v, n);
     LAUNCH_CHECK();
     return PYSDR_OK;
@@ -260,7 +260,7 @@ extern "C" int pysdr_lfilter(const double *b, int nb, const double *a, int na, c
         case 16: rc = lfilter_run<16>(bn, an, d_x, d_y, n, n_ch, stride, d_zp, st, g_lf_mode); break;
         default: rc = lfilter_run<32>(bn, an, d_x, d_y, n, n_ch, stride, d_zp, st, g_lf_mode); break;
     }
-    if (rc) return rc;
+    if (rc) { cudaFreeAsync(d_zp, st); return rc; }
     CUDA_TRY(cudaMemcpy2DAsync(d_zi, sizeof(double) * order, d_zp, sizeof(double) * K, sizeof(double) * order, n_ch,
                                cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaFreeAsync(d_zp, st));

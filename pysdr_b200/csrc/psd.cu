@@ -301,7 +301,7 @@ extern "C" int pysdr_waterfall_rgba(const float *d_img, int64_t n, const float *
     if (!d_img || !d_bkgnd || !d_scratch || !d_lut256 || !d_rgba || n < 0) { pysdr_set_error("waterfall_rgba: bad arguments"); return PYSDR_ERR_ARG; }
     if (n == 0) return PYSDR_OK;
     const float *mx = d_scratch + (size_t)nfft * ncols + nfft;           // where pysdr_waterfall_push left max(wf)
-    wf_rgba_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(d_img, n, d_bkgnd, mx, pan_dr, (const uchar4 *)d_lut256, (uchar4 *)d_rgba);
+    wf_rgba_kernel<<<pysdr_sm_count(), 256, 0, (cudaStream_t)stream>>>(d_img, n, d_bkgnd, mx, pan_dr, (const uchar4 *)d_lut256, (uchar4 *)d_rgba);
     LAUNCH_CHECK();
     return PYSDR_OK;
 }
@@ -324,7 +324,7 @@ extern "C" int pysdr_waterfall_push(float *d_wf, int32_t nfft, int32_t ncols, in
     LAUNCH_CHECK();
     wf_max_kernel<<<1, 1024, 0, st>>>(d_wf, (i64)npsd * ncols, mx);
     LAUNCH_CHECK();
-    wf_image_kernel<<<148, 256, 0, st>>>(d_wf, (i64)npsd * ncols, d_bkgnd, mx, pan_dr, d_img);
+    wf_image_kernel<<<pysdr_sm_count(), 256, 0, st>>>(d_wf, (i64)npsd * ncols, d_bkgnd, mx, pan_dr, d_img);
     LAUNCH_CHECK();
     return PYSDR_OK;
 }

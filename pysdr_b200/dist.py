@@ -52,6 +52,63 @@ def exchange_agc_peaks(peaks, rank, world, group=None):
     return allp[:rank].permute(1, 0, 2).reshape(n_rx, rank * n_blocks).contiguous()
 
 
+AGC_SUMMARY_LEN = 19          # include/pysdr_b200.h PYSDR_AGC_SUMMARY_LEN
+
+
+def exchange_agc_summaries(own, out, world, group=None):
+    """own: float64 [n_rx, AGC_SUMMARY_LEN] summary of this rank's shard (pysdr_bank_agc_summary); out: preallocated
+    float64 [world, n_rx, AGC_SUMMARY_LEN].  THE collective of the time-sharded path: one all-gather of 152 bytes per receiver
+    per rank, independent of the shard length (the r01 protocol gathered every block peak: O(blocks))."""
+    if world == 1:
+        out[0].copy_(own)
+        return out
+    if own.is_cuda:
+        dist.all_gather_into_tensor(out, own, group=group)
+    else:
+        parts = [torch.empty_like(own) for _ in range(world)]
+        dist.all_gather(parts, own, group=group)
+        out.copy_(torch.stack(parts))
+    return out
+
+
+def agc_enter_reference(sums, n_before, ref=0.25, beta=0.1, nb=8, gmax=1.0e4, floor=1.0e-9):
+    """Host restatement of agc_enter_kernel (bank.cu) for one receiver: sums = float64 [n_before, AGC_SUMMARY_LEN].
+    Returns (gain, ring, k) entering the next shard.  Used by the gloo test and as documentation of the carry."""
+    ring, k, gain = [0.0] * nb, 0, 1.0
+    for q in range(n_before):
+        o = [float(v) for v in sums[q]]
+        n = int(o[18])
+        for j in range(min(n, 7)):
+            ring[k % nb] = o[3 + j]
+            k += 1
+            want = min(ref / max(max(ring), floor), gmax)
+            gain = want if want < gain else beta * want + (1.0 - beta) * gain
+        if n > 7:
+            gain = min(o[0], o[1] + o[2] * gain)
+            for t in range(8):
+                ring[(k + (n - 7) - 1 - t) % nb] = o[17 - t]
+            k += n - 7
+    return gain, ring, k
+
+
+def agc_summary_reference(peaks, ref=0.25, beta=0.1, gmax=1.0e4, floor=1.0e-9):
+    """Host restatement of agc_summary_kernel for one receiver's block peaks (float32 array, n >= 1)."""
+    import numpy as np
+    p = np.asarray(peaks, np.float32)
+    n = len(p)
+    A, C, D = 1.0e300, 0.0, 1.0
+    for b in range(7, n):
+        w = min(ref / max(float(np.max(p[b - 7:b + 1])), floor), gmax)
+        A, C, D = min(w, beta * w + (1.0 - beta) * A), (1.0 - beta) * C + beta * w, (1.0 - beta) * D
+    o = np.zeros(AGC_SUMMARY_LEN, np.float64)
+    o[0:3] = A, C, D
+    o[3:3 + min(n, 7)] = p[:7]
+    last = p[max(0, n - 8):]
+    o[18 - len(last):18] = last
+    o[18] = n
+    return o
+
+
 class ShardedCapture:
     """Per-rank driver of one time shard on the GPU bank (used by bench.py for N>1 and by receiver-level tools).
 
@@ -74,8 +131,12 @@ class ShardedCapture:
         self.skip_out = (-((-up * s0) // down)) - (-((-up * (s0 - w * C)) // down))     # outputs of the warm-up blocks
         if bank.max_in < self.plan['n'] + w * C:
             raise ValueError("bank.max_in must cover the shard plus its %d warm-up chunk(s)" % w)
+        # O(1) carry: needs at least 8 real blocks per shard (the summary's peak buffer); shorter shards gather the peaks
+        self.o1 = self.plan['n_blocks'] >= 8
+        self.summary = torch.zeros((bank.n_rx, AGC_SUMMARY_LEN), dtype=torch.float64, device=dev)
+        self.all_sum = torch.zeros((world, bank.n_rx, AGC_SUMMARY_LEN), dtype=torch.float64, device=dev)
 
-    def front(self, xbuf):
+    def front(self, xbuf, copy_own=True):
         """K1 + audio-rate filters + block peaks of this shard (and its warm-up).  xbuf: device tensor holding samples
         [first_sample, start+n) of the capture.  Leaves this rank's own block peaks in self.own."""
         p, b = self.plan, self.bank
@@ -84,7 +145,8 @@ class ShardedCapture:
         if w:
             b.seek(p['start'] - w * C)
             b.process_front(xbuf[p['halo']:], self.peaks_ext, halo_in_place=p['halo'] > 0)
-            self.own.copy_(self.peaks_ext[:, w:])
+            if copy_own:
+                self.own.copy_(self.peaks_ext[:, w:])
         else:
             b.seek(0)
             b.process_front(xbuf[p['lead']:], self.peaks_ext)
@@ -99,9 +161,21 @@ class ShardedCapture:
         return [a[k:] for a in am], [a[k:] for a in iq], [a[k:] for a in dc]
 
     def step(self, xbuf, want_dc=False):
-        own = self.front(xbuf)
-        prev = exchange_agc_peaks(own, self.rank, self.world)           # the one collective of the path
-        return self.back(prev, want_dc=want_dc)
+        import ctypes
+        from ._lib import check
+        from .bank import _stream_ptr
+        if not self.o1:
+            own = self.front(xbuf)
+            prev = exchange_agc_peaks(own, self.rank, self.world)
+            return self.back(prev, want_dc=want_dc)
+        b = self.bank
+        self.front(xbuf, copy_own=False)
+        w = self.plan['warm_chunks']
+        if self.world > 1:
+            check(b.lib.pysdr_bank_agc_summary(b.h, w, ctypes.c_void_p(self.summary.data_ptr()), _stream_ptr()))
+            exchange_agc_summaries(self.summary, self.all_sum, self.world)      # the one collective of the path
+        check(b.lib.pysdr_bank_agc_enter(b.h, ctypes.c_void_p(self.all_sum.data_ptr()), self.rank, _stream_ptr()))
+        return self.back(None, want_dc=want_dc)
 
 
 # ---- the other natural axis (SURVEY.md 8e axis 1): shard by receiver, no data-path collective -----------------------

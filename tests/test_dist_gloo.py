@@ -11,7 +11,8 @@ import torch.multiprocessing as mp
 
 from oracle import receiver_oracle as rxo
 from oracle import sig_proc_oracle as odsp
-from pysdr_b200.dist import exchange_agc_peaks, shard_plan
+from pysdr_b200.dist import (AGC_SUMMARY_LEN, agc_enter_reference, agc_summary_reference, exchange_agc_peaks,
+                             exchange_agc_summaries, shard_plan)
 
 
 def _free_port():
@@ -69,9 +70,19 @@ def _worker(rank, world, port, chunks_per_rank, q):
                 a.append(_pre_agc(rx, P, x[s:s + C]))
                 peaks[irx, c] = np.max(np.abs(a[-1]))
             pre.append(a)
+        out = []
+        if chunks_per_rank >= 8:
+            # O(1) carry: 19 doubles per receiver per rank cross the wire, whatever the shard length
+            own = torch.from_numpy(np.array([agc_summary_reference(peaks[irx]) for irx in range(2)]))
+            allsum = exchange_agc_summaries(own, torch.zeros((world, 2, AGC_SUMMARY_LEN), dtype=torch.float64), world).numpy()
+            for irx in range(2):
+                g = odsp.agc()
+                g.gain, g.ring, g.k = agc_enter_reference(allsum[:, irx], rank)
+                out.append(np.concatenate([pre[irx][c] * g.update(peaks[irx, c]) for c in range(chunks_per_rank)]))
+            q.put((rank, out))
+            return
         prev = exchange_agc_peaks(torch.from_numpy(peaks), rank, world)
         assert (prev is None) == (rank == 0)
-        out = []
         for irx in range(2):
             g = odsp.agc()
             if prev is not None:
@@ -84,8 +95,12 @@ def _worker(rank, world, port, chunks_per_rank, q):
         dist.destroy_process_group()
 
 
-def test_two_rank_time_shard_equals_single_stream():
-    world, cpr = 2, 3
+import pytest
+
+
+@pytest.mark.parametrize("cpr", [3, 8])
+def test_two_rank_time_shard_equals_single_stream(cpr):
+    world = 2
     port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -53,7 +53,7 @@ def test_cuda_matches_golden(name):
         np.testing.assert_array_equal([len(a) for a in am[r]], ref["nout%d" % r])       # indexing: bit-exact
         assert_parity(np.concatenate(iq[r]), ref["iq%d" % r], "%s iq%d" % (name, r))
         assert_parity(np.concatenate(am[r]), ref["am%d" % r], "%s am%d" % (name, r))
-        assert_parity(np.concatenate(dc[r]), ref["dc%d" % r], "%s dc%d" % (name, r), rel_tol=2e-4, snr_min=74)
+        assert_parity(np.concatenate(dc[r]), ref["dc%d" % r], "%s dc%d" % (name, r))
 
 
 @pytest.mark.gpu

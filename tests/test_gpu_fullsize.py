@@ -27,7 +27,8 @@ def cfg2():
     x = synth_iq(n, P.SRATE, offs, MODES, seed=31, device="cuda")
     bank = ReceiverBank(P, offs, max_in=n)
     am, iq, _ = bank.process(x, want_dc=False)
-    out = dict(P=P, Po=Po, x=x, n=n, offs=offs, n_out=bank.n_out, am=[a.clone() for a in am], iq=[q.clone() for q in iq])
+    out = dict(P=P, Po=Po, x=x, n=n, offs=offs, n_out=bank.n_out, am=[a.clone() for a in am], iq=[q.clone() for q in iq],
+               trace=bank.agc_trace())
     del bank
     return out
 
@@ -95,6 +96,40 @@ def test_cfg2_full_size_spot_parity_with_oracle(cfg2, blk):
         ref = np.concatenate(got)
         assert len(ref) == m_hi - m_lo
         assert_parity(cfg2['iq'][r][m_lo:m_hi].cpu().numpy(), ref, "iq rx%d blocks %d..%d" % (r, blk, blk + 3))
+
+
+def test_cfg2_full_size_agc_trajectory_and_audio(cfg2):
+    """The AUDIO of the full 60 s capture against the oracle (r01 only spot-checked the baseband):
+      (1) the oracle's AGC law run over all 2812 blocks on the device's own block peaks reproduces the device's gain
+          trajectory (the float64 ordered scan vs the serial recursion);
+      (2) for blocks 1, 1406 and 2805 an oracle receiver started two chunks earlier yields the pre-AGC audio: its block
+          peak equals the device's, and  pre-AGC audio x oracle-trajectory gain  equals the device's audio at the gate."""
+    P, Po = cfg2['P'], cfg2['Po']
+    C = P.IN_CHUNK_SIZE
+    pk, gn = cfg2['trace']
+    assert pk.shape == gn.shape == (4, N_CHUNKS)
+    traj = np.zeros_like(gn, dtype=np.float64)
+    for r in range(4):
+        g = odsp.agc()
+        traj[r] = [g.update(p) for p in pk[r]]
+        assert np.max(np.abs(traj[r] - gn[r]) / traj[r]) <= 2e-7, r        # float32 storage of a float64 recursion
+    for blk in (1, 1406, 2805):
+        warm = min(2, blk)
+        s0 = (blk - warm) * C
+        xs = cfg2['x'][s0:(blk + 1) * C].cpu().numpy()
+        m_lo = odsp.n_out_total(blk * C, P.UP, P.DOWN)
+        m_hi = odsp.n_out_total((blk + 1) * C, P.UP, P.DOWN)
+        for r in range(4):
+            orx = odsp.Receiver(Po, cfg2['offs'][r], r, str(r), fast=True)
+            orx.lo.advance(s0)
+            orx.dec.n0 = s0
+            orx.demod.m0 = odsp.n_out_total(s0, P.UP, P.DOWN)
+            for c in range(warm + 1):
+                iq = orx.dec.resamp_fast(xs[c * C:(c + 1) * C], orx.lo)
+                a = orx.demod.demod(iq, MODES[r], odsp._af_index(Po, r), odsp.per_rx(Po.BFO, r))
+            assert len(a) == m_hi - m_lo
+            assert abs(np.max(np.abs(a)) - pk[r, blk]) <= 1e-5 * pk[r, blk], (blk, r)
+            assert_parity(cfg2['am'][r][m_lo:m_hi].cpu().numpy(), np.asarray(a) * traj[r, blk], "audio rx%d block %d" % (r, blk))
 
 
 def test_cfg3_full_size_psd_parseval(cfg2):

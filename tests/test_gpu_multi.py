@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 
 FCS = [-500, 700, 1400, 3100]
 MODES = ['AM', 'NFM', 'USB', 'CW']
-CPRS = [4, 1]                             # chunks per rank; 1: rank 1's warm-up starts at the very first sample
+CPRS = [4, 1, 9]                          # chunks per rank; 1: rank 1's warm-up starts at the very first sample;
+                                          # 9: >= 8 blocks per shard -> the O(1) AGC summary exchange instead of the peak gather
 
 
 def _P():

@@ -1,0 +1,179 @@
+"""Round-2 robustness cases: even AF filter lengths through the multi-block FFT path (16-byte aligned staging), AGC
+read-outs, K1 on streams cut into pieces shorter than one tile (every tile an edge tile), two devices in one process."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import receiver_oracle as rxo
+from oracle import sig_proc_oracle as odsp
+from tests.util import assert_parity, make_both
+
+pytestmark = pytest.mark.gpu
+
+
+def _noise(n, seed, scale=0.1):
+    rng = np.random.default_rng(seed)
+    return ((rng.normal(size=n) + 1j * rng.normal(size=n)) * scale).astype(np.complex64)
+
+
+def _sig(n, P, offs, seed):
+    t = np.arange(n)
+    x = _noise(n, seed, 0.01).astype(np.complex128)
+    for k, f in enumerate(offs):
+        x += 0.05 * (1 + 0.4 * np.sin(2 * np.pi * (400.0 + 90 * k) * t / P.SRATE)) * np.exp(2j * np.pi * (f + 300.0) * t / P.SRATE)
+    return x.astype(np.complex64)
+
+
+def _bank(P, max_in, device=None):
+    from pysdr_b200.bank import ReceiverBank
+    from pysdr_b200.receiver import receiver_offsets
+    return ReceiverBank(P, receiver_offsets(P), max_in=max_in, device=device)
+
+
+@pytest.mark.parametrize("nfilt", [200, 100, 1000])
+def test_even_af_length_many_blocks_per_call(nfilt):
+    """-nfilt even => V = N-(L-1) odd: every other overlap-save block starts at an odd sample of the complex memory.  With
+    >= 8 chunks per call the FFT path runs several blocks per receiver (misaligned 16-byte cp.async)."""
+    from pysdr_b200.receiver import receiver_offsets
+    P, Po = make_both(2.048, [1000, 1020, 1045, 990], ['AM', 'NFM', 'USB', 'CW'], af_bw_khz=[5, 10, 2, 0.5], nfilt=nfilt)
+    C = P.IN_CHUNK_SIZE
+    k = 12
+    x = _sig(k * C, P, receiver_offsets(P), 77)
+    bank = _bank(P, k * C)
+    am, iq, _ = bank.process(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    rxo.create_receivers(Po)
+    for r in range(4):
+        ref = np.concatenate([Po.rx[r].demod_data(x[c * C:(c + 1) * C]) for c in range(k)])
+        assert_parity(am[r].cpu().numpy(), ref, "nfilt %d rx%d" % (nfilt, r))
+
+
+def test_agc_readouts_match_oracle():
+    """rx.agc.{agc,gain,maxbuf,ref,err} (reference watchdog.py:298-302): agc = the gain the loop asks for, gain = applied."""
+    from pysdr_b200 import sig_proc as dsp
+    P, Po = make_both(2.048, [1000], ['AM'], af_bw_khz=[5], nfilt=301)
+    C = P.IN_CHUNK_SIZE
+    x = _sig(12 * C, P, [P.FOFFSET], 5)
+    x[1 * C:2 * C] *= 4.0                                           # attack; 8 blocks later the burst leaves the peak buffer
+    rx = dsp.Receiver(P, P.FOFFSET, 0, '1')
+    orx = odsp.Receiver(Po, Po.FOFFSET, 0, '1')
+    for c in range(12):
+        rx.demod_data(x[c * C:(c + 1) * C])
+        orx.demod_data(x[c * C:(c + 1) * C])
+        for k in ('agc', 'gain', 'maxbuf', 'ref', 'err'):
+            got, ref = getattr(rx.agc, k), getattr(orx.agc, k)
+            assert abs(got - ref) <= 1e-4 * max(abs(ref), 1e-6), (c, k, got, ref)
+    assert rx.agc.agc != rx.agc.gain                                # decaying: the loop filter lags the wanted gain
+    rx.agc.reset()
+    assert rx.agc.gain == 1.0 and rx.agc.agc == 1.0 and rx.agc.maxbuf == 0.0
+
+
+@pytest.mark.parametrize("geom", [(8, 1001), (2.048, 1001), (10, 301)])
+def test_k1_every_tile_an_edge_tile(geom):
+    """Calls far shorter than one K1 tile (a tile is ~9000 samples): every tile of every call is filled by produce()'s
+    edge path — carried history before x[0], plain stores, zero fill past the end, odd alignments — never by the
+    interior bulk-copy path.  Baseband must equal the one-call result BIT FOR BIT (K1's arithmetic does not depend on how
+    the stream is cut) and match the oracle."""
+    srate, nfilt = geom
+    P, Po = make_both(srate, [1000, 1300, 870], ['IQ', 'IQ', 'IQ'], nfilt=nfilt)
+    C = P.IN_CHUNK_SIZE
+    x = _noise(C, 123)
+    whole = _bank(P, C)
+    _, iq_w, _ = whole.process(torch.from_numpy(x).cuda())
+    iq_w = [v.cpu().numpy().copy() for v in iq_w]
+    rng = np.random.default_rng(9)
+    for trial in range(3):
+        # one stream of C samples cut at random points: pieces of 1 .. 3000 samples, odd and even lengths
+        cuts = [0]
+        while cuts[-1] < C:
+            cuts.append(min(C, cuts[-1] + int(rng.integers(1, 3000))))
+        from pysdr_b200._lib import check
+        import ctypes
+        b = _bank(P, C)
+        xd = torch.from_numpy(x).cuda()
+        parts = [[] for _ in range(3)]
+        for a0, a1 in zip(cuts[:-1], cuts[1:]):
+            # K1 only, at arbitrary stream positions: the bank's k1_only mode moves the input memory along without the
+            # block-aligned audio stages
+            check(b.lib.pysdr_bank_set_k1_only(b.h, 1))
+            n_out = ctypes.c_int64(0)
+            check(b.lib.pysdr_bank_process_front(b.h, ctypes.c_void_p(xd[a0:a1].data_ptr()), a1 - a0, 0, None, b.max_out,
+                                                 ctypes.c_void_p(b._am.data_ptr()), ctypes.byref(n_out),
+                                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            b.n_out = n_out.value
+            for r in range(3):
+                parts[r].append(b.iq_row(r).cpu().numpy().copy())
+        for r in range(3):
+            got = np.concatenate(parts[r])
+            assert got.shape == iq_w[r].shape
+            assert np.array_equal(got, iq_w[r]), "trial %d rx%d: cut stream differs from the one-call result" % (trial, r)
+    rxo.create_receivers(Po)
+    for r in range(3):
+        Po.rx[r].demod_data(x)
+        assert_parity(iq_w[r], Po.rx[r].iq, "iq rx%d" % r)
+
+
+def test_two_devices_in_one_process():
+    """Per-device one-time kernel set-up (cudaFuncSetAttribute is per device): a bank on cuda:1 after one on cuda:0."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    P, Po = make_both(8, [1000, 1300], ['USB', 'AM'], af_bw_khz=[2, 5])
+    C = P.IN_CHUNK_SIZE
+    x = _noise(2 * C, 3)
+    outs = []
+    for d in (0, 1):
+        with torch.cuda.device(d):
+            b = _bank(P, 2 * C, device="cuda:%d" % d)
+            am, iq, _ = b.process(torch.from_numpy(x).to("cuda:%d" % d))
+            torch.cuda.synchronize()
+            outs.append([v.cpu().numpy().copy() for v in am])
+    for r in range(2):
+        assert np.array_equal(outs[0][r], outs[1][r])
+
+
+def test_o1_agc_carry_three_shards_emulated_on_one_gpu():
+    """The O(1) AGC hand-over of time-sharded runs (pysdr_bank_agc_summary / pysdr_bank_agc_enter: 19 doubles per
+    receiver per shard instead of every block peak), with three shards played one after the other on ONE device — the
+    NCCL version of the same thing needs 2 GPUs (test_gpu_multi.py).  Sharded audio == single-stream audio."""
+    import ctypes
+    from pysdr_b200._lib import check
+    from pysdr_b200.bank import _stream_ptr
+    from pysdr_b200.dist import AGC_SUMMARY_LEN, ShardedCapture, agc_enter_reference
+    from pysdr_b200.receiver import receiver_offsets
+    world, cpr = 3, 9
+    P, _ = make_both(2.048, [1000, 1020, 1045, 990], ['AM', 'NFM', 'USB', 'CW'], af_bw_khz=[5, 10, 2, 0.5], nfilt=301)
+    C = P.IN_CHUNK_SIZE
+    n = world * cpr * C
+    x = _sig(n, P, receiver_offsets(P), 321)
+    env = np.ones(n, np.float32)
+    env[4 * C:6 * C] = 5.0                                          # a burst in shard 0 whose decay crosses into shard 1
+    env[20 * C:] = 0.2                                              # a fade in shard 2
+    xd = torch.from_numpy(x * env).cuda()
+    single = _bank(P, n)
+    am, _, _ = single.process(xd)
+    ref = [a.cpu().numpy().copy() for a in am]
+    pk_ref, gn_ref = single.agc_trace()
+    shards, all_sum = [], torch.zeros((world, 4, AGC_SUMMARY_LEN), dtype=torch.float64, device="cuda")
+    for r in range(world):
+        b = _bank(P, (cpr + 1) * C)
+        sh = ShardedCapture(b, P, r, world, cpr)
+        assert sh.o1
+        pl = sh.plan
+        sh.front(xd[pl['first_sample']:pl['start'] + pl['n']], copy_own=False)
+        check(b.lib.pysdr_bank_agc_summary(b.h, pl['warm_chunks'], ctypes.c_void_p(all_sum[r].data_ptr()), _stream_ptr()))
+        shards.append(sh)
+    torch.cuda.synchronize()
+    sums = all_sum.cpu().numpy()
+    for r in range(world):
+        sh, b = shards[r], shards[r].bank
+        check(b.lib.pysdr_bank_agc_enter(b.h, ctypes.c_void_p(all_sum.data_ptr()), r, _stream_ptr()))
+        st = b.agc_get(0)
+        g_host, ring_host, _ = agc_enter_reference(sums[:, 0], r)   # the host restatement of the same carry
+        assert abs(st['gain'] - g_host) <= 1e-12 * g_host
+        if r:
+            assert abs(st['gain'] - gn_ref[0, r * cpr - 1]) <= 1e-6 * st['gain']          # = the single stream's gain there
+        got, _, _ = sh.back(None)
+        m0 = odsp.n_out_total(r * cpr * C, P.UP, P.DOWN)
+        for k in range(4):
+            g = got[k].cpu().numpy()
+            assert_parity(g, ref[k][m0:m0 + len(g)], "shard %d rx%d vs single stream" % (r, k), rel_tol=2e-5, snr_min=90)

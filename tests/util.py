@@ -1,3 +1,6 @@
+import json
+import os
+
 import numpy as np
 
 REL_TOL = 1e-4          # north_star: max-abs relative error <= 1e-4
@@ -19,6 +22,11 @@ def err_metrics(got, ref):
 
 def assert_parity(got, ref, what="", rel_tol=REL_TOL, snr_min=SNR_MIN_DB):
     rel, snr = err_metrics(got, ref)
+    log = os.environ.get("PYSDR_PARITY_LOG")                 # margins of every comparison, for profiles/parity_report_*.txt
+    if log:
+        with open(log, "a") as f:
+            f.write(json.dumps({"test": os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0], "what": what, "rel": rel,
+                                "snr_db": None if snr == np.inf else snr, "rel_tol": rel_tol, "snr_min": snr_min}) + "\n")
     assert rel <= rel_tol and snr >= snr_min, "%s: max-abs rel err %.3e (tol %.1e), diff SNR %.1f dB (min %.0f)" % (
         what, rel, rel_tol, snr, snr_min)
     return rel, snr
