@@ -148,6 +148,13 @@ int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks, int64_t n_
 #define PYSDR_AGC_SUMMARY_LEN 19
 int pysdr_bank_agc_summary(pysdr_bank *b, int64_t skip_blocks, double *d_summary, void *stream);
 int pysdr_bank_agc_enter(pysdr_bank *b, const double *d_summaries, int n_before, void *stream);
+/* process_back with the entry state taken from the summaries of the n_before earlier shards (agc_enter fused into the same
+ * launch as the scan and the gain application). */
+int pysdr_bank_process_back_carry(pysdr_bank *b, const double *d_summaries, int n_before, int64_t skip_blocks,
+                                  float *d_am, float *d_am_dc, int64_t out_stride, void *stream);
+/* Testing: on != 0 runs the tail as stand-alone kernels (block peaks, AGC scan, gain application, seek reset) instead of the
+ * fused back kernel (one co-resident grid, two grid barriers). */
+int pysdr_bank_force_unfused(pysdr_bank *b, int on);
 
 /* Move the stream position without processing (time shards): n0 must be a multiple of in_chunk.
  * LO/BFO accumulators follow; filter memories are cleared; n0 == 0 also resets the AGC (stream restart).

@@ -74,6 +74,8 @@ SIGNATURES = {
     "pysdr_bank_launch_count": (c_i64, [c_vp]),
     "pysdr_bank_agc_summary": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "pysdr_bank_agc_enter": (c_int, [c_vp, c_vp, c_int, c_vp]),
+    "pysdr_bank_process_back_carry": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "pysdr_bank_force_unfused": (c_int, [c_vp, c_int]),
     "pysdr_bank_agc_trace": (c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),
     "pysdr_lfilter_set_mode": (c_int, [c_int]),
     "pysdr_lfilter": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),

@@ -254,6 +254,18 @@ class ReceiverBank:
                                                self.max_out, _stream_ptr()))
         return self.views()
 
+    def process_back_carry(self, summaries, n_before, want_dc=True, skip_blocks=0):
+        """process_back whose AGC entry state comes from the summaries of the n_before earlier time shards (float64 device
+        tensor [>= n_before, n_rx, 19], see dist.py) — entry state, scan and gain application in one launch."""
+        check(self.lib.pysdr_bank_process_back_carry(self.h, ctypes.c_void_p(summaries.data_ptr()) if n_before else None,
+                                                     int(n_before), int(skip_blocks), ctypes.c_void_p(self._am.data_ptr()),
+                                                     ctypes.c_void_p(self._am_dc.data_ptr()) if want_dc else None,
+                                                     self.max_out, _stream_ptr()))
+        return self.views()
+
+    def force_unfused(self, on=True):
+        check(self.lib.pysdr_bank_force_unfused(self.h, 1 if on else 0))
+
     def n_blocks(self, n_in):
         return self.lib.pysdr_bank_n_blocks(self.h, int(n_in))
 

@@ -278,7 +278,7 @@ __device__ __forceinline__ void state_update_item(const StateArgs &sa, int item)
         const int e = threadIdx.x + k * T;
         if (e < sa.need) {
             const i64 idx = sa.n_in - sa.need + e;           // relative to x[0]
-            tmp[k] = idx >= 0 ? sa.x[idx] : sa.hist_src[sa.need + idx];
+            tmp[k] = idx >= 0 ? sa.x[idx] : (sa.hist_src ? sa.hist_src[sa.need + idx] : make_float2(0.f, 0.f));
         }
     }
     __syncthreads();
@@ -292,17 +292,10 @@ __device__ __forceinline__ void state_update_item(const StateArgs &sa, int item)
 // K2c: peak of |a| per block.  One warp per block (a block is ~OUT_CHUNK_SIZE = 1024 samples), 8 blocks per CTA,
 // 8 loads in flight per lane.  grid (ceil(n_blocks/8), n_rx).
 #define BLK_WARPS 8
-__global__ void __launch_bounds__(32 * BLK_WARPS)
-block_peak_kernel(const float *__restrict__ a, i64 a_row, float *__restrict__ peaks, i64 peaks_row, i64 n_blocks, i64 B0,
-                  i64 in_chunk, int up, int down, i64 m0, i64 n_out, int n_rows, const StateArgs sa) {
-    if ((int)blockIdx.y == n_rows) {         // extra grid row: the end-of-call state update rides this launch
-        if ((int)blockIdx.x <= sa.n_rx) state_update_item(sa, blockIdx.x);
-        return;
-    }
+// peak of |a| over AGC block `blk` of one receiver row (warp-collective); lane 0 stores it
+__device__ __forceinline__ void block_peak_warp(const float *__restrict__ a, float *__restrict__ peak_out, i64 blk, i64 B0,
+                                                i64 in_chunk, int up, int down, i64 m0, i64 n_out) {
     const int lane = threadIdx.x & 31;
-    const i64 blk = (i64)blockIdx.x * BLK_WARPS + (threadIdx.x >> 5);
-    if (blk >= n_blocks) return;
-    a += (size_t)blockIdx.y * a_row;
     i64 lo, hi;
     block_range_warp(blk, B0, in_chunk, up, down, m0, n_out, lo, hi);
     float mx = 0.f;
@@ -326,7 +319,20 @@ block_peak_kernel(const float *__restrict__ a, i64 a_row, float *__restrict__ pe
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) peaks[(size_t)blockIdx.y * peaks_row + blk] = mx;
+    if (lane == 0) *peak_out = mx;
+}
+
+__global__ void __launch_bounds__(32 * BLK_WARPS)
+block_peak_kernel(const float *__restrict__ a, i64 a_row, float *__restrict__ peaks, i64 peaks_row, i64 n_blocks, i64 B0,
+                  i64 in_chunk, int up, int down, i64 m0, i64 n_out, int n_rows, const StateArgs sa) {
+    if ((int)blockIdx.y == n_rows) {         // extra grid row: the end-of-call state update rides this launch
+        if ((int)blockIdx.x <= sa.n_rx) state_update_item(sa, blockIdx.x);
+        return;
+    }
+    const i64 blk = (i64)blockIdx.x * BLK_WARPS + (threadIdx.x >> 5);
+    if (blk >= n_blocks) return;
+    block_peak_warp(a + (size_t)blockIdx.y * a_row, peaks + (size_t)blockIdx.y * peaks_row + blk, blk, B0, in_chunk, up, down,
+                    m0, n_out);
 }
 
 // K2d: AGC recursion, one thread per receiver.  Law documented in oracle/sig_proc_oracle.py (class agc);
@@ -379,8 +385,8 @@ __device__ __forceinline__ AgcFn agc_compose(const AgcFn &f1, const AgcFn &f2) {
     return r;
 }
 
-__global__ void __launch_bounds__(AGC_THREADS) agc_scan_kernel(AgcScanArgs p) {
-    const int rx = blockIdx.x;
+// the scan of ONE receiver by one CTA of AGC_THREADS threads (every thread of the CTA must call it)
+__device__ void agc_scan_rx(const AgcScanArgs &p, const int rx) {
     const int tid = threadIdx.x;
     float *gains = p.gains + (size_t)rx * p.gains_stride;
     if (!p.enabled[rx]) {
@@ -419,7 +425,7 @@ __global__ void __launch_bounds__(AGC_THREADS) agc_scan_kernel(AgcScanArgs p) {
         __syncthreads();
         for (int i = tid; i < len; i += AGC_THREADS) {
             const i64 e = t0 + i;
-            s_pk[7 + i] = e < n_prev ? prev[e] : own[e - n_prev];
+            s_pk[7 + i] = e < n_prev ? __ldcg(prev + e) : __ldcg(own + (e - n_prev));     // L2: written by other SMs in the fused kernel
         }
         __syncthreads();
         for (int i = tid; i < len; i += AGC_THREADS) {
@@ -486,7 +492,7 @@ __global__ void __launch_bounds__(AGC_THREADS) agc_scan_kernel(AgcScanArgs p) {
     __syncthreads();
     if (tid < 8) {                                                         // ring <- the last 8 peaks seen (one lane each)
         const i64 e = n_total - 1 - tid;
-        if (e >= 0) st.ring[(int)((k0 + e) & 7)] = (double)(e < n_prev ? prev[e] : own[e - n_prev]);
+        if (e >= 0) st.ring[(int)((k0 + e) & 7)] = (double)(e < n_prev ? __ldcg(prev + e) : __ldcg(own + (e - n_prev)));
     }
     if (tid == 8) { st.gain = s_g; st.err = s_err; st.maxbuf = s_mb; st.k = k0 + n_total; }
     __syncthreads();
@@ -494,6 +500,8 @@ __global__ void __launch_bounds__(AGC_THREADS) agc_scan_kernel(AgcScanArgs p) {
     if (tid < (int)(sizeof(AgcState) / 8))
         ((unsigned long long *)&p.state[rx])[tid] = ((const unsigned long long *)&st)[tid];
 }
+
+__global__ void __launch_bounds__(AGC_THREADS) agc_scan_kernel(AgcScanArgs p) { agc_scan_rx(p, blockIdx.x); }
 
 // ---- O(1) AGC carry between time shards (include/pysdr_b200.h: pysdr_bank_agc_summary / _enter) -----------------------
 // One CTA per receiver: ordered reduction (composition is associative, not commutative) of the block functions of
@@ -531,15 +539,13 @@ __global__ void __launch_bounds__(SUM_THREADS) agc_summary_kernel(const AgcState
     if (tid < 8) { const i64 e = n - 8 + tid; o[10 + tid] = e >= 0 ? (double)own[e] : 0.0; }
 }
 
-__global__ void agc_enter_kernel(AgcState *__restrict__ state, const double *__restrict__ sums, int n_before, int n_rx) {
-    const int rx = threadIdx.x;
-    if (rx >= n_rx) return;
+__device__ void agc_enter_rx(AgcState *state, const double *sums, int n_before, int n_rx, int rx) {
     AgcState s = state[rx];
     for (int i = 0; i < PYSDR_AGC_NB; ++i) s.ring[i] = 0.0;
     s.k = 0; s.gain = 1.0; s.maxbuf = 0.0; s.err = 0.0;
     for (int q = 0; q < n_before; ++q) {
         const double *o = sums + ((size_t)q * n_rx + rx) * PYSDR_AGC_SUMMARY_LEN;
-        const i64 n = (i64)o[18];
+        const i64 n = (i64)__ldcg(o + 18);
         const int head = n < 7 ? (int)n : 7;
         for (int j = 0; j < head; ++j) agc_update(s, o[3 + j]);
         if (n > 7) {
@@ -555,26 +561,20 @@ __global__ void agc_enter_kernel(AgcState *__restrict__ state, const double *__r
     }
     state[rx] = s;
 }
+__global__ void agc_enter_kernel(AgcState *__restrict__ state, const double *__restrict__ sums, int n_before, int n_rx) {
+    if ((int)threadIdx.x < n_rx) agc_enter_rx(state, sums, n_before, n_rx, threadIdx.x);
+}
 
 // K2e: am = a*gain ; am_dc = am - mean_block(am) for AM/USB.  grid (n_blocks, n_rx); IQ rows are skipped.
-struct ApplyKinds { int kind[PYSDR_MAX_RX]; };     // 0 skip (IQ), 1 real, 2 real + per-block DC removal
-__global__ void __launch_bounds__(32 * BLK_WARPS)
-agc_apply_kernel(const float *__restrict__ a, i64 a_row, const float *__restrict__ gains, i64 g_row, float *__restrict__ am,
-                 float *__restrict__ am_dc, i64 am_row, ApplyKinds kinds, i64 n_blocks, i64 B0, i64 in_chunk, int up, int down,
-                 i64 m0, i64 n_out) {
-    // one warp per block, 8 blocks per CTA: grid (ceil(n_blocks/8), n_rx)
-    const int kind = kinds.kind[blockIdx.y];
-    if (kind == 0) return;
+struct ApplyKinds { int kind[PYSDR_MAX_RX]; };     // 0 skip, 1 real, 2 real + per-block DC removal, 3 complex copy (IQ / RTTY rows)
+// gain (and optional block-mean removal) on AGC block `blk` of one receiver row, warp-collective; pointers are row bases
+__device__ __forceinline__ void agc_apply_warp(const float *__restrict__ a, const float g, float *__restrict__ am,
+                                               float *__restrict__ am_dc, const int kind, i64 blk, i64 B0, i64 in_chunk, int up,
+                                               int down, i64 m0, i64 n_out) {
     const int lane = threadIdx.x & 31;
-    const i64 blk = (i64)blockIdx.x * BLK_WARPS + (threadIdx.x >> 5);
-    if (blk >= n_blocks) return;
     const int dc_remove = kind == 2;
-    a += (size_t)blockIdx.y * a_row;
-    am += (size_t)blockIdx.y * am_row;
-    if (am_dc) am_dc += (size_t)blockIdx.y * am_row;
     i64 lo, hi;
     block_range_warp(blk, B0, in_chunk, up, down, m0, n_out, lo, hi);
-    const float g = gains[(size_t)blockIdx.y * g_row + blk];
     if (!am_dc && ((((unsigned long long)(a + lo)) ^ ((unsigned long long)(am + lo))) & 15ull) == 0) {
         // audio only, source and destination equally aligned: scalar head, 16-byte body, scalar tail
         const i64 head = ((4 - (i64)(((unsigned long long)(a + lo) >> 2) & 3ull)) & 3);
@@ -613,6 +613,102 @@ agc_apply_kernel(const float *__restrict__ a, i64 a_row, const float *__restrict
     for (i64 i = lo + lane; i < hi; i += 32) am_dc[i] = a[i] * g - mean;
 }
 
+__global__ void __launch_bounds__(32 * BLK_WARPS)
+agc_apply_kernel(const float *__restrict__ a, i64 a_row, const float *__restrict__ gains, i64 g_row, float *__restrict__ am,
+                 float *__restrict__ am_dc, i64 am_row, ApplyKinds kinds, i64 n_blocks, i64 B0, i64 in_chunk, int up, int down,
+                 i64 m0, i64 n_out) {
+    // one warp per block, 8 blocks per CTA: grid (ceil(n_blocks/8), n_rx)
+    const int kind = kinds.kind[blockIdx.y];
+    if (kind != 1 && kind != 2) return;
+    const i64 blk = (i64)blockIdx.x * BLK_WARPS + (threadIdx.x >> 5);
+    if (blk >= n_blocks) return;
+    agc_apply_warp(a + (size_t)blockIdx.y * a_row, gains[(size_t)blockIdx.y * g_row + blk], am + (size_t)blockIdx.y * am_row,
+                   am_dc ? am_dc + (size_t)blockIdx.y * am_row : nullptr, kind, blk, B0, in_chunk, up, down, m0, n_out);
+}
+
+// ---- fused "back": block peaks -> AGC scan -> gain / DC removal in ONE launch -------------------------------------------
+// The three stages are separated by grid-wide dependencies (every block peak of a receiver before its scan, every gain
+// before it is applied), which used to cost two extra launches and their drain/fill gaps for ~90 MB of traffic.  Here a
+// co-resident grid (sized from the occupancy calculator, so that every CTA is running) walks the stages with two
+// grid barriers on a monotonically increasing device counter.  Stage bodies are the same device functions the
+// stand-alone kernels use (kept for the time-sharded split form and for stereo WFM2).
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned long long *ctr, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1ull);
+        while (ld_acquire_u64(ctr) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+struct BackArgs {
+    int do_peaks, do_enter, n_before, n_rx;
+    const float *a; i64 a_row;                       // pre-AGC audio rows (floats)
+    float *peaks; i64 peaks_row;
+    i64 n_blocks, B0, in_chunk, m0, n_out;
+    int up, down;
+    StateArgs sa;
+    AgcScanArgs scan;
+    const double *sums;
+    const float *gains; i64 g_row;
+    float *am, *am_dc; i64 am_row;
+    ApplyKinds kinds;
+    unsigned long long *bar; unsigned long long bar_base;
+};
+
+#define BACK_THREADS AGC_THREADS
+__global__ void __launch_bounds__(BACK_THREADS) agc_back_fused_kernel(const BackArgs p) {
+    const int warp = threadIdx.x >> 5, wpc = BACK_THREADS / 32;
+    const i64 gw = (i64)blockIdx.x * wpc + warp, gstride = (i64)gridDim.x * wpc;
+    const i64 total = (i64)p.n_rx * p.n_blocks;
+    if (p.do_peaks) {
+        // the end-of-call state update rides on the LAST CTAs (the first n_rx run the scans)
+        const int item = (int)gridDim.x - 1 - (int)blockIdx.x;
+        if (p.sa.enabled && item <= p.sa.n_rx) state_update_item(p.sa, item);
+        for (i64 t = gw; t < total; t += gstride) {
+            const int rx = (int)(t / p.n_blocks);
+            const i64 blk = t - (i64)rx * p.n_blocks;
+            block_peak_warp(p.a + (size_t)rx * p.a_row, p.peaks + (size_t)rx * p.peaks_row + blk, blk, p.B0, p.in_chunk, p.up,
+                            p.down, p.m0, p.n_out);
+        }
+        grid_barrier(p.bar, p.bar_base + gridDim.x);
+    }
+    if ((int)blockIdx.x < p.n_rx) {
+        if (p.do_enter) {
+            if (threadIdx.x == 0) agc_enter_rx(p.scan.state, p.sums, p.n_before, p.n_rx, blockIdx.x);
+            __syncthreads();
+        }
+        agc_scan_rx(p.scan, blockIdx.x);
+    }
+    grid_barrier(p.bar, p.bar_base + (p.do_peaks ? 2ull : 1ull) * gridDim.x);
+    for (i64 t = gw; t < total; t += gstride) {
+        const int rx = (int)(t / p.n_blocks);
+        const int kind = p.kinds.kind[rx];
+        if (kind != 1 && kind != 2) continue;
+        const i64 blk = t - (i64)rx * p.n_blocks;
+        agc_apply_warp(p.a + (size_t)rx * p.a_row, __ldcg(p.gains + (size_t)rx * p.g_row + blk), p.am + (size_t)rx * p.am_row,
+                       p.am_dc ? p.am_dc + (size_t)rx * p.am_row : nullptr, kind, blk, p.B0, p.in_chunk, p.up, p.down, p.m0,
+                       p.n_out);
+    }
+    for (int rx = 0; rx < p.n_rx; ++rx) {            // complex rows (IQ / RTTY): plain copy of 2*n_out floats
+        if (p.kinds.kind[rx] != 3) continue;
+        const float *src = p.a + (size_t)rx * p.a_row;
+        float *d0 = p.am + (size_t)rx * p.am_row, *d1 = p.am_dc ? p.am_dc + (size_t)rx * p.am_row : nullptr;
+        for (i64 i = (i64)blockIdx.x * BACK_THREADS + threadIdx.x; i < 2 * p.n_out; i += (i64)gridDim.x * BACK_THREADS) {
+            const float v = src[i];
+            d0[i] = v;
+            if (d1) d1[i] = v;
+        }
+    }
+}
+
 __global__ void copy_f32_kernel(const float *__restrict__ s, float *__restrict__ d, i64 n) {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 stride = (i64)gridDim.x * blockDim.x;
@@ -628,7 +724,7 @@ __global__ void hist_update_kernel(float2 *hist, const float2 *__restrict__ hist
         const int e = threadIdx.x + k * 1024;
         if (e < need) {
             const i64 idx = n_in - need + e;                 // relative to x[0]
-            tmp[k] = idx >= 0 ? x[idx] : hist_src[need + idx];
+            tmp[k] = idx >= 0 ? x[idx] : (hist_src ? hist_src[need + idx] : make_float2(0.f, 0.f));
         }
     }
     __syncthreads();
@@ -693,11 +789,24 @@ struct pysdr_bank {
     const float *pend_peaks;
     bool pending;
     bool force_generic;
+    // fused back (agc_back_fused_kernel): block peaks deferred from front into the back launch; grid barrier counter
+    bool force_unfused;                      // testing: the stand-alone tail kernels
+    bool defer_peaks, peaks_deferred;
+    StateArgs pend_sa;
+    unsigned long long *d_bar;
+    unsigned long long bar_count;
+    int back_grid;
+    // seek() folded into the next process_front / process_back (no launch of its own)
+    bool lazy_seek, lazy_reset_agc;
     i64 launches;
     // optional on-stream stage timing (bench.py roofline): events e0 |K1| e1 |rest of front| e2 ... e3 |back| e4
     bool timing;
     std::vector<cudaEvent_t> evs;
 };
+
+static int flush_seek(pysdr_bank *b, cudaStream_t st);
+static int launch_block_peaks(pysdr_bank *b, float *d_peaks, const StateArgs &sa, i64 n_blocks, i64 B0, i64 m0, i64 n_out,
+                              cudaStream_t st);
 
 static int bank_alloc(pysdr_bank *b) {
     const pysdr_bank_config &c = b->cfg;
@@ -714,6 +823,8 @@ static int bank_alloc(pysdr_bank *b) {
     CUDA_TRY(cudaMalloc(&b->d_gains, sizeof(float) * (size_t)c.n_rx * b->max_blocks));
     CUDA_TRY(cudaMalloc(&b->d_agc, sizeof(AgcState) * PYSDR_MAX_RX));
     CUDA_TRY(cudaMalloc(&b->d_pll, sizeof(double2) * PYSDR_MAX_RX));
+    CUDA_TRY(cudaMalloc(&b->d_bar, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(b->d_bar, 0, sizeof(unsigned long long)));
     return PYSDR_OK;
 }
 
@@ -728,6 +839,7 @@ extern "C" int pysdr_bank_reset(pysdr_bank *b) {
     if (!b) { pysdr_set_error("null bank"); return PYSDR_ERR_ARG; }
     b->n0 = 0;
     b->pending = false;
+    b->lazy_seek = false; b->lazy_reset_agc = false; b->peaks_deferred = false;
     CUDA_TRY(cudaMemset(b->d_hist, 0, sizeof(float2) * (size_t)(b->need + 8)));
     CUDA_TRY(cudaMemset(b->d_C, 0, sizeof(float2) * (size_t)b->cfg.n_rx * b->c_stride));
     CUDA_TRY(cudaMemset(b->d_pll, 0, sizeof(double2) * PYSDR_MAX_RX));
@@ -778,6 +890,9 @@ extern "C" int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out)
     b->timing = false;
     b->launches = 0;
     b->pending = false;
+    b->force_unfused = false; b->defer_peaks = false; b->peaks_deferred = false;
+    b->bar_count = 0; b->back_grid = 0;
+    b->lazy_seek = false; b->lazy_reset_agc = false;
     for (int r = 0; r < PYSDR_MAX_RX; ++r) {
         b->inc[r] = 0; b->acc0[r] = 0; b->mode[r] = PYSDR_MODE_IQ; b->af_cplx[r] = 0; b->bfo_inc[r] = 0;
         b->demod_set[r] = false;
@@ -803,7 +918,7 @@ extern "C" int pysdr_bank_destroy(pysdr_bank *b) {
     cudaFree(b->d_H);
     if (!b->c_external) cudaFree(b->d_C);
     cudaFree(b->d_hist); cudaFree(b->d_g); cudaFree(b->d_af); cudaFree(b->d_R);
-    cudaFree(b->d_a); cudaFree(b->d_peaks); cudaFree(b->d_gains); cudaFree(b->d_agc); cudaFree(b->d_pll);
+    cudaFree(b->d_a); cudaFree(b->d_peaks); cudaFree(b->d_gains); cudaFree(b->d_agc); cudaFree(b->d_pll); cudaFree(b->d_bar);
     delete b;
     return PYSDR_OK;
 }
@@ -856,6 +971,8 @@ extern "C" int pysdr_bank_set_demod(pysdr_bank *b, int rx, int mode, const float
         else t[j] = make_float2(taps[j], 0.f);
     }
     CUDA_TRY(cudaMemcpy(b->d_af + (size_t)rx * b->cfg.af_len, t.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    if (mode == PYSDR_MODE_AMSYNC && b->mode[rx] != PYSDR_MODE_AMSYNC)
+        CUDA_TRY(cudaMemset(b->d_pll + rx, 0, sizeof(double2)));               // the loop starts from rest (receiver.py:649)
     b->mode[rx] = mode;
     b->af_cplx[rx] = is_complex;
     b->bfo_inc[rx] = bfo_inc;
@@ -874,6 +991,7 @@ extern "C" int pysdr_bank_set_stereo(pysdr_bank *b, int on, double pilot_min) {
 
 extern "C" int pysdr_bank_pll_reset(pysdr_bank *b, int rx) {
     CHECK_RX(b, rx);
+    { int rc = flush_seek(b, 0); if (rc) return rc; }
     CUDA_TRY(cudaMemset(b->d_pll + rx, 0, sizeof(double2)));
     return PYSDR_OK;
 }
@@ -881,6 +999,7 @@ extern "C" int pysdr_bank_pll_reset(pysdr_bank *b, int rx) {
 extern "C" int pysdr_bank_pll_get(pysdr_bank *b, int rx, double *out2, void *stream) {
     CHECK_RX(b, rx);
     if (!out2) { pysdr_set_error("pll_get: null output"); return PYSDR_ERR_ARG; }
+    { int rc = flush_seek(b, (cudaStream_t)stream); if (rc) return rc; }
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     CUDA_TRY(cudaMemcpy(out2, b->d_pll + rx, sizeof(double2), cudaMemcpyDeviceToHost));
     return PYSDR_OK;
@@ -888,6 +1007,7 @@ extern "C" int pysdr_bank_pll_get(pysdr_bank *b, int rx, double *out2, void *str
 
 extern "C" int pysdr_bank_agc_reset(pysdr_bank *b, int rx) {
     CHECK_RX(b, rx);
+    { int rc = flush_seek(b, 0); if (rc) return rc; }
     AgcState s;
     CUDA_TRY(cudaMemcpy(&s, b->d_agc + rx, sizeof(s), cudaMemcpyDeviceToHost));
     agc_host_reset(s, s.ref, s.beta);
@@ -897,6 +1017,7 @@ extern "C" int pysdr_bank_agc_reset(pysdr_bank *b, int rx) {
 
 extern "C" int pysdr_bank_agc_config(pysdr_bank *b, int rx, double ref, double beta) {
     CHECK_RX(b, rx);
+    { int rc = flush_seek(b, 0); if (rc) return rc; }
     AgcState s;
     CUDA_TRY(cudaMemcpy(&s, b->d_agc + rx, sizeof(s), cudaMemcpyDeviceToHost));
     s.ref = ref;
@@ -907,6 +1028,7 @@ extern "C" int pysdr_bank_agc_config(pysdr_bank *b, int rx, double ref, double b
 
 extern "C" int pysdr_bank_agc_get(pysdr_bank *b, int rx, double out5[5], void *stream) {
     CHECK_RX(b, rx);
+    { int rc = flush_seek(b, (cudaStream_t)stream); if (rc) return rc; }
     AgcState s;
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     CUDA_TRY(cudaMemcpy(&s, b->d_agc + rx, sizeof(s), cudaMemcpyDeviceToHost));
@@ -1189,9 +1311,19 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
     const i64 B0 = b->n0 / c.in_chunk;
     const i64 n_blocks = (n_in + c.in_chunk - 1) / c.in_chunk;
 
+    // a pending seek() rides this call when K1 can absorb it (tap-stationary variant, audio stages present, no carrier PLL
+    // state to clear): K1 reads a zero history and clears the carried complex memory; the AGC restart rides the back kernel
+    bool any_sync = false;
+    for (int r = 0; r < c.n_rx; ++r) any_sync = any_sync || b->mode[r] == PYSDR_MODE_AMSYNC;
+    const bool k1_is_fast = !b->force_generic && k1_fast_supported(c.up, c.down, b->lp, c.n_rx);
+    const bool fold_seek = b->lazy_seek && k1_is_fast && !b->k1_external && !b->k1_only && !any_sync && n_out > 0 && !b->force_unfused;
+    if (b->lazy_seek && !fold_seek) { int rc0 = flush_seek(b, st); if (rc0) return rc0; }
+    if (fold_seek) b->lazy_seek = false;
+
     K1Args a;
     a.x = (const float2 *)d_iq;
-    a.hist = halo_in_place ? a.x - b->need : b->d_hist;
+    a.hist = halo_in_place ? a.x - b->need : (fold_seek ? nullptr : b->d_hist);
+    a.zero_c_hist = fold_seek ? 1 : 0;
     a.need = b->need;
     a.n0 = b->n0; a.n_in = n_in; a.m0 = m0; a.n_out = n_out;
     a.up = c.up; a.down = c.down; a.lp = b->lp; a.lp_pad = b->lp_pad; a.n_rx = c.n_rx;
@@ -1312,18 +1444,20 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
         b->launches += 3;
     }
     {
-        // block peaks (IQ-mode rows produce unused values) + one extra grid row that carries the end-of-call state update:
-        // complex memory C[0..hc) <- C[n_out .. n_out+hc) and the raw input memory, for the next call
+        // block peaks (IQ-mode rows produce unused values) + the end-of-call state update: complex memory
+        // C[0..hc) <- C[n_out .. n_out+hc) and the raw input memory, for the next call.  When back follows at once
+        // (pysdr_bank_process) both ride the fused back kernel instead of a launch of their own.
         StateArgs sa;
         sa.C = b->d_C; sa.c_stride = b->c_stride; sa.n_out = n_out; sa.hc = b->hc; sa.n_rx = c.n_rx;
         sa.hist = b->d_hist; sa.hist_src = a.hist; sa.x = a.x; sa.need = b->need; sa.n_in = n_in; sa.enabled = 1;
-        unsigned gx = (unsigned)((n_blocks + BLK_WARPS - 1) / BLK_WARPS);
-        if (gx < (unsigned)c.n_rx + 1) gx = (unsigned)c.n_rx + 1;
-        dim3 grid(gx, (unsigned)c.n_rx + 1);
-        block_peak_kernel<<<grid, 32 * BLK_WARPS, 0, st>>>((const float *)b->d_a, 2 * b->a_stride, d_peaks, n_blocks, n_blocks, B0,
-                                                            c.in_chunk, c.up, c.down, m0, n_out, c.n_rx, sa);
-        LAUNCH_CHECK();
-        b->launches++;
+        if (b->defer_peaks && !b->stereo && !b->force_unfused) {
+            b->pend_sa = sa;
+            b->peaks_deferred = true;
+        } else {
+            b->peaks_deferred = false;
+            rc = launch_block_peaks(b, d_peaks, sa, n_blocks, B0, m0, n_out, st);
+            if (rc) return rc;
+        }
     }
     if (b->stereo) {
         peak_link_kernel<<<(unsigned)((n_blocks + 255) / 256), 256, 0, st>>>(d_peaks, d_peaks + n_blocks, n_blocks);
@@ -1340,15 +1474,35 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
     return PYSDR_OK;
 }
 
-extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, int64_t skip_blocks,
-                                       float *d_am, float *d_am_dc, int64_t out_stride, void *stream) {
+static int launch_block_peaks(pysdr_bank *b, float *d_peaks, const StateArgs &sa, i64 n_blocks, i64 B0, i64 m0, i64 n_out,
+                              cudaStream_t st) {
+    const pysdr_bank_config &c = b->cfg;
+    unsigned gx = (unsigned)((n_blocks + BLK_WARPS - 1) / BLK_WARPS);
+    if (gx < (unsigned)c.n_rx + 1) gx = (unsigned)c.n_rx + 1;
+    dim3 grid(gx, (unsigned)c.n_rx + 1);
+    block_peak_kernel<<<grid, 32 * BLK_WARPS, 0, st>>>((const float *)b->d_a, 2 * b->a_stride, d_peaks, n_blocks, n_blocks, B0,
+                                                        c.in_chunk, c.up, c.down, m0, n_out, c.n_rx, sa);
+    LAUNCH_CHECK();
+    b->launches++;
+    return PYSDR_OK;
+}
+
+// back = AGC entry state (optional) -> [deferred block peaks] -> scan -> gain / DC removal.  One fused launch unless the
+// bank is the stereo WFM2 resampler (its L/R peaks are linked between the stages) or the stand-alone kernels are forced.
+static int back_impl(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, int64_t skip_blocks, const double *d_sums,
+                     int n_before, bool enter, float *d_am, float *d_am_dc, int64_t out_stride, cudaStream_t st) {
     if (!b || !b->pending) { pysdr_set_error("process_back without process_front"); return PYSDR_ERR_STATE; }
     if (!d_am) { pysdr_set_error("process_back: d_am is null"); return PYSDR_ERR_ARG; }
     const pysdr_bank_config &c = b->cfg;
-    cudaStream_t st = (cudaStream_t)stream;
     const i64 n_out = b->pend_n_out, n_blocks = b->pend_blocks;
     if (n_out > out_stride) { pysdr_set_error("process_back: out_stride too small"); return PYSDR_ERR_CAPACITY; }
+    if (enter) b->lazy_reset_agc = false;          // an explicit entry state replaces the restart a seek(0) asked for
     if (n_out == 0) {                        // nothing was emitted: the AGC does not advance (like the reference's empty am)
+        if (enter) {
+            agc_enter_kernel<<<1, 32, 0, st>>>(b->d_agc, d_sums, n_before, c.n_rx);
+            LAUNCH_CHECK();
+            b->launches++;
+        }
         if (b->timing) {
             for (int k = 0; k < 2; ++k) {
                 cudaEvent_t e;
@@ -1358,34 +1512,89 @@ extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks,
             }
         }
         b->pending = false;
+        b->peaks_deferred = false;
         return PYSDR_OK;
+    }
+    if (skip_blocks < 0 || skip_blocks >= n_blocks) { pysdr_set_error("process_back: bad skip_blocks"); return PYSDR_ERR_ARG; }
+    if (!enter && b->lazy_reset_agc) {       // seek(0) folded into this call: the AGCs restart (the peak replay restarts them itself)
+        enter = n_prev <= 0;
+        d_sums = nullptr;
+        n_before = 0;
+        b->lazy_reset_agc = false;
     }
     AgcScanArgs s;
     s.state = b->d_agc;
     s.peaks = b->pend_peaks; s.peaks_stride = n_blocks;
     s.prev_peaks = (n_prev > 0) ? d_prev_peaks : nullptr; s.n_prev = n_prev;
     s.gains = b->d_gains; s.gains_stride = b->max_blocks;
-    if (skip_blocks < 0 || skip_blocks >= n_blocks) { pysdr_set_error("process_back: bad skip_blocks"); return PYSDR_ERR_ARG; }
     s.n_blocks = n_blocks; s.n_rx = c.n_rx; s.skip = skip_blocks;
     for (int r = 0; r < PYSDR_MAX_RX; ++r) s.enabled[r] = (r < c.n_rx && (b->mode[r] != PYSDR_MODE_IQ || (b->stereo && r < 2))) ? 1 : 0;
+    ApplyKinds kinds;
+    bool any_real = false;
+    for (int r = 0; r < PYSDR_MAX_RX; ++r) {
+        kinds.kind[r] = 0;
+        if (r >= c.n_rx) continue;
+        if (b->mode[r] == PYSDR_MODE_IQ && !(b->stereo && r < 2)) kinds.kind[r] = 3;
+        else {
+            kinds.kind[r] = (b->mode[r] == PYSDR_MODE_AM || b->mode[r] == PYSDR_MODE_USB) ? 2 : 1;
+            any_real = true;
+        }
+    }
     if (b->timing) {
         cudaEvent_t e;
         CUDA_TRY(cudaEventCreate(&e));
         CUDA_TRY(cudaEventRecord(e, st));
         b->evs.push_back(e);
     }
-    agc_scan_kernel<<<c.n_rx, AGC_THREADS, 0, st>>>(s);
-    LAUNCH_CHECK();
-    b->launches++;
-    ApplyKinds kinds;
-    bool any_real = false;
-    for (int r = 0; r < PYSDR_MAX_RX; ++r) {
-        kinds.kind[r] = 0;
-        if (r >= c.n_rx) continue;
-        const float *aout = (const float *)(b->d_a + (size_t)r * b->a_stride);
-        float *am = d_am + (size_t)r * 2 * out_stride;
-        float *amdc = d_am_dc ? d_am_dc + (size_t)r * 2 * out_stride : nullptr;
-        if (b->mode[r] == PYSDR_MODE_IQ && !(b->stereo && r < 2)) {
+    const bool fuse = !b->force_unfused && !b->stereo;
+    if (fuse) {
+        if (b->back_grid <= 0) {
+            int occ = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, agc_back_fused_kernel, BACK_THREADS, 0));
+            if (occ < 1) { pysdr_set_error("fused back kernel does not fit on an SM"); return PYSDR_ERR_CUDA; }
+            b->back_grid = pysdr_sm_count() * (occ > 4 ? 4 : occ);         // every CTA resident at once: the grid barrier needs it
+        }
+        BackArgs p;
+        memset(&p, 0, sizeof(p));
+        p.do_peaks = b->peaks_deferred ? 1 : 0;
+        p.do_enter = enter ? 1 : 0; p.n_before = n_before; p.sums = d_sums; p.n_rx = c.n_rx;
+        p.a = (const float *)b->d_a; p.a_row = 2 * b->a_stride;
+        p.peaks = (float *)b->pend_peaks; p.peaks_row = n_blocks;
+        p.n_blocks = n_blocks; p.B0 = b->pend_B0; p.in_chunk = c.in_chunk; p.m0 = b->pend_m0; p.n_out = n_out;
+        p.up = c.up; p.down = c.down;
+        if (b->peaks_deferred) p.sa = b->pend_sa;
+        p.scan = s;
+        p.gains = b->d_gains; p.g_row = b->max_blocks;
+        p.am = d_am; p.am_dc = d_am_dc; p.am_row = 2 * out_stride;
+        p.kinds = kinds;
+        p.bar = b->d_bar; p.bar_base = b->bar_count;
+        i64 want = ((i64)c.n_rx * n_blocks + BACK_THREADS / 32 - 1) / (BACK_THREADS / 32);
+        if (want < c.n_rx + 2) want = c.n_rx + 2;                          // scans + the state-update items
+        const int grid = (int)(want < b->back_grid ? want : b->back_grid);
+        agc_back_fused_kernel<<<grid, BACK_THREADS, 0, st>>>(p);
+        LAUNCH_CHECK();
+        b->launches++;
+        b->bar_count += (unsigned long long)grid * (p.do_peaks ? 2ull : 1ull);
+        b->peaks_deferred = false;
+    } else {
+        if (b->peaks_deferred) {
+            int rc = launch_block_peaks(b, (float *)b->pend_peaks, b->pend_sa, n_blocks, b->pend_B0, b->pend_m0, n_out, st);
+            if (rc) return rc;
+            b->peaks_deferred = false;
+        }
+        if (enter) {
+            agc_enter_kernel<<<1, 32, 0, st>>>(b->d_agc, d_sums, n_before, c.n_rx);
+            LAUNCH_CHECK();
+            b->launches++;
+        }
+        agc_scan_kernel<<<c.n_rx, AGC_THREADS, 0, st>>>(s);
+        LAUNCH_CHECK();
+        b->launches++;
+        for (int r = 0; r < c.n_rx; ++r) {
+            if (kinds.kind[r] != 3) continue;
+            const float *aout = (const float *)(b->d_a + (size_t)r * b->a_stride);
+            float *am = d_am + (size_t)r * 2 * out_stride;
+            float *amdc = d_am_dc ? d_am_dc + (size_t)r * 2 * out_stride : nullptr;
             i64 n = 2 * n_out, blocks = (n + 255) / 256;
             if (blocks > (i64)pysdr_sm_count() * 8) blocks = (i64)pysdr_sm_count() * 8;
             copy_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(aout, am, n);
@@ -1396,18 +1605,15 @@ extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks,
                 LAUNCH_CHECK();
                 b->launches++;
             }
-        } else {
-            kinds.kind[r] = (b->mode[r] == PYSDR_MODE_AM || b->mode[r] == PYSDR_MODE_USB) ? 2 : 1;
-            any_real = true;
         }
-    }
-    if (any_real) {
-        dim3 grid((unsigned)((n_blocks + BLK_WARPS - 1) / BLK_WARPS), (unsigned)c.n_rx);
-        agc_apply_kernel<<<grid, 32 * BLK_WARPS, 0, st>>>((const float *)b->d_a, 2 * b->a_stride, b->d_gains, b->max_blocks, d_am,
-                                                           d_am_dc, 2 * out_stride, kinds, n_blocks, b->pend_B0, c.in_chunk, c.up,
-                                                           c.down, b->pend_m0, n_out);
-        LAUNCH_CHECK();
-        b->launches++;
+        if (any_real) {
+            dim3 grid((unsigned)((n_blocks + BLK_WARPS - 1) / BLK_WARPS), (unsigned)c.n_rx);
+            agc_apply_kernel<<<grid, 32 * BLK_WARPS, 0, st>>>((const float *)b->d_a, 2 * b->a_stride, b->d_gains, b->max_blocks, d_am,
+                                                               d_am_dc, 2 * out_stride, kinds, n_blocks, b->pend_B0, c.in_chunk, c.up,
+                                                               c.down, b->pend_m0, n_out);
+            LAUNCH_CHECK();
+            b->launches++;
+        }
     }
     if (b->timing) {
         cudaEvent_t e;
@@ -1416,6 +1622,23 @@ extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks,
         b->evs.push_back(e);
     }
     b->pending = false;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, int64_t skip_blocks,
+                                       float *d_am, float *d_am_dc, int64_t out_stride, void *stream) {
+    return back_impl(b, d_prev_peaks, n_prev, skip_blocks, nullptr, 0, false, d_am, d_am_dc, out_stride, (cudaStream_t)stream);
+}
+
+extern "C" int pysdr_bank_process_back_carry(pysdr_bank *b, const double *d_summaries, int n_before, int64_t skip_blocks,
+                                             float *d_am, float *d_am_dc, int64_t out_stride, void *stream) {
+    if (n_before < 0 || (n_before > 0 && !d_summaries)) { pysdr_set_error("process_back_carry: bad arguments"); return PYSDR_ERR_ARG; }
+    return back_impl(b, nullptr, 0, skip_blocks, d_summaries, n_before, true, d_am, d_am_dc, out_stride, (cudaStream_t)stream);
+}
+
+extern "C" int pysdr_bank_force_unfused(pysdr_bank *b, int on) {
+    if (!b) return PYSDR_ERR_ARG;
+    b->force_unfused = on != 0;
     return PYSDR_OK;
 }
 
@@ -1432,6 +1655,8 @@ extern "C" int pysdr_bank_agc_summary(pysdr_bank *b, int64_t skip_blocks, double
 
 extern "C" int pysdr_bank_agc_enter(pysdr_bank *b, const double *d_summaries, int n_before, void *stream) {
     if (!b || n_before < 0 || (n_before > 0 && !d_summaries)) { pysdr_set_error("agc_enter: bad arguments"); return PYSDR_ERR_ARG; }
+    b->lazy_reset_agc = false;               // this entry state replaces the restart a seek(0) asked for ...
+    { int rc = flush_seek(b, (cudaStream_t)stream); if (rc) return rc; }     // ... and a pending seek must not undo it afterwards
     agc_enter_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(b->d_agc, d_summaries, n_before, b->cfg.n_rx);
     LAUNCH_CHECK();
     b->launches++;
@@ -1467,9 +1692,31 @@ extern "C" int pysdr_bank_get_timing(pysdr_bank *b, double out4[4], void *stream
 extern "C" int pysdr_bank_process(pysdr_bank *b, const void *d_iq, int64_t n_in, int halo_in_place, void *d_iq_bb,
                                   float *d_am, float *d_am_dc, int64_t out_stride, int64_t *n_out, void *stream) {
     if (!b) { pysdr_set_error("null bank"); return PYSDR_ERR_ARG; }
+    b->defer_peaks = true;                   // back follows at once: block peaks + state update ride its fused launch
     int rc = pysdr_bank_process_front(b, d_iq, n_in, halo_in_place, d_iq_bb, out_stride, b->d_peaks, n_out, stream);
+    b->defer_peaks = false;
     if (rc) return rc;
     return pysdr_bank_process_back(b, nullptr, 0, 0, d_am, d_am_dc, out_stride, stream);
+}
+
+// A pending seek() is materialised either inside the next process call (K1 clears the carried complex memory and reads a
+// zero history, the fused back kernel restarts the AGC: no launch of its own) or, for every other API that looks at the
+// carried state, by this flush.
+static int flush_seek(pysdr_bank *b, cudaStream_t st) {
+    if (b->lazy_seek) {
+        seek_reset_kernel<<<b->cfg.n_rx + 1, 256, 0, st>>>(b->d_C, b->c_stride, b->hc, b->cfg.n_rx, b->d_hist, b->need + 8, b->d_pll,
+                                                           b->d_agc, b->lazy_reset_agc ? 1 : 0);
+        LAUNCH_CHECK();
+        b->launches++;
+        b->lazy_seek = false;
+        b->lazy_reset_agc = false;
+    } else if (b->lazy_reset_agc) {              // the seek itself was folded into a front call; the AGC restart is still due
+        agc_enter_kernel<<<1, 32, 0, st>>>(b->d_agc, nullptr, 0, b->cfg.n_rx);
+        LAUNCH_CHECK();
+        b->launches++;
+        b->lazy_reset_agc = false;
+    }
+    return PYSDR_OK;
 }
 
 extern "C" int pysdr_bank_seek(pysdr_bank *b, int64_t n0_abs, void *stream) {
@@ -1477,14 +1724,13 @@ extern "C" int pysdr_bank_seek(pysdr_bank *b, int64_t n0_abs, void *stream) {
         pysdr_set_error("seek: position must be a non-negative multiple of IN_CHUNK_SIZE");
         return PYSDR_ERR_ALIGN;
     }
-    cudaStream_t st = (cudaStream_t)stream;
+    (void)stream;
     b->n0 = n0_abs;
     b->pending = false;
-    // one launch; at the stream origin (n0 = 0) the AGCs restart too: a fresh set of receivers
-    seek_reset_kernel<<<b->cfg.n_rx + 1, 256, 0, st>>>(b->d_C, b->c_stride, b->hc, b->cfg.n_rx, b->d_hist, b->need + 8, b->d_pll,
-                                                       b->d_agc, n0_abs == 0 ? 1 : 0);
-    LAUNCH_CHECK();
-    b->launches++;
+    b->peaks_deferred = false;
+    // every carried state goes back to "nothing before this sample"; at the stream origin (n0 = 0) the AGCs restart too
+    b->lazy_seek = true;
+    b->lazy_reset_agc = b->lazy_reset_agc || n0_abs == 0;
     return PYSDR_OK;
 }
 
@@ -1505,6 +1751,7 @@ extern "C" int64_t pysdr_bank_state_size(const pysdr_bank *b) {
 
 extern "C" int pysdr_bank_get_state(pysdr_bank *b, void *blob, int64_t size, void *stream) {
     if (!b || !blob || size < pysdr_bank_state_size(b)) { pysdr_set_error("get_state: bad blob"); return PYSDR_ERR_ARG; }
+    { int rc = flush_seek(b, (cudaStream_t)stream); if (rc) return rc; }
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     char *p = (char *)blob;
     StateHeader h;
@@ -1526,6 +1773,7 @@ extern "C" int pysdr_bank_get_state(pysdr_bank *b, void *blob, int64_t size, voi
 
 extern "C" int pysdr_bank_set_state(pysdr_bank *b, const void *blob, int64_t size, void *stream) {
     if (!b || !blob || size < pysdr_bank_state_size(b)) { pysdr_set_error("set_state: bad blob"); return PYSDR_ERR_ARG; }
+    b->lazy_seek = false; b->lazy_reset_agc = false; b->peaks_deferred = false;      // the blob replaces every carried state
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     const char *p = (const char *)blob;
     StateHeader h;

@@ -94,6 +94,12 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (a.zero_c_hist && g.rx0 == 0) {                                     // a pending seek(): nothing before this sample
+        for (int r = blockIdx.x; r < a.n_rx; r += gridDim.x) {
+            float2 *row = a.c_out + (size_t)r * a.c_stride;
+            for (int e = tid; e < a.hc; e += K1F_THREADS) row[e] = make_float2(0.f, 0.f);
+        }
+    }
 
     // tile geometry ---------------------------------------------------------------------------------
     auto tile_a2 = [&](i64 T, i64 &a2, int &cnt2) {
@@ -127,7 +133,7 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
             const i64 rel = a2 + ee;
             float2 v = make_float2(0.f, 0.f);
             if (rel >= 0) { if (rel < a.n_in) v = a.x[rel]; }
-            else if (rel >= -(i64)a.need) v = a.hist[a.need + rel];
+            else if (rel >= -(i64)a.need && a.hist) v = a.hist[a.need + rel];
             dst[ee] = v;
         }
         __syncwarp();

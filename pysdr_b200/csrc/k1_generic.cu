@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) k1_generic_kernel(K1Args a) {
             const i64 idx = r0 - j;
             float2 xv;
             if (idx >= 0) xv = __ldg(a.x + idx);
-            else if (idx >= -(i64)a.need) xv = a.hist[a.need + idx];
+            else if (idx >= -(i64)a.need && a.hist) xv = a.hist[a.need + idx];
             else xv = make_float2(0.f, 0.f);
 #pragma unroll
             for (int r = 0; r < PYSDR_MAX_RX; ++r) {

@@ -169,13 +169,16 @@ class ShardedCapture:
             prev = exchange_agc_peaks(own, self.rank, self.world)
             return self.back(prev, want_dc=want_dc)
         b = self.bank
+        if self.world == 1:                                                  # nothing to exchange: the plain whole-capture call
+            b.seek(0)
+            return b.process(xbuf[self.plan['lead']:], want_dc=want_dc)
         self.front(xbuf, copy_own=False)
         w = self.plan['warm_chunks']
-        if self.world > 1:
-            check(b.lib.pysdr_bank_agc_summary(b.h, w, ctypes.c_void_p(self.summary.data_ptr()), _stream_ptr()))
-            exchange_agc_summaries(self.summary, self.all_sum, self.world)      # the one collective of the path
-        check(b.lib.pysdr_bank_agc_enter(b.h, ctypes.c_void_p(self.all_sum.data_ptr()), self.rank, _stream_ptr()))
-        return self.back(None, want_dc=want_dc)
+        check(b.lib.pysdr_bank_agc_summary(b.h, w, ctypes.c_void_p(self.summary.data_ptr()), _stream_ptr()))
+        exchange_agc_summaries(self.summary, self.all_sum, self.world)       # the one collective of the path
+        am, iq, dc = b.process_back_carry(self.all_sum, self.rank, want_dc=want_dc, skip_blocks=w)
+        k = self.skip_out
+        return [a[k:] for a in am], [a[k:] for a in iq], [a[k:] for a in dc]
 
 
 # ---- the other natural axis (SURVEY.md 8e axis 1): shard by receiver, no data-path collective -----------------------

@@ -177,3 +177,41 @@ def test_o1_agc_carry_three_shards_emulated_on_one_gpu():
         for k in range(4):
             g = got[k].cpu().numpy()
             assert_parity(g, ref[k][m0:m0 + len(g)], "shard %d rx%d vs single stream" % (r, k), rel_tol=2e-5, snr_min=90)
+
+
+@pytest.mark.parametrize("modes", [['AM', 'NFM', 'USB', 'CW'], ['IQ', 'AM', 'LSB'], ['RTTY'], ['USB', 'IQ', 'AM', 'NFM', 'CW', 'LSB']])
+def test_fused_back_kernel_equals_standalone_tail_kernels(modes):
+    """agc_back_fused_kernel (block peaks + state update -> grid barrier -> scan -> grid barrier -> gain / DC removal, with
+    seek() and the AGC restart folded in) against the stand-alone kernels it replaces: bit-identical audio, DC-removed
+    audio, baseband, AGC state and carried memories, over whole-capture calls, chunked calls, re-seeks and a ragged tail."""
+    n_rx = len(modes)
+    P, _ = make_both(2.048, [1000 + 17 * k for k in range(n_rx)], modes, af_bw_khz=[2] * n_rx, nfilt=301)
+    C = P.IN_CHUNK_SIZE
+    from pysdr_b200.receiver import receiver_offsets
+    x = torch.from_numpy(_sig(9 * C + 777, P, receiver_offsets(P), 11)).cuda()
+    banks = [_bank(P, 9 * C + 777), _bank(P, 9 * C + 777)]
+    banks[1].force_unfused(True)
+    plans = [[(0, 9 * C + 777)],                                      # one ragged call
+             [(0, 4 * C), (4 * C, 5 * C), (5 * C, 9 * C)],            # chunked, carried state between calls
+             [(0, 2 * C), (2 * C, 9 * C + 777)]]
+    for plan in plans:
+        outs = []
+        for b in banks:
+            b.seek(0)                                                 # folded into the next call on the fused bank
+            got = []
+            for a0, a1 in plan:
+                am, iq, dc = b.process(x[a0:a1], want_dc=True)
+                got.append(([v.clone() for v in am], [v.clone() for v in iq], [v.clone() for v in dc]))
+            got.append(b.agc_get(0))
+            outs.append(got)
+        for (amA, iqA, dcA), (amB, iqB, dcB) in zip(outs[0][:-1], outs[1][:-1]):
+            for r in range(n_rx):
+                assert torch.equal(amA[r], amB[r]) and torch.equal(iqA[r], iqB[r]) and torch.equal(dcA[r], dcB[r]), (plan, r)
+        assert outs[0][-1] == outs[1][-1]
+    for b in banks:                                                   # a seek to a later block: memories cleared, AGC kept
+        b.seek(3 * C)
+        am, _, _ = b.process(x[3 * C:6 * C])
+        b._keep = [v.clone() for v in am]
+    for r in range(n_rx):
+        assert torch.equal(banks[0]._keep[r], banks[1]._keep[r])
+    assert banks[0].get_state() == banks[1].get_state()
