@@ -31,6 +31,52 @@ ALGO_BYTES_PER_SAMPLE = 8.0 + 4 * (3.0 / 500.0) * 4  # 8.096 B (SURVEY 8d / BASE
 METRIC = "IQ Msamples/s through 4-RX demod chain"
 
 
+def workload_config(n_chunks):
+    """The `config` object — identical in the own arm and the reference arm (what differs between the arms lives under
+    `arm`, `cpu_baseline.sample` and `e2e.how`)."""
+    C = 170666
+    return {"workload": "cfg2: 4 independent receivers (AM, NFM, USB, CW) on a 60 s 8 MS/s synthetic IQ capture "
+                        "(%d blocks x %d = %d samples per GPU), 8 MS/s -> 48 kHz (3/500), FILT_LEN 1001, AF FIR 1001"
+                        % (n_chunks, C, n_chunks * C),
+            "l2": "input per step (%.2f GB) exceeds L2; no flush needed" % (n_chunks * C * 8 / 1e9),
+            "offsets_khz": FCS_KHZ, "modes": MODES, "af_bw_khz": AF_BW_KHZ}
+
+
+def host_info():
+    model = "?"
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    try:
+        usable = len(os.sched_getaffinity(0))
+    except Exception:
+        usable = os.cpu_count() or 1
+    return {"cpu_model": model, "nproc": os.cpu_count(), "usable_cores": usable}
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads to the cores NVML reports as local to its GPU, BEFORE any pinned allocation, so that
+    the capture's pages and the staging buffers land on the GPU's own NUMA node (first touch).  Returns a description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w in range(n_words) for b in range(64) if (int(mask[w]) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"bound": True, "cores": len(allowed), "first": allowed[0], "last": allowed[-1]}
+        return {"bound": False, "why": "NVML affinity set empty or outside this process's cpuset"}
+    except Exception as e:                     # no NVML / no permission: run unbound and say so
+        return {"bound": False, "why": "%s: %s" % (type(e).__name__, e)}
+
+
 def cfg_argv():
     return (['-fs', str(SRATE_MHZ), '-fc'] + [str(f) for f in FCS_KHZ] + ['-mode'] + MODES +
             ['-foffset', '100', '-af_bw'] + [str(b) for b in AF_BW_KHZ])
@@ -107,72 +153,102 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """The reference's own CPU implementation of the path = our oracle port (upstream sig_proc is not obtainable,
-    see oracle/sig_proc_oracle.py) in the reference's MP_SCHEME 3 shape: one worker process per receiver, the same
-    chunk sequence for each, joined per step."""
+    """The reference's own CPU implementation of the path = our oracle port (upstream sig_proc is not obtainable, see
+    oracle/sig_proc_oracle.py) in the reference's MP_SCHEME 3 shape — one worker process per receiver fed with the same
+    chunk sequence (reference mp.py:146-175, receiver.py:726-739) — with the LO taken from a table as the reference
+    arranges (params.py:470-471).  To use all the host cores the box has, G = usable_cores // 4 such 4-process groups run
+    side by side, each replaying its own segment of the capture (what several pySDR instances on one host would do).
+    Each step is a bounded sample of the 2812-block workload, sized from a calibration step so that the whole
+    --steps/--warmup run takes about a minute."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import multiprocessing as mp
     import numpy as np
-    sample_chunks = int(args.ref_chunks)
+    hi = host_info()
+    # headline: ONE group = the parallelism the reference itself has (NUM_RX processes).  --ref-groups G > 1 runs G such
+    # groups side by side; the all-cores figure is reported next to the headline under arm.all_cores.
+    groups = max(1, min(int(args.ref_groups) if args.ref_groups else 1, 16))
     ctx = mp.get_context("fork")
     from oracle import receiver_oracle as rxo
     Po = rxo.make_P(SRATE_MHZ * 1e6, [f * 1e3 for f in FCS_KHZ], MODES, foffset=100e3, af_bw=[b * 1e3 for b in AF_BW_KHZ])
     offs = [Po.FOFFSET + f - Po.FC[0] for f in Po.FC]
     from pysdr_b200.synth import synth_iq
-    n = sample_chunks * Po.IN_CHUNK_SIZE
-    x = synth_iq(n, Po.SRATE, offs, MODES, seed=1234).numpy()
+    C = Po.IN_CHUNK_SIZE
+    max_chunks = 192                                                 # per group; segments of one shared synthetic capture
+    x = synth_iq(max_chunks * C, Po.SRATE, offs, MODES, seed=1234).numpy()
 
-    def worker(irx, conn):
+    def worker(g, irx, conn):
         os.environ["OMP_NUM_THREADS"] = "1"
         from oracle import sig_proc_oracle as dsp
         P = rxo.make_P(SRATE_MHZ * 1e6, [f * 1e3 for f in FCS_KHZ], MODES, foffset=100e3,
                        af_bw=[b * 1e3 for b in AF_BW_KHZ])
         rx = dsp.Receiver(P, offs[irx], irx, str(irx + 1), dtype=np.complex64, fast=True)
-        C = P.IN_CHUNK_SIZE
         while True:
             msg = conn.recv()
             if msg == 'quit':
                 break
             acc = 0.0
-            for c in range(sample_chunks):
-                am = rx.demod_data(x[c * C:(c + 1) * C])
+            for c in range(int(msg)):
+                k = (c + 7 * g) % max_chunks                        # every group walks its own part of the capture
+                am = rx.demod_data(x[k * C:(k + 1) * C])
                 acc += float(am[0])
             conn.send(acc)
 
     procs, conns = [], []
-    for irx in range(4):
-        a, b = ctx.Pipe()
-        p = ctx.Process(target=worker, args=(irx, b), daemon=True)
-        p.start()
-        procs.append(p)
-        conns.append(a)
+    for g in range(groups):
+        for irx in range(4):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=worker, args=(g, irx, b), daemon=True)
+            p.start()
+            procs.append(p)
+            conns.append(a)
 
-    def step():
+    def step(chunks):
         for c in conns:
-            c.send('go')
+            c.send(chunks)
         for c in conns:
             c.recv()
 
+    t0 = time.perf_counter()
+    step(8)                                                          # calibration (also warms caches / FFT plans)
+    rate = 8 * C * groups / (time.perf_counter() - t0)              # samples/s over all groups
+    total_steps = args.steps + max(1, args.warmup)
+    chunks = int(args.ref_chunks) if args.ref_chunks else int(max(8, min(max_chunks, 60.0 * rate / (total_steps * C * groups))))
     for _ in range(max(1, args.warmup)):
-        step()
+        step(chunks)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        step(chunks)
     dt = time.perf_counter() - t0
     for c in conns:
         c.send('quit')
+    n = chunks * C * groups
     val = n * args.steps / dt / 1e6
-    sample = "%d chunks (%.2f s of the 60 s capture, %d samples) per step, complex64 numpy/scipy oracle port" % (
-        sample_chunks, n / Po.SRATE, n)
+    all_cores = None
+    if not args.ref_groups and hi["usable_cores"] >= 8 and not args.no_all_cores:
+        # informational: G = usable_cores // 4 independent 4-process groups (several pySDR instances on one host)
+        import subprocess
+        G = min(hi["usable_cores"] // 4, 16)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-groups", str(G),
+                                "--steps", "3", "--warmup", "1", "--no-all-cores"], capture_output=True, text=True, timeout=240)
+            sub = json.loads(r.stdout.strip().splitlines()[-1])
+            all_cores = {"value": sub["value"], "unit": "Msamples/s", "processes": 4 * G,
+                         "note": "%d independent 4-process groups side by side, each on its own segment of the capture" % G}
+        except Exception as e:
+            all_cores = {"error": "%s: %s" % (type(e).__name__, e)}
+    sample = ("%d chunks (%.2f s of the 60 s capture) per 4-process group per step, %d group(s) side by side = %d samples "
+              "per step; complex64 numpy/scipy oracle port (upfirdn + fftconvolve), table LO" % (
+                  chunks, chunks * C / Po.SRATE, groups, n))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex64/f32",
-            "data": "synthetic",
-            "config": {"workload": "cfg2: 4 RX AM/NFM/USB/CW, 8 MS/s -> 48 kHz, FILT_LEN 1001; bounded sample: " + sample,
-                       "parallelism": "MP_SCHEME 3: one CPU process per receiver"},
-            "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": 4, "kind": "port", "sample": sample},
+            "data": "synthetic", "config": workload_config(int(args.chunks)),
+            "arm": {"parallelism": "MP_SCHEME 3: one CPU process per receiver, x%d groups = %d processes" % (groups, 4 * groups),
+                    "bounded_sample": sample, "host": hi, "all_cores": all_cores},
+            "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": 4 * groups, "kind": "port", "sample": sample,
+                             "cpu_model": hi["cpu_model"], "nproc": hi["nproc"]},
             "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -202,9 +278,70 @@ def cpu_baseline_single(seconds_target=12.0):
         if time.perf_counter() - t0 > seconds_target:
             break
     dt = time.perf_counter() - t0
-    return {"value": done / dt / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port",
-            "sample": "%d samples (%.1f s of signal) of the same 4-RX workload, complex64 numpy/scipy oracle port, "
-                      "1 process (MP_SCHEME 1)" % (done, done / P.SRATE)}
+    hi = host_info()
+    return {"value": done / dt / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port", "cpu_model": hi["cpu_model"],
+            "nproc": hi["nproc"],
+            "sample": "%d samples (%.1f s of signal) of the same 4-RX workload, complex64 numpy/scipy oracle port with a table "
+                      "LO, 1 process (MP_SCHEME 1)" % (done, done / P.SRATE)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def parity_check(P, offs, rank, world, dev, cpr=9):
+    """Correctness carried by the bench line itself: on a small capture of world x 9 blocks every rank compares the audio
+    of ITS time shard (the timed code path: filter warm-up, halo in place, O(1) AGC carry over the collective) with the same
+    blocks taken from a single-stream pass it runs locally.  N = 1: whole-capture call against chunk-at-a-time calls.
+    Returns the worst max-abs relative error and difference SNR over ranks and receivers (gate 2e-5 / 90 dB: the two sides
+    differ only by FFT block alignment and the re-associated AGC composition)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pysdr_b200.bank import ReceiverBank
+    from pysdr_b200.dist import ShardedCapture
+    from pysdr_b200.synth import synth_iq
+    C = int(P.IN_CHUNK_SIZE)
+    n_tot = world * cpr * C
+    x = synth_iq(n_tot, P.SRATE, offs, MODES, seed=99, device=dev, block=1 << 18)
+    env = torch.ones(n_tot, device=dev)
+    env[2 * C:3 * C] = 4.0                                          # a burst whose AGC recovery crosses shard boundaries
+    x = x * env
+    single = ReceiverBank(P, offs, max_in=(rank + 1) * cpr * C, device=dev)
+    ref_am, _, _ = single.process(x[:(rank + 1) * cpr * C], want_dc=False)
+    m0 = -((-int(P.UP) * rank * cpr * C) // int(P.DOWN))
+    ref = [a[m0:].clone() for a in ref_am]
+    if world == 1:
+        b = ReceiverBank(P, offs, max_in=C, device=dev)
+        parts = [[] for _ in offs]
+        for c in range(cpr):
+            am, _, _ = b.process(x[c * C:(c + 1) * C], want_dc=False)
+            for r in range(len(offs)):
+                parts[r].append(am[r].clone())
+        got = [torch.cat(p) for p in parts]
+        how = "whole-capture call vs %d chunk-at-a-time calls" % cpr
+    else:
+        b = ReceiverBank(P, offs, max_in=(cpr + 1) * C, device=dev)
+        sh = ShardedCapture(b, P, rank, world, cpr)
+        pl = sh.plan
+        am, _, _ = sh.step(x[pl['first_sample']:pl['start'] + pl['n']])
+        got = [a.clone() for a in am]
+        how = "each rank's time shard (%d blocks, O(1) AGC carry over the collective) vs a local single-stream pass" % cpr
+    worst_rel, worst_snr = 0.0, 1e9
+    for g, r in zip(got, ref):
+        assert g.shape == r.shape, (g.shape, r.shape)
+        d = (g.double() - r.double())
+        rel = float(d.abs().max() / r.abs().max())
+        snr = float(10 * torch.log10((r.double() ** 2).sum() / (d ** 2).sum().clamp_min(1e-300)))
+        worst_rel, worst_snr = max(worst_rel, rel), min(worst_snr, snr)
+    if world > 1:
+        t = torch.tensor([worst_rel, -worst_snr], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        worst_rel, worst_snr = float(t[0]), -float(t[1])
+    ok = worst_rel <= 2e-5 and worst_snr >= 90.0
+    res = {"ok": bool(ok), "max_abs_rel_err": worst_rel, "min_diff_snr_db": worst_snr, "blocks_per_rank": cpr, "ranks": world,
+           "compared": how, "gate": "rel <= 2e-5 and SNR >= 90 dB"}
+    if not ok:
+        raise SystemExit("bench.py: parity check failed before timing: %s" % json.dumps(res))
+    del single, b
+    return res
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -221,6 +358,7 @@ def run_own(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(local) if not args.no_numa_bind else {"bound": False, "why": "--no-numa-bind"}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -238,8 +376,10 @@ def run_own(args):
     xbuf = synth_iq(plan['lead'] + n, P.SRATE, offs, MODES, seed=1234, device=dev, n0=plan['first_sample'])
     x_main = xbuf[plan['lead']:]
 
+    parity = parity_check(P, offs, rank, world, dev)                # sharded == single stream, before anything is timed
+
     def step():
-        shard.step(xbuf)                                            # front -> all-gather of AGC peaks -> back
+        shard.step(xbuf)                                            # front -> AGC summary exchange (N > 1) -> back
 
     def barrier():
         if world > 1:
@@ -250,7 +390,6 @@ def run_own(args):
         step()
     barrier()
     l0 = bank.launches
-    bank.set_timing(True)
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -262,9 +401,15 @@ def run_own(args):
     barrier()
     clocks = sampler.result()
     ms = e0.elapsed_time(e1)
+    l1 = bank.launches
+    # stage breakdown (roofline of the dominant kernel): a second, separate pass with CUDA events recorded between the
+    # kernels on their stream — the event records would break the programmatic dependent launches of the headline loop
+    bank.set_timing(True)
+    for _ in range(args.steps):
+        step()
     tm = bank.get_timing()
     bank.set_timing(False)
-    launches = bank.launches - l0
+    launches = l1 - l0
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -304,7 +449,30 @@ def run_own(args):
                "d2h_bytes_per_step": int(4 * n_out_tot * 4), "steps": ksteps,
                "how": "pinned host complex64 capture -> 64-chunk segments double-buffered H2D on a copy stream -> "
                       "bank.process -> audio D2H to pinned host, per GPU"}
-        del hx, streamer
+        del streamer
+        # the call the reference's own loop makes (receiver.py:724-725): one IN_CHUNK_SIZE chunk per call, host numpy in,
+        # host numpy out, all four receivers of the chunk served from one upload (ReceiverBank.process_host)
+        hx_np = hx.numpy()
+        pcb = ReceiverBank(P, offs, max_in=C, device=dev)
+        n_pc = 256
+        for c in range(8):
+            pcb.process_host(hx_np[c * C:(c + 1) * C], want_dc=False)
+        barrier()
+        t0 = time.perf_counter()
+        for c in range(n_pc):
+            am_pc, _, _ = pcb.process_host(hx_np[c * C:(c + 1) * C], want_dc=False)
+        barrier()
+        dt_pc = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt_pc], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_pc = float(t.item())
+        e2e["per_chunk"] = {"value": world * n_pc * C / dt_pc / 1e6, "unit": "Msamples/s", "ms_per_chunk": dt_pc / n_pc * 1e3,
+                            "realtime_factor": (C / P.SRATE) / (dt_pc / n_pc), "chunks": n_pc,
+                            "how": "ReceiverBank.process_host per 170666-sample chunk (21.3 ms of signal): numpy chunk -> pinned "
+                                   "staging -> H2D -> kernels -> D2H -> numpy, synchronous, per GPU"}
+        e2e["numa"] = numa
+        del hx, pcb, hx_np
         # the same capture as the hardware delivers it: CS16 (reference receiver.py:609-617), 4 bytes per sample over PCIe,
         # converted on the device.  Informational: the headline e2e above stays on the complex64 capture of the config.
         st16 = ReplayStreamer(P, seg_chunks=64, device=dev, fmt='cs16')
@@ -344,20 +512,18 @@ def run_own(args):
             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * n, "k1_ms_per_launch": k1_ms,
             "traffic": (tr or {}).get("dram_bytes_per_launch_scaled_to", {}).get(str(n)) if tr else None,
             "traffic_note": (tr or {}).get("note") if tr else "no ncu --set full capture committed yet",
-            "stage_ms_per_step": {"k1": k1_ms, "front_rest(K2 detect+AF FIR+peaks+rolls)": tm["front_rest_ms"] / max(1, tm["calls"]),
-                                  "back(AGC scan+apply)": tm["back_ms"] / max(1, tm["calls"])},
+            "stage_ms_per_step": {"k1": k1_ms, "front_rest(K2: detect + AF FIR)": tm["front_rest_ms"] / max(1, tm["calls"]),
+                                  "back(fused: block peaks + state update, AGC scan, gain)": tm["back_ms"] / max(1, tm["calls"])},
             "whole_chain_frac": (ALGO_BYTES_PER_SAMPLE * world * n * args.steps / (ms * 1e-3) / 1e9) / (peak * world)}
     cpu = None if args.no_cpu else cpu_baseline_single()
     line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (complex64 samples; f64/u64 phase; f64 AGC)", "data": "synthetic",
-            "config": {"workload": "cfg2: 4 independent receivers (AM, NFM, USB, CW) on a 60 s 8 MS/s synthetic IQ capture "
-                                   "per GPU (%d blocks x %d = %d samples), 8 MS/s -> 48 kHz (3/500), FILT_LEN 1001, AF FIR 1001"
-                                   % (n_chunks, C, n),
-                       "parallelism": "time-sharded x%d (filter-memory warm-up chunk + all-gather of AGC block peaks)" % world
-                       if world > 1 else "single GPU, all 4 receivers share one read",
-                       "l2": "input per step (%.2f GB) exceeds L2; no flush needed" % (n * 8 / 1e9),
-                       "timed_region": "inputs resident in HBM; CUDA events on the launch stream; max over ranks"},
+            "config": workload_config(n_chunks),
+            "arm": {"parallelism": "time-sharded x%d (filter-memory warm-up chunk + ONE all-gather of a 152-byte AGC summary per "
+                                   "receiver per rank)" % world if world > 1 else "single GPU, all 4 receivers share one read",
+                    "timed_region": "inputs resident in HBM; CUDA events on the launch stream; max over ranks"},
+            "parity_check": parity,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
     emit(line)
     if world > 1:
@@ -389,9 +555,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--chunks", type=int, default=N_CHUNKS, help="IN_CHUNK_SIZE blocks per GPU per step")
-    ap.add_argument("--ref-chunks", type=int, default=96, help="reference arm: chunks per step (bounded sample)")
+    ap.add_argument("--ref-chunks", type=int, default=0, help="reference arm: chunks per group per step (0 = sized from a calibration step)")
+    ap.add_argument("--ref-groups", type=int, default=0, help="reference arm: 4-process groups side by side (0 = usable cores // 4)")
+    ap.add_argument("--no-all-cores", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "own":
         args.warmup = 3

@@ -255,6 +255,21 @@ class decimator:
         raw = np.concatenate((hist[len(hist) - H:], x))
         if lo is None:
             return raw, raw
+        if getattr(self, 'lo_table', False):
+            # CPU-baseline path: the LO as a two-level table instead of one complex exponential per sample — the reference
+            # arranges its tuning offset "so we don't have to compute sines/cosines over and over in the local osc"
+            # (params.py:470-471, utils.py:277-289).  exp(-j th(k)) with th(k) = base + inc*k, k = q*B + r, is
+            # T2[q] * T1[r]: T1 (B entries) is cached per LO increment, T2 has n/B entries per chunk; phases stay exact u64.
+            B = 4096
+            n = H + len(x)
+            if getattr(self, '_t1_inc', None) != lo.inc:
+                self._t1 = np.exp(-2j * np.pi * nco_phase_cycles(0, lo.inc, np.arange(B))).astype(self.dtype)
+                self._t1_inc = lo.inc
+            base = (lo.acc - lo.inc * H) & MASK64
+            q = np.arange(-(-n // B), dtype=np.int64)
+            t2 = np.exp(-2j * np.pi * nco_phase_cycles(base, (lo.inc * B) & MASK64, q)).astype(self.dtype)
+            z = (t2[:, None] * self._t1[None, :]).reshape(-1)[:n]              # in self.dtype: no widening pass
+            return raw, raw * z
         k = np.arange(-H, len(x), dtype=np.int64)
         ph = nco_phase_cycles(lo.acc, lo.inc, k)      # negative k wraps mod 2^64 = phase run backwards
         z = np.exp(-2j * np.pi * ph)
@@ -585,6 +600,7 @@ class Receiver:
         self.lo = signal_generator(frq, P.IN_CHUNK_SIZE, P.SRATE, True)
         self.dec = decimator(P.SRATE, P.UP, P.DOWN, P.FILT_LEN, video_bws, P.VIDEO_BW, dtype)
         self.dec.h = self.dec.filter_bank[_video_index(P, video_bws)]
+        self.dec.lo_table = bool(fast)               # CPU-baseline runs: table LO (same numbers to ~2e-16)
         self.demod = demodulator(P.FS_OUT, P.FILT_LEN, af_bws, dtype, exact=not fast)
         self.agc = agc()
         self.mute_cnt = 0

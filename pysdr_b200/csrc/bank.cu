@@ -10,6 +10,7 @@
 //   K2f roll the complex memory
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -23,6 +24,11 @@ void pysdr_set_error(const char *fmt, ...) {
 }
 extern "C" const char *pysdr_last_error(void) { return g_err; }
 
+bool pysdr_pdl_enabled(void) {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("PYSDR_NO_PDL"); on = (e && e[0] == '1') ? 0 : 1; }
+    return on != 0;
+}
 int pysdr_device(void) {
     int d = 0;
     if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
@@ -668,6 +674,8 @@ __global__ void __launch_bounds__(BACK_THREADS) agc_back_fused_kernel(const Back
     const int warp = threadIdx.x >> 5, wpc = BACK_THREADS / 32;
     const i64 gw = (i64)blockIdx.x * wpc + warp, gstride = (i64)gridDim.x * wpc;
     const i64 total = (i64)p.n_rx * p.n_blocks;
+    pdl_trigger();
+    pdl_wait();                                      // the AF filter kernel's audio (and, in split runs, the block peaks)
     if (p.do_peaks) {
         // the end-of-call state update rides on the LAST CTAs (the first n_rx run the scans)
         const int item = (int)gridDim.x - 1 - (int)blockIdx.x;
@@ -793,8 +801,8 @@ struct pysdr_bank {
     bool force_unfused;                      // testing: the stand-alone tail kernels
     bool defer_peaks, peaks_deferred;
     StateArgs pend_sa;
-    unsigned long long *d_bar;
-    unsigned long long bar_count;
+    unsigned long long *d_bar;               // grid barrier counter of the fused back kernel (monotonic)
+    unsigned long long bar_count;            // its value when the next launch starts
     int back_grid;
     // seek() folded into the next process_front / process_back (no launch of its own)
     bool lazy_seek, lazy_reset_agc;
@@ -823,8 +831,8 @@ static int bank_alloc(pysdr_bank *b) {
     CUDA_TRY(cudaMalloc(&b->d_gains, sizeof(float) * (size_t)c.n_rx * b->max_blocks));
     CUDA_TRY(cudaMalloc(&b->d_agc, sizeof(AgcState) * PYSDR_MAX_RX));
     CUDA_TRY(cudaMalloc(&b->d_pll, sizeof(double2) * PYSDR_MAX_RX));
-    CUDA_TRY(cudaMalloc(&b->d_bar, sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemset(b->d_bar, 0, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&b->d_bar, sizeof(unsigned long long) * (2 * PYSDR_MAX_RX + 2)));
+    CUDA_TRY(cudaMemset(b->d_bar, 0, sizeof(unsigned long long) * (2 * PYSDR_MAX_RX + 2)));
     return PYSDR_OK;
 }
 
@@ -971,7 +979,7 @@ extern "C" int pysdr_bank_set_demod(pysdr_bank *b, int rx, int mode, const float
         else t[j] = make_float2(taps[j], 0.f);
     }
     CUDA_TRY(cudaMemcpy(b->d_af + (size_t)rx * b->cfg.af_len, t.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
-    if (mode == PYSDR_MODE_AMSYNC && b->mode[rx] != PYSDR_MODE_AMSYNC)
+    if (mode == PYSDR_MODE_AMSYNC && b->demod_set[rx] && b->mode[rx] != PYSDR_MODE_AMSYNC)   // a real mode change, not set-up
         CUDA_TRY(cudaMemset(b->d_pll + rx, 0, sizeof(double2)));               // the loop starts from rest (receiver.py:649)
     b->mode[rx] = mode;
     b->af_cplx[rx] = is_complex;
@@ -1571,10 +1579,9 @@ static int back_impl(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, i
         i64 want = ((i64)c.n_rx * n_blocks + BACK_THREADS / 32 - 1) / (BACK_THREADS / 32);
         if (want < c.n_rx + 2) want = c.n_rx + 2;                          // scans + the state-update items
         const int grid = (int)(want < b->back_grid ? want : b->back_grid);
-        agc_back_fused_kernel<<<grid, BACK_THREADS, 0, st>>>(p);
-        LAUNCH_CHECK();
-        b->launches++;
+        CUDA_TRY(launch_pdl(agc_back_fused_kernel, dim3(grid), dim3(BACK_THREADS), 0, st, p));
         b->bar_count += (unsigned long long)grid * (p.do_peaks ? 2ull : 1ull);
+        b->launches++;
         b->peaks_deferred = false;
     } else {
         if (b->peaks_deferred) {

@@ -37,6 +37,27 @@ int pysdr_device(void);
         }                                                                                      \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------------
+// The three kernels of a step (K1 -> AF filter -> fused back) run back to back on one stream.  Launched with
+// programmaticStreamSerializationAllowed, a kernel's grid may be set up while its predecessor drains; it must not touch
+// anything the predecessor writes before pdl_wait() (griddepcontrol.wait), and the predecessor lets the launch proceed as
+// soon as all of its CTAs have passed pdl_trigger() (griddepcontrol.launch_dependents) — the dependent still cannot take
+// an SM slot from a predecessor CTA that has not started.  PYSDR_NO_PDL=1 in the environment turns the attribute off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pysdr_pdl_enabled(void);
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pysdr_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 static inline i64 ceil_div_i64(i64 a, i64 b) { return -((-a) / b) ; }   // b>0, a>=0 in our uses
 static inline i64 n_out_total(i64 n_in, int up, int down) { return (up * n_in + down - 1) / down; }
 

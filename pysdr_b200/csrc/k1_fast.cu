@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
         for (int s = 0; s < K1F_STAGES; ++s) { mbar_init(smem_u32(&bars[s]), 1); done_cnt[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_trigger();
+    pdl_wait();                      // x may come from a conversion kernel; C is still read by the previous call's back kernel
     __syncthreads();
     if (a.zero_c_hist && g.rx0 == 0) {                                     // a pending seek(): nothing before this sample
         for (int r = blockIdx.x; r < a.n_rx; r += gridDim.x) {
@@ -405,8 +407,7 @@ static int launch_one(const K1Args &a, const FastGeom &g, int grid, cudaStream_t
         CUDA_TRY(cudaFuncSetAttribute(k1_fast_kernel<NRXP, TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done |= dev_bit;
     }
-    k1_fast_kernel<NRXP, TPL><<<grid, K1F_THREADS, smem, st>>>(a, g);
-    LAUNCH_CHECK();
+    CUDA_TRY(launch_pdl(k1_fast_kernel<NRXP, TPL>, dim3(grid), dim3(K1F_THREADS), smem, st, a, g));
     return PYSDR_OK;
 }
 

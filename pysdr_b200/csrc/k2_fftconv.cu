@@ -86,6 +86,8 @@ af_fftconv_kernel(const FftConvArgs a) {
     float2 *s2 = s + FFT_SMEM_ELEMS(N);                                   // second buffer (N = 4096 launches only)
     __shared__ float s_max[2][FftPlan<N>::THREADS / 32];
     int pair_exp = 0;                                                     // b rides the transform scaled by 2^pair_exp
+    pdl_trigger();
+    pdl_wait();                                                           // K1's complex memory
 
     // ---- stage raw samples (async), detect from shared memory, lay out for the FFT ---------------------------------
     const int sh = (int)(k0 & 1);                                         // cp.async sources must be 16-byte aligned
@@ -260,8 +262,7 @@ static int fftconv_launch_n(const FftConvArgs &a0, int n_rx, cudaStream_t st) {
     if (n_units == 0) return PYSDR_OK;
     const int V = N - (a.L - 1);
     dim3 grid((unsigned)((a.n_out + V - 1) / V), (unsigned)n_units);
-    af_fftconv_kernel<N><<<grid, FftPlan<N>::THREADS, smem, st>>>(a);
-    LAUNCH_CHECK();
+    CUDA_TRY(launch_pdl(af_fftconv_kernel<N>, grid, dim3(FftPlan<N>::THREADS), smem, st, a));
     return PYSDR_OK;
 }
 

@@ -114,22 +114,30 @@ def test_cfg2_full_size_agc_trajectory_and_audio(cfg2):
         traj[r] = [g.update(p) for p in pk[r]]
         assert np.max(np.abs(traj[r] - gn[r]) / traj[r]) <= 2e-7, r        # float32 storage of a float64 recursion
     for blk in (1, 1406, 2805):
-        warm = min(2, blk)
+        # three consecutive blocks: a keyed CW carrier is silent for whole blocks, and the float32 FFT filter's rounding
+        # error scales with the loudest sample in its 4096-point window — errors are measured against the receiver's level
+        # over the span (and the capture, for the peaks), not against a silent block's own residue
+        warm, span = min(2, blk), 3
         s0 = (blk - warm) * C
-        xs = cfg2['x'][s0:(blk + 1) * C].cpu().numpy()
-        m_lo = odsp.n_out_total(blk * C, P.UP, P.DOWN)
-        m_hi = odsp.n_out_total((blk + 1) * C, P.UP, P.DOWN)
+        xs = cfg2['x'][s0:(blk + span) * C].cpu().numpy()
         for r in range(4):
             orx = odsp.Receiver(Po, cfg2['offs'][r], r, str(r), fast=True)
             orx.lo.advance(s0)
             orx.dec.n0 = s0
             orx.demod.m0 = odsp.n_out_total(s0, P.UP, P.DOWN)
-            for c in range(warm + 1):
+            ref = []
+            for c in range(warm + span):
                 iq = orx.dec.resamp_fast(xs[c * C:(c + 1) * C], orx.lo)
                 a = orx.demod.demod(iq, MODES[r], odsp._af_index(Po, r), odsp.per_rx(Po.BFO, r))
-            assert len(a) == m_hi - m_lo
-            assert abs(np.max(np.abs(a)) - pk[r, blk]) <= 1e-5 * pk[r, blk], (blk, r)
-            assert_parity(cfg2['am'][r][m_lo:m_hi].cpu().numpy(), np.asarray(a) * traj[r, blk], "audio rx%d block %d" % (r, blk))
+                if c >= warm:
+                    b = blk + c - warm
+                    assert abs(np.max(np.abs(a)) - pk[r, b]) <= 1e-5 * np.max(pk[r]), (b, r)
+                    ref.append(np.asarray(a) * traj[r, b])
+            m_lo = odsp.n_out_total(blk * C, P.UP, P.DOWN)
+            m_hi = odsp.n_out_total((blk + span) * C, P.UP, P.DOWN)
+            ref = np.concatenate(ref)
+            assert len(ref) == m_hi - m_lo
+            assert_parity(cfg2['am'][r][m_lo:m_hi].cpu().numpy(), ref, "audio rx%d blocks %d..%d" % (r, blk, blk + span - 1))
 
 
 def test_cfg3_full_size_psd_parseval(cfg2):
