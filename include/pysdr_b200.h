@@ -121,6 +121,18 @@ int pysdr_bank_process(pysdr_bank *b, const void *d_iq, int64_t n_in, int halo_i
                        void *d_iq_bb, float *d_am, float *d_am_dc, int64_t out_stride,
                        int64_t *n_out, void *stream);
 
+/* The reference-facing per-chunk call with HOST buffers (what `for irx: demodulate_data(P, self.x, irx)` amounts to,
+ * reference receiver.py:724-725): h_iq complex64[n_in] in host memory (page-locked memory is read by DMA directly, pageable
+ * memory goes through a pinned staging copy); on return *h_am / *h_iq_bb / *h_am_dc point at rows of a page-locked result
+ * block owned by the bank, valid until the next call: row r starts *row_floats floats after row r-1 and holds n_out
+ * float32 (real modes) or n_out complex64 (IQ / RTTY rows, and every *h_iq_bb row).  One call = upload, kernels, download,
+ * one synchronisation of `stream`.  want_iq / want_dc = 0 skip the baseband / DC-removed downloads. */
+int pysdr_bank_process_host(pysdr_bank *b, const void *h_iq, int64_t n_in, int want_iq, int want_dc, float **h_am,
+                            void **h_iq_bb, float **h_am_dc, int64_t *row_floats, int64_t *n_out, void *stream);
+
+/* Device copy of the chunk the last pysdr_bank_process_host call uploaded (e.g. for the auto-mute power detector). */
+int pysdr_bank_host_chunk_ptr(pysdr_bank *b, void **d_in);
+
 /* Split form for time-sharded multi-GPU runs: front = everything up to the per-block AGC peaks
  * (no cross-block dependency), back = AGC recursion + gain/DC application.  Between the two the
  * caller may all-gather d_peaks across ranks (NCCL) and pass the peaks of ALL earlier blocks.
@@ -172,9 +184,26 @@ int pysdr_bank_force_generic(pysdr_bank *b, int on);
 /* K1-only bank (WFM video stage: LO + FIR at the RF rate, UP = DOWN = 1): process() stops after K1; its output is the
  * new-sample part of the complex memory (pysdr_bank_c_memory) and, when given, d_iq_bb. */
 int pysdr_bank_set_k1_only(pysdr_bank *b, int on);
+/* on != 0: the caller promises that every input sample has a zero imaginary part (the WFM resampler rows are fed with the
+ * real FM discriminator output stored as complex64): the tap-stationary K1 then skips the Im-x half of its FMAs. */
+int pysdr_bank_set_real_input(pysdr_bank *b, int on);
 /* 3-point FM discriminator at any rate (reference sigs/nfm.m:123-127) with two carried samples:
  * out[n] = (Im(conj(y[n-1]) * (y[n] - y[n-2])), 0) as complex64; d_prev2: complex64[2] in/out. */
 int pysdr_fm_disc(const void *d_y, int64_t n, void *d_prev2, void *d_out, void *stream);
+/* WFM / WFM2 video stage at the RF rate ("demodulate first, then resample", reference gui.py:1703,1759-1762): LO mix +
+ * video FIR (rx.demod.wfm_video.h, gui.py:1704) + 3-point FM discriminator (sigs/nfm.m:123-127) fused in one overlap-save
+ * FFT-convolution kernel.
+ *   pysdr_fir_spectrum : d_taps_c64[L] complex64 (device) -> d_H, the filter's spectrum in the transform's position order
+ *                        with 1/N folded in (4096 complex64 for L <= 2047, else 8192).  For the video stage the taps are
+ *                        h[j] * e^{+j 2 pi f j / fs} (LO folded in, host float64).
+ *   pysdr_wfm_video_disc: d_x complex64[n_in]; d_hist complex64[L+1] = the raw samples preceding d_x (zeros at the stream
+ *                        origin), updated to the last L+1 samples of the call; d_prev2 complex64[2][2]: slot prev2_slot holds
+ *                        the last two video-filter outputs of the previous call (zeros at the origin), the new pair is written
+ *                        to the other slot (the caller toggles prev2_slot after every call with n_in > 0); acc0 = LO phase
+ *                        accumulator at d_x[0], inc per sample (pysdr_freq_to_phase_inc); d_fm complex64[n_in] receives (fm, 0). */
+int pysdr_fir_spectrum(const void *d_taps_c64, int L, void *d_H, void *stream);
+int pysdr_wfm_video_disc(const void *d_x, int64_t n_in, void *d_hist, void *d_prev2, int prev2_slot, const void *d_H, int L,
+                         uint64_t acc0, uint64_t inc, void *d_fm, void *stream);
 /* AF filter variant: default = overlap-save FFT convolution in shared memory; on != 0 forces the direct-form FIR. */
 int pysdr_bank_force_direct_fir(pysdr_bank *b, int on);
 /* On-stream stage timing for bench.py's roofline: out4 = {sum K1 ms, sum rest-of-front ms, sum back ms,

@@ -55,6 +55,9 @@ SIGNATURES = {
     "pysdr_bank_position": (c_i64, [c_vp]),
     "pysdr_bank_n_blocks": (c_i64, [c_vp, c_i64]),
     "pysdr_bank_process": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),
+    "pysdr_bank_process_host": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
+                                        ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_vp]),
+    "pysdr_bank_host_chunk_ptr": (c_int, [c_vp, ctypes.POINTER(c_vp)]),
     "pysdr_bank_process_front": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, ctypes.POINTER(c_i64), c_vp]),
     "pysdr_bank_process_back": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "pysdr_bank_seek": (c_int, [c_vp, c_i64, c_vp]),
@@ -66,7 +69,10 @@ SIGNATURES = {
     "pysdr_bank_k1_variant": (c_int, [c_vp]),
     "pysdr_bank_force_generic": (c_int, [c_vp, c_int]),
     "pysdr_bank_set_k1_only": (c_int, [c_vp, c_int]),
+    "pysdr_bank_set_real_input": (c_int, [c_vp, c_int]),
     "pysdr_fm_disc": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "pysdr_fir_spectrum": (c_int, [c_vp, c_int, c_vp, c_vp]),
+    "pysdr_wfm_video_disc": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_int, c_u64, c_u64, c_vp, c_vp]),
     "pysdr_bank_force_direct_fir": (c_int, [c_vp, c_int]),
     "pysdr_bank_adopt_c_memory": (c_int, [c_vp, c_vp, c_i64]),
     "pysdr_bank_set_k1_external": (c_int, [c_vp, c_int]),

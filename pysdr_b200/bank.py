@@ -299,37 +299,38 @@ class ReceiverBank:
             return self._iq[r, :n]
         return self._cmem[r, self._hc:self._hc + n]
 
-    def process_host(self, x_np, want_dc=True):
-        """Host buffers in, host buffers out (the reference-facing call): H2D, kernels, D2H."""
+    def process_host(self, x_np, want_dc=True, want_iq=True):
+        """Host buffers in, host buffers out (the reference-facing call): ONE C call does upload, kernels, download and the
+        synchronisation (pysdr_bank_process_host); the arrays returned are copies (a few KB per receiver), so they stay valid
+        as long as the caller keeps them."""
         if len(x_np) == 0:                                    # nothing in, nothing out (no state change)
             e = [np.zeros(0, np.complex64 if self._mode_of(r) in ('IQ', 'RTTY') else np.float32) for r in range(self.n_rx)]
             return e, [np.zeros(0, np.complex64) for _ in range(self.n_rx)], [v.copy() for v in e]
+        x_np = np.asarray(x_np)
+        if x_np.dtype != np.complex64 or not x_np.flags['C_CONTIGUOUS']:
+            x_np = np.ascontiguousarray(x_np, np.complex64)
         n = len(x_np)
         if n > self.max_in:
             raise PysdrError("chunk of %d samples exceeds max_in=%d" % (n, self.max_in))
-        if getattr(self, '_h_in', None) is None:              # pinned staging: one async H2D, one sync, async D2H rows
-            self._h_in = torch.empty(self.max_in, dtype=torch.complex64, pin_memory=True)
-            self._d_in = torch.empty(self.max_in, dtype=torch.complex64, device=self.device)
-            self._h_am = torch.empty((self.n_rx, 2 * self.max_out), dtype=torch.float32, pin_memory=True)
-            self._h_dc = torch.empty((self.n_rx, 2 * self.max_out), dtype=torch.float32, pin_memory=True)
-            self._h_iq = torch.empty((self.n_rx, self.max_out), dtype=torch.complex64, pin_memory=True)
-        np.copyto(self._h_in.numpy()[:n], np.asarray(x_np), casting='same_kind')
-        self._d_in[:n].copy_(self._h_in[:n], non_blocking=True)
-        self.process(self._d_in[:n], want_dc=want_dc)
-        no = self.n_out
+        self.sync_demod()
+        p_am, p_iq, p_dc = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        row, n_out = ctypes.c_int64(0), ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            check(self.lib.pysdr_bank_process_host(self.h, x_np.ctypes.data_as(ctypes.c_void_p), n, 1 if want_iq else 0,
+                                                   1 if want_dc else 0, ctypes.byref(p_am), ctypes.byref(p_iq), ctypes.byref(p_dc),
+                                                   ctypes.byref(row), ctypes.byref(n_out), _stream_ptr()))
+        no = self.n_out = n_out.value
+        if getattr(self, '_hp', None) != (p_am.value, row.value):           # wrap the bank's pinned result block once
+            nfl = row.value * self.n_rx
+            as_f32 = lambda p: np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_float)), shape=(nfl,)).reshape(self.n_rx, row.value)
+            self._h_am_np, self._h_iq_np, self._h_dc_np = as_f32(p_am), as_f32(p_iq), as_f32(p_dc)
+            self._hp = (p_am.value, row.value)
         cplx = [self._mode_of(r) in ('IQ', 'RTTY') for r in range(self.n_rx)]
-        for r in range(self.n_rx):
-            w = 2 * no if cplx[r] else no
-            self._h_am[r, :w].copy_(self._am[r, :w], non_blocking=True)
-            self._h_iq[r, :no].copy_(self.iq_row(r, no), non_blocking=True)
-            if want_dc:
-                self._h_dc[r, :w].copy_(self._am_dc[r, :w], non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
 
         def host(buf, r):
-            row = buf[r].numpy()
-            return row[:2 * no].view(np.complex64).copy() if cplx[r] else row[:no].copy()
-        am = [host(self._h_am, r) for r in range(self.n_rx)]
-        iq = [self._h_iq[r, :no].numpy().copy() for r in range(self.n_rx)]
-        dc = [host(self._h_dc, r) for r in range(self.n_rx)] if want_dc else [a.copy() for a in am]
+            return buf[r, :2 * no].view(np.complex64).copy() if cplx[r] else buf[r, :no].copy()
+        am = [host(self._h_am_np, r) for r in range(self.n_rx)]
+        iq = [self._h_iq_np[r, :2 * no].view(np.complex64).copy() for r in range(self.n_rx)] if want_iq else \
+            [np.zeros(0, np.complex64) for _ in range(self.n_rx)]
+        dc = [host(self._h_dc_np, r) for r in range(self.n_rx)] if want_dc else [a.copy() for a in am]
         return am, iq, dc

@@ -781,6 +781,7 @@ struct pysdr_bank {
     bool h_dirty[PYSDR_MAX_RX];             // AF taps changed: their position-order FFT must be refreshed
     bool force_direct_fir;                  // testing: use the direct-form AF FIR instead of the FFT path
     bool k1_only;                           // WFM video stage: stop after K1
+    bool real_input;                        // the caller promises Im x == 0 (pysdr_bank_set_real_input)
     bool k1_external;                       // the caller fills C[r][hc .. hc+n_out) itself (raster channelizer, wola.cu)
     bool c_external;                        // d_C was adopted from the caller (not freed here)
     float2 *d_H;                            // [n_rx][Nfft] FFT of AF taps (position order, 1/N folded in)
@@ -804,6 +805,10 @@ struct pysdr_bank {
     unsigned long long *d_bar;               // grid barrier counter of the fused back kernel (monotonic)
     unsigned long long bar_count;            // its value when the next launch starts
     int back_grid;
+    // host-chunk executive (pysdr_bank_process_host): pinned staging + own device buffers, allocated on first use
+    float2 *hc_h_in, *hc_d_in, *hc_d_iq;
+    float *hc_d_am, *hc_d_dc;
+    char *hc_h_out;                          // pinned: am [n_rx][2 max_out] f32 | iq [n_rx][max_out] c64 | am_dc [n_rx][2 max_out] f32
     // seek() folded into the next process_front / process_back (no launch of its own)
     bool lazy_seek, lazy_reset_agc;
     i64 launches;
@@ -893,7 +898,7 @@ extern "C" int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out)
     b->force_generic = false;
     b->force_direct_fir = false;
     b->k1_only = false;
-    b->k1_external = false; b->c_external = false;
+    b->k1_external = false; b->c_external = false; b->real_input = false;
     b->stereo = false; b->pilot_min = 0.f;
     b->timing = false;
     b->launches = 0;
@@ -901,6 +906,7 @@ extern "C" int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out)
     b->force_unfused = false; b->defer_peaks = false; b->peaks_deferred = false;
     b->bar_count = 0; b->back_grid = 0;
     b->lazy_seek = false; b->lazy_reset_agc = false;
+    b->hc_h_in = nullptr; b->hc_d_in = nullptr; b->hc_d_iq = nullptr; b->hc_d_am = nullptr; b->hc_d_dc = nullptr; b->hc_h_out = nullptr;
     for (int r = 0; r < PYSDR_MAX_RX; ++r) {
         b->inc[r] = 0; b->acc0[r] = 0; b->mode[r] = PYSDR_MODE_IQ; b->af_cplx[r] = 0; b->bfo_inc[r] = 0;
         b->demod_set[r] = false;
@@ -924,6 +930,9 @@ extern "C" int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out)
 extern "C" int pysdr_bank_destroy(pysdr_bank *b) {
     if (!b) return PYSDR_OK;
     cudaFree(b->d_H);
+    if (b->hc_h_in) cudaFreeHost(b->hc_h_in);
+    if (b->hc_h_out) cudaFreeHost(b->hc_h_out);
+    cudaFree(b->hc_d_in); cudaFree(b->hc_d_iq); cudaFree(b->hc_d_am); cudaFree(b->hc_d_dc);
     if (!b->c_external) cudaFree(b->d_C);
     cudaFree(b->d_hist); cudaFree(b->d_g); cudaFree(b->d_af); cudaFree(b->d_R);
     cudaFree(b->d_a); cudaFree(b->d_peaks); cudaFree(b->d_gains); cudaFree(b->d_agc); cudaFree(b->d_pll); cudaFree(b->d_bar);
@@ -1091,6 +1100,12 @@ extern "C" int pysdr_bank_adopt_c_memory(pysdr_bank *b, void *d_ptr, int64_t row
 extern "C" int pysdr_bank_set_k1_external(pysdr_bank *b, int on) {
     if (!b) { pysdr_set_error("null bank"); return PYSDR_ERR_ARG; }
     b->k1_external = on != 0;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_set_real_input(pysdr_bank *b, int on) {
+    if (!b) return PYSDR_ERR_ARG;
+    b->real_input = on != 0;
     return PYSDR_OK;
 }
 
@@ -1332,6 +1347,7 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
     a.x = (const float2 *)d_iq;
     a.hist = halo_in_place ? a.x - b->need : (fold_seek ? nullptr : b->d_hist);
     a.zero_c_hist = fold_seek ? 1 : 0;
+    a.real_input = b->real_input ? 1 : 0;
     a.need = b->need;
     a.n0 = b->n0; a.n_in = n_in; a.m0 = m0; a.n_out = n_out;
     a.up = c.up; a.down = c.down; a.lp = b->lp; a.lp_pad = b->lp_pad; a.n_rx = c.n_rx;
@@ -1704,6 +1720,73 @@ extern "C" int pysdr_bank_process(pysdr_bank *b, const void *d_iq, int64_t n_in,
     b->defer_peaks = false;
     if (rc) return rc;
     return pysdr_bank_process_back(b, nullptr, 0, 0, d_am, d_am_dc, out_stride, stream);
+}
+
+// ---- host-chunk executive -------------------------------------------------------------------------------------------------
+// The call the reference's loop makes per chunk (receiver.py:724-725 -> demodulate_data -> rx.demod_data(x)): a HOST
+// chunk in, HOST results out, for every receiver of the bank at once.  Everything between the two host buffers happens in
+// this one C call on `stream`: upload (directly from the caller's buffer when it is page-locked, else through a pinned
+// staging copy), the three step kernels, the result rows downloaded into ONE pinned block, one synchronisation.
+// r01 did this from Python with ~14 tensor operations per chunk (0.33 ms per 21 ms chunk for 4 receivers).
+extern "C" int pysdr_bank_process_host(pysdr_bank *b, const void *h_iq, int64_t n_in, int want_iq, int want_dc, float **h_am,
+                                       void **h_iq_bb, float **h_am_dc, int64_t *row_floats, int64_t *n_out_p, void *stream) {
+    if (!b || !h_iq || n_in < 1 || !h_am || !row_floats || !n_out_p) { pysdr_set_error("process_host: bad arguments"); return PYSDR_ERR_ARG; }
+    const pysdr_bank_config &c = b->cfg;
+    if (n_in > c.max_in) { pysdr_set_error("process_host: n_in=%lld exceeds max_in=%lld", (i64)n_in, (i64)c.max_in); return PYSDR_ERR_CAPACITY; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t row = 2 * (size_t)b->max_out;                                  // floats per result row
+    const size_t am_bytes = sizeof(float) * row * c.n_rx;
+    if (!b->hc_h_in) {
+        CUDA_TRY(cudaHostAlloc(&b->hc_h_in, sizeof(float2) * (size_t)c.max_in, cudaHostAllocDefault));
+        CUDA_TRY(cudaHostAlloc(&b->hc_h_out, 3 * am_bytes, cudaHostAllocDefault));
+        CUDA_TRY(cudaMalloc(&b->hc_d_in, sizeof(float2) * (size_t)c.max_in));
+        CUDA_TRY(cudaMalloc(&b->hc_d_am, am_bytes));
+        CUDA_TRY(cudaMalloc(&b->hc_d_dc, am_bytes));
+        CUDA_TRY(cudaMalloc(&b->hc_d_iq, am_bytes));
+    }
+    const void *src = h_iq;
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, h_iq) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
+        cudaGetLastError();                                                      // pageable memory: stage through the pinned block
+        memcpy(b->hc_h_in, h_iq, sizeof(float2) * (size_t)n_in);
+        src = b->hc_h_in;
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->hc_d_in, src, sizeof(float2) * (size_t)n_in, cudaMemcpyHostToDevice, st));
+    bool any_sync = false;
+    for (int r = 0; r < c.n_rx; ++r) any_sync = any_sync || b->mode[r] == PYSDR_MODE_AMSYNC;
+    int64_t n_out = 0;
+    int rc = pysdr_bank_process(b, b->hc_d_in, n_in, 0, any_sync ? (void *)b->hc_d_iq : nullptr, b->hc_d_am, want_dc ? b->hc_d_dc : nullptr,
+                                (int64_t)b->max_out, &n_out, stream);
+    if (rc) return rc;
+    float *o_am = (float *)b->hc_h_out, *o_dc = (float *)(b->hc_h_out + 2 * am_bytes);
+    float2 *o_iq = (float2 *)(b->hc_h_out + am_bytes);
+    if (n_out > 0) {
+        const size_t w = sizeof(float) * 2 * (size_t)n_out;                      // complex rows use all of it, real rows the first half
+        CUDA_TRY(cudaMemcpy2DAsync(o_am, sizeof(float) * row, b->hc_d_am, sizeof(float) * row, w, c.n_rx, cudaMemcpyDeviceToHost, st));
+        if (want_dc)
+            CUDA_TRY(cudaMemcpy2DAsync(o_dc, sizeof(float) * row, b->hc_d_dc, sizeof(float) * row, w, c.n_rx, cudaMemcpyDeviceToHost, st));
+        if (want_iq) {
+            if (any_sync)
+                CUDA_TRY(cudaMemcpy2DAsync(o_iq, sizeof(float) * row, b->hc_d_iq, sizeof(float2) * (size_t)b->max_out, w, c.n_rx,
+                                           cudaMemcpyDeviceToHost, st));
+            else
+                CUDA_TRY(cudaMemcpy2DAsync(o_iq, sizeof(float) * row, b->d_C + b->hc, sizeof(float2) * (size_t)b->c_stride, w, c.n_rx,
+                                           cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *h_am = o_am;
+    if (h_iq_bb) *h_iq_bb = o_iq;
+    if (h_am_dc) *h_am_dc = o_dc;
+    *row_floats = (int64_t)row;
+    *n_out_p = n_out;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_host_chunk_ptr(pysdr_bank *b, void **d_in) {
+    if (!b || !d_in || !b->hc_d_in) { pysdr_set_error("host_chunk_ptr: no host chunk has been processed yet"); return PYSDR_ERR_STATE; }
+    *d_in = b->hc_d_in;
+    return PYSDR_OK;
 }
 
 // A pending seek() is materialised either inside the next process call (K1 clears the carried complex memory and reads a

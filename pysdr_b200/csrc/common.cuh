@@ -81,6 +81,7 @@ struct AgcState {
 struct K1Args {
     const float2 *x;          // chunk, n_in samples (absolute index n0..)
     const float2 *hist;       // `need` samples preceding x (absolute n0-need..n0-1); NULL = all zero (stream start / after seek)
+    int real_input;           // != 0: Im x == 0 for every sample (caller's promise): K1 skips the Im-x half of the FMAs
     int zero_c_hist;          // != 0: also clear the carried part C[rx][0..hc) of every complex memory row (seek folded into K1)
     int need;                 // lp-1
     i64 n0, n_in, m0, n_out;

@@ -18,6 +18,7 @@
 // Spectra are only ever touched in the transforms' "position" order (host code permutes the chirp spectrum once), so
 // there is no reordering pass.  host side: pysdr_b200/sig_proc.py (class spectrum), tables from numpy in float64.
 #include "common.cuh"
+#define FFT_PACKED 0                     /* see fft_smem.cuh: this kernel sits at its register limit */
 #include "fft_smem.cuh"
 
 #define CZT_N1 512

@@ -69,7 +69,9 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar) {
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int NRXP, int TPL>
+// REAL: the input samples are real (imaginary parts identically zero, e.g. the FM discriminator output that feeds the
+// WFM resampler rows): the FFMA2 stream that multiplies the taps by Im x is skipped — half the FMAs.
+template <int NRXP, int TPL, bool REAL = false>
 __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a, const FastGeom g) {
     constexpr int RB = Bits<NRXP>::RB;
     constexpr int SB = Bits<NRXP>::SB;
@@ -294,10 +296,12 @@ __global__ void __launch_bounds__(K1F_THREADS, 1) k1_fast_kernel(const K1Args a,
                             const int slot = (stop << 2) | (r << (2 - RB)) | sl;
                             A[slot] = __ffma2_rn(tap[r][k], xrr, A[slot]);
                         }
+                        if constexpr (!REAL) {
 #pragma unroll
-                        for (int r = 0; r < NRXP; ++r) {
-                            const int slot = (stop << 2) | (r << (2 - RB)) | sl;
-                            B[slot] = __ffma2_rn(tap[r][k], xii, B[slot]);
+                            for (int r = 0; r < NRXP; ++r) {
+                                const int slot = (stop << 2) | (r << (2 - RB)) | sl;
+                                B[slot] = __ffma2_rn(tap[r][k], xii, B[slot]);
+                            }
                         }
                     }
                 }
@@ -398,16 +402,19 @@ int k1_fast_supported(int up, int down, int lp, int n_rx) {
     return 1;
 }
 
-template <int NRXP, int TPL>
+template <int NRXP, int TPL, bool REAL = false>
 static int launch_one(const K1Args &a, const FastGeom &g, int grid, cudaStream_t st) {
+    if constexpr (!REAL && NRXP == 1) {
+        if (a.real_input) return launch_one<NRXP, TPL, true>(a, g, grid, st);
+    }
     const size_t smem = 64 + sizeof(float2) * (size_t)K1F_STAGES * K1F_STAGE_ELEMS;
     static unsigned long long attr_done = 0ull;          // one bit per device: the attribute is per (function, device)
     const unsigned long long dev_bit = 1ull << (pysdr_device() & 63);
     if (!(attr_done & dev_bit)) {
-        CUDA_TRY(cudaFuncSetAttribute(k1_fast_kernel<NRXP, TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k1_fast_kernel<NRXP, TPL, REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done |= dev_bit;
     }
-    CUDA_TRY(launch_pdl(k1_fast_kernel<NRXP, TPL>, dim3(grid), dim3(K1F_THREADS), smem, st, a, g));
+    CUDA_TRY(launch_pdl(k1_fast_kernel<NRXP, TPL, REAL>, dim3(grid), dim3(K1F_THREADS), smem, st, a, g));
     return PYSDR_OK;
 }
 

@@ -274,3 +274,139 @@ int fftconv_launch(const FftConvArgs &a, int n_rx, cudaStream_t st) {
     pysdr_set_error("fftconv: unsupported AF filter length %d", a.L);
     return PYSDR_ERR_ARG;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// WFM video stage at the RF rate: LO + 1001-tap video FIR + FM discriminator in ONE kernel ("BCB FM is wideband so we need
+// to demodulate first before resampling", reference gui.py:1703,1759-1762).  r01 ran the FIR in direct form through K1
+// (8 008 flop per input sample, 31 TFLOP/s, 0.45 % of the HBM roofline); here it is an overlap-save fast convolution on
+// the same shared-memory FFT as the AF filter:
+//     y[n]  = e^{-j th(n)} * sum_j G[j] x[n-j],   G[j] = h[j] e^{+j w j}   (LO folded into the taps, like K1)
+//     fm[n] = Re y[n-1] * Im d - Im y[n-1] * Re d,  d = y[n] - y[n-2]      (reference sigs/nfm.m:123-127)
+// A CTA transforms N raw samples and emits S = N - (L-1) - 2 discriminator outputs: the two extra outputs of overlap
+// make y[n-1], y[n-2] available in the block.  Carried state: the last L+1 RAW samples, and the last two y of the previous
+// call (prev2) for the first two outputs — they are NOT recomputed from the raw memory, because after a retune the memory
+// is seen through the new LO while y[-1], y[-2] were produced with the old one (what the reference's chunk-wise chain
+// does).  prev2 is double buffered (slot `par` is read, slot par^1 written by the CTA that owns the last sample).
+// Output is complex64 (fm, 0): the resampler bank reads complex.
+struct WfmVidArgs {
+    const float2 *x;          // n_in new samples
+    const float2 *hist;       // L+1 samples preceding x
+    const float2 *H;          // spectrum of G in position order, 1/N folded in
+    float2 *fm;               // [n_in]
+    float2 *prev2;            // [2][2]: y[-2], y[-1] of the previous call in slot par; the new pair goes to slot par ^ 1
+    int par;
+    i64 n_in;
+    int L;
+    u64 acc0, inc;            // LO phase at x[0], per-sample increment
+};
+
+template <int N>
+__global__ void __launch_bounds__(FftPlan<N>::THREADS, (N == 4096 ? 3 : 1)) wfm_video_disc_kernel(const WfmVidArgs a) {
+    extern __shared__ __align__(16) float2 s[];
+    constexpr int T = FftPlan<N>::THREADS;
+    constexpr int PER = N / T;
+    const int tid = threadIdx.x;
+    const int L = a.L, Hn = L + 1;
+    const int S = N - (L - 1) - 2;
+    const i64 g0 = (i64)blockIdx.x * S - Hn;                               // index (rel. x[0]) of this block's first sample
+    pdl_trigger();
+    pdl_wait();
+    {
+        float2 v[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const i64 g = g0 + tid + i * T;
+            v[i] = g < 0 ? a.hist[g + Hn] : (g < a.n_in ? a.x[g] : make_float2(0.f, 0.f));
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) s[FFT_PAD(tid + i * T)] = v[i];
+    }
+    __syncthreads();
+    fft_smem<N, false>(s, tid);
+    {
+        float2 h[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) h[i] = __ldg(a.H + tid + i * T);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int p = tid + i * T;
+            s[FFT_PAD(p)] = cmul(s[FFT_PAD(p)], h[i]);
+        }
+    }
+    __syncthreads();
+    fft_smem<N, true>(s, tid);
+    // de-rotate the valid outputs (positions L-1 .. N-1) by the exact LO phase of their sample
+    for (int j = L - 1 + tid; j < N; j += T) {
+        const float2 cs = nco_cs(a.acc0 + a.inc * (u64)(g0 + j));
+        const float2 z = s[FFT_PAD(j)];
+        s[FFT_PAD(j)] = make_float2(z.x * cs.x + z.y * cs.y, z.y * cs.x - z.x * cs.y);
+    }
+    __syncthreads();
+    const float2 *pin = a.prev2 + 2 * a.par;
+    for (int j = L + 1 + tid; j < N; j += T) {
+        const i64 n = g0 + j;
+        if (n >= a.n_in) break;
+        const float2 c2 = s[FFT_PAD(j)];
+        const float2 c1 = n >= 1 ? s[FFT_PAD(j - 1)] : pin[1];
+        const float2 c0 = n >= 2 ? s[FFT_PAD(j - 2)] : pin[n];             // n = 0 -> y[-2], n = 1 -> y[-1]
+        const float dr = c2.x - c0.x, di = c2.y - c0.y;
+        a.fm[n] = make_float2(c1.x * di - c1.y * dr, 0.f);
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) {                         // this CTA owns the last sample of the call
+        const int jl = (int)(a.n_in - 1 - g0);
+        float2 *pout = a.prev2 + 2 * (a.par ^ 1);
+        pout[1] = s[FFT_PAD(jl)];
+        pout[0] = a.n_in >= 2 ? s[FFT_PAD(jl - 1)] : pin[1];
+    }
+}
+
+// dst[0..n_keep) <- the last n_keep samples of [hist | x]
+__global__ void wfm_hist_kernel(float2 *hist, const float2 *__restrict__ x, int n_keep, i64 n_in) {
+    float2 tmp[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int e = threadIdx.x + k * 1024;
+        if (e < n_keep) {
+            const i64 idx = n_in - n_keep + e;
+            tmp[k] = idx >= 0 ? x[idx] : hist[n_keep + idx];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int e = threadIdx.x + k * 1024;
+        if (e < n_keep) hist[e] = tmp[k];
+    }
+}
+
+extern "C" int pysdr_fir_spectrum(const void *d_taps_c64, int L, void *d_H, void *stream) {
+    if (!d_taps_c64 || !d_H || !fftconv_supported(L)) { pysdr_set_error("fir_spectrum: unsupported filter length %d", L); return PYSDR_ERR_ARG; }
+    return fftconv_prepare_taps((const float2 *)d_taps_c64, L, (float2 *)d_H, (cudaStream_t)stream);
+}
+
+extern "C" int pysdr_wfm_video_disc(const void *d_x, int64_t n_in, void *d_hist, void *d_prev2, int prev2_slot, const void *d_H,
+                                    int L, uint64_t acc0, uint64_t inc, void *d_fm, void *stream) {
+    if (!d_x || !d_hist || !d_prev2 || !d_H || !d_fm || n_in < 0 || L < 2 || (prev2_slot & ~1)) { pysdr_set_error("wfm_video_disc: bad arguments"); return PYSDR_ERR_ARG; }
+    if (n_in == 0) return PYSDR_OK;
+    const int N = fftconv_n_for(L + 2);
+    if (N == 0 || L + 1 > 8192) { pysdr_set_error("wfm_video_disc: video filter length %d unsupported", L); return PYSDR_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    WfmVidArgs a;
+    a.x = (const float2 *)d_x; a.hist = (const float2 *)d_hist; a.H = (const float2 *)d_H; a.fm = (float2 *)d_fm;
+    a.n_in = n_in; a.L = L; a.acc0 = acc0; a.inc = inc;
+    a.prev2 = (float2 *)d_prev2; a.par = prev2_slot;
+    if (fftconv_n_for(L) != N) { pysdr_set_error("wfm_video_disc: video filter length %d unsupported", L); return PYSDR_ERR_ARG; }
+    const int S = N - (L - 1) - 2;
+    const unsigned grid = (unsigned)((n_in + S - 1) / S);
+    const size_t smem = sizeof(float2) * FFT_SMEM_ELEMS(N);
+    if (N == 4096) {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(wfm_video_disc_kernel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(launch_pdl(wfm_video_disc_kernel<4096>, dim3(grid), dim3(FftPlan<4096>::THREADS), smem, st, a));
+    } else {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(wfm_video_disc_kernel<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(launch_pdl(wfm_video_disc_kernel<8192>, dim3(grid), dim3(FftPlan<8192>::THREADS), smem, st, a));
+    }
+    wfm_hist_kernel<<<1, 1024, 0, st>>>((float2 *)d_hist, (const float2 *)d_x, L + 1, n_in);
+    LAUNCH_CHECK();
+    return PYSDR_OK;
+}

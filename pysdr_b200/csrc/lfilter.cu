@@ -7,14 +7,20 @@
 //     y[n]   = b0 x[n] + z0[n-1]
 //     z_i[n] = b_{i+1} x[n] + z_{i+1}[n-1] - a_{i+1} y[n]          (z_K = 0)
 // The recursion is linear in (z, x), so a sequence of B samples maps z -> Phi^B z + s, with s the state
-// reached from z = 0.  Three passes:
-//   P1  every block (B samples) runs the recursion from zero state, keeps s_b           (parallel)
-//   P2  one warp per channel chains z_{b+1} = Phi^B z_b + s_b over the blocks           (serial, tiny)
-//   P3  every block re-runs the recursion from its true entry state and writes y        (parallel)
-// Phi^B is formed on the host in float64 by repeated squaring of the KxK companion matrix.
+// reached from z = 0.  A hierarchical scan (float64 throughout):
+//   P1   every block of B = 32 samples runs the recursion from zero state, keeps s_b                     (parallel)
+//   UP   groups of 32 units chain z <- Phi^unit z + s_u from zero state, keep the group's s; repeated with Phi^(32 unit)
+//        until at most 32 units are left                                                                  (parallel per level)
+//   TOP  one warp per channel chains the remaining units from the carried state zi                        (<= 32 steps)
+//   DOWN every group re-chains its units from its true entry state, level by level, down to the blocks    (parallel per level)
+//   P3   every block re-runs the recursion from its true entry state and writes y                         (parallel)
+// (r01 chained all 512-sample blocks serially in one warp and gave every thread 512 dependent float64 steps: 242 us for a
+// one-pole filter over 10 s of 48 kHz audio; the de-emphasis of the stereo FM decoder spent more time there than the RF-rate
+// stages.)  Phi^32 is formed on the host by running the recursion from the unit states, the higher powers by squaring.
 #include "common.cuh"
 
-#define LF_B 512            /* samples per scan block */
+#define LF_B 32             /* samples per scan block */
+#define LF_G 32             /* units per group in the up / down passes */
 #define LF_ROWS 32          /* blocks handled per CTA (one per thread) */
 
 // One DF2T step in scipy's own operation order without FMA contraction (scipy/signal/_lfilter.c.in:
@@ -81,21 +87,28 @@ lf_block_kernel(LfCoef<K> c, const float *__restrict__ x, float *__restrict__ y,
     }
 }
 
-// P2: z_entry[b+1] = PhiB z_entry[b] + s[b]; lane i owns row i.  The last partial block is handled by P3
-// itself for y, and for the carried state by stepping the tail exactly (host passes n_tail) via phi_tail.
+// Chain over units: grid (n_groups, n_ch), one warp each.  Group g covers units [g*gsz, min((g+1)*gsz, n_units)).
+//   z <- phi z + s[u]  from  z = z_in[g] (or 0);  z_entry[u] (optional) = state ENTERING unit u;  s_out[g] (optional) =
+//   state leaving the group.  Lane i owns row i of phi (K <= 32).
 template <int K>
-__global__ void lf_chain_kernel(const double *__restrict__ phiB /* [K][K] */, const double *__restrict__ s /* [n_ch][nblk][K] */,
-                                double *__restrict__ z_entry /* [n_ch][nblk][K] */, double *__restrict__ zi /* [n_ch][K] in: entry of block 0 */,
-                                i64 nblk) {
-    const int ch = blockIdx.x;
+__global__ void __launch_bounds__(32)
+lf_chain_kernel(const double *__restrict__ phi /* [K][K] */, const double *__restrict__ s /* [n_ch][n_units][K] */, i64 n_units,
+                i64 gsz, const double *__restrict__ z_in /* [n_ch][n_groups][K] or null */, i64 z_in_stride,
+                double *__restrict__ z_entry /* [n_ch][n_units][K] or null */, double *__restrict__ s_out /* [n_ch][n_groups][K] or null */) {
+    const int ch = blockIdx.y;
+    const i64 g = blockIdx.x, n_groups = gridDim.x;
     const int lane = threadIdx.x;
     double row[K];
 #pragma unroll
-    for (int j = 0; j < K; ++j) row[j] = (lane < K) ? phiB[lane * K + j] : 0.0;
-    double zl = (lane < K) ? zi[(size_t)ch * K + lane] : 0.0;
-    for (i64 b = 0; b < nblk; ++b) {
-        if (lane < K) z_entry[((size_t)ch * nblk + b) * K + lane] = zl;
-        double acc = (lane < K) ? s[((size_t)ch * nblk + b) * K + lane] : 0.0;
+    for (int j = 0; j < K; ++j) row[j] = (lane < K) ? phi[lane * K + j] : 0.0;
+    double zl = (z_in && lane < K) ? z_in[((size_t)ch * z_in_stride + g) * K + lane] : 0.0;
+    const i64 u0 = g * gsz, u1 = (u0 + gsz < n_units) ? u0 + gsz : n_units;
+    const double *sp = s + ((size_t)ch * n_units + u0) * K;
+    double nxt = (lane < K && u0 < u1) ? sp[lane] : 0.0;                 // one unit of look-ahead on the s loads
+    for (i64 u = u0; u < u1; ++u) {
+        if (z_entry && lane < K) z_entry[((size_t)ch * n_units + u) * K + lane] = zl;
+        double acc = nxt;
+        if (lane < K && u + 1 < u1) nxt = sp[(u + 1 - u0) * K + lane];
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const double zj = __shfl_sync(0xffffffffu, zl, j);
@@ -103,8 +116,7 @@ __global__ void lf_chain_kernel(const double *__restrict__ phiB /* [K][K] */, co
         }
         zl = acc;
     }
-    // zl is now the state after nblk FULL blocks; only meaningful when n is a multiple of LF_B (see host)
-    if (lane < K) zi[(size_t)ch * K + lane] = zl;
+    if (s_out && lane < K) s_out[((size_t)ch * n_groups + g) * K + lane] = zl;
 }
 
 // exact tail: final carried state when n is not a multiple of LF_B (one thread per channel re-runs the
@@ -171,23 +183,74 @@ static int lfilter_run(const double *bn, const double *an, const float *d_x, flo
         return PYSDR_OK;
     }
 
-    double *d_ws = nullptr;      // [phiB K*K][s n_ch*nblk*K][z_entry n_ch*nblk*K]
-    const size_t per = (size_t)n_ch * nblk * K;
-    CUDA_TRY(cudaMallocAsync(&d_ws, sizeof(double) * ((size_t)K * K + 2 * per), st));
-    double *d_phi = d_ws, *d_s = d_ws + (size_t)K * K, *d_ze = d_s + per;
-    CUDA_TRY(cudaMemcpyAsync(d_phi, phiB.data(), sizeof(double) * K * K, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));          // phiB is host-stack owned
+    // levels: level 0 = blocks; level l+1 = groups of LF_G level-l units, until <= LF_G units remain
+    std::vector<i64> cnt;
+    cnt.push_back(nblk);
+    while (cnt.back() > LF_G) cnt.push_back((cnt.back() + LF_G - 1) / LF_G);
+    const int n_lev = (int)cnt.size();
+    // transition matrices per level: phi[0] = Phi^B, phi[l+1] = phi[l]^LF_G (5 squarings, long double)
+    std::vector<double> phis((size_t)n_lev * K * K);
+    {
+        std::vector<long double> m((size_t)K * K), t((size_t)K * K);
+        for (size_t i = 0; i < (size_t)K * K; ++i) { m[i] = phiB[i]; phis[i] = phiB[i]; }
+        for (int l = 1; l < n_lev; ++l) {
+            for (int sq = 0; sq < 5; ++sq) {                              // LF_G = 32 = 2^5
+                for (int i = 0; i < K; ++i)
+                    for (int j = 0; j < K; ++j) {
+                        long double acc = 0.0L;
+                        for (int k = 0; k < K; ++k) acc += m[(size_t)i * K + k] * m[(size_t)k * K + j];
+                        t[(size_t)i * K + j] = acc;
+                    }
+                m.swap(t);
+            }
+            for (size_t i = 0; i < (size_t)K * K; ++i) {
+                phis[(size_t)l * K * K + i] = (double)m[i];
+                if (!(fabs((double)m[i]) <= 1.0e3)) {                     // growing powers: fall back to the sequential form
+                    lf_seq_kernel<K><<<n_ch, 1, 0, st>>>(c, d_x, d_y, n, stride, d_zi);
+                    LAUNCH_CHECK();
+                    return PYSDR_OK;
+                }
+            }
+        }
+    }
+    static_assert(LF_G == 32, "the level matrices are formed by five squarings");
+    // workspace: [phis][per level: s (n_ch * cnt[l] * K) and z_entry (same)]
+    size_t tot = (size_t)n_lev * K * K;
+    std::vector<size_t> off_s(n_lev), off_z(n_lev);
+    for (int l = 0; l < n_lev; ++l) {
+        off_s[l] = tot; tot += (size_t)n_ch * cnt[l] * K;
+        off_z[l] = tot; tot += (size_t)n_ch * cnt[l] * K;
+    }
+    double *d_ws = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_ws, sizeof(double) * tot, st));
+    CUDA_TRY(cudaMemcpyAsync(d_ws, phis.data(), sizeof(double) * phis.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));          // phis is host-stack owned
     dim3 grid((unsigned)((nblk + LF_ROWS - 1) / LF_ROWS), (unsigned)n_ch);
-    lf_block_kernel<K, false><<<grid, LF_ROWS, 0, st>>>(c, d_x, nullptr, n, stride, nullptr, d_s, nblk);
+    lf_block_kernel<K, false><<<grid, LF_ROWS, 0, st>>>(c, d_x, nullptr, n, stride, nullptr, d_ws + off_s[0], nblk);
     LAUNCH_CHECK();
-    lf_chain_kernel<K><<<n_ch, 32, 0, st>>>(d_phi, d_s, d_ze, d_zi, nblk);
-    LAUNCH_CHECK();
-    lf_block_kernel<K, true><<<grid, LF_ROWS, 0, st>>>(c, d_x, d_y, n, stride, d_ze, nullptr, nblk);
-    LAUNCH_CHECK();
-    if (n % LF_B != 0) {
-        lf_tail_kernel<K><<<n_ch, 1, 0, st>>>(c, d_x, n, stride, d_ze, d_zi, nblk);
+    for (int l = 0; l + 1 < n_lev; ++l) {         // UP: zero-state exit of every group of level-l units
+        dim3 g((unsigned)cnt[l + 1], (unsigned)n_ch);
+        lf_chain_kernel<K><<<g, 32, 0, st>>>(d_ws + (size_t)l * K * K, d_ws + off_s[l], cnt[l], LF_G, nullptr, 0, nullptr,
+                                              d_ws + off_s[l + 1]);
         LAUNCH_CHECK();
     }
+    {                                              // TOP: the <= LF_G remaining units from the carried state
+        const int l = n_lev - 1;
+        dim3 g(1, (unsigned)n_ch);
+        lf_chain_kernel<K><<<g, 32, 0, st>>>(d_ws + (size_t)l * K * K, d_ws + off_s[l], cnt[l], cnt[l], d_zi, 1, d_ws + off_z[l], nullptr);
+        LAUNCH_CHECK();
+    }
+    for (int l = n_lev - 2; l >= 0; --l) {         // DOWN: entry states of the level-l units from their group's entry state
+        dim3 g((unsigned)cnt[l + 1], (unsigned)n_ch);
+        lf_chain_kernel<K><<<g, 32, 0, st>>>(d_ws + (size_t)l * K * K, d_ws + off_s[l], cnt[l], LF_G, d_ws + off_z[l + 1], cnt[l + 1],
+                                              d_ws + off_z[l], nullptr);
+        LAUNCH_CHECK();
+    }
+    lf_block_kernel<K, true><<<grid, LF_ROWS, 0, st>>>(c, d_x, d_y, n, stride, d_ws + off_z[0], nullptr, nblk);
+    LAUNCH_CHECK();
+    // carried state after all n samples: the last block re-run from its entry state (exact also for a partial block)
+    lf_tail_kernel<K><<<n_ch, 1, 0, st>>>(c, d_x, n, stride, d_ws + off_z[0], d_zi, nblk);
+    LAUNCH_CHECK();
     CUDA_TRY(cudaFreeAsync(d_ws, st));
     return PYSDR_OK;
 }

@@ -8,6 +8,7 @@
 // and accumulates |X|^2 in registers in POSITION order; only the final line is permuted to bins and
 // fftshifted.  cuFFT is not used anywhere (tests cross-check against numpy).
 #include "common.cuh"
+#define FFT_PACKED 0                     /* see fft_smem.cuh: this kernel sits at its register limit */
 #include "fft_smem.cuh"
 
 struct pysdr_psd {

@@ -216,7 +216,9 @@ class SDR_EXECUTIVE:
         if self._pw is None:
             b = self.bank
             n = len(x)
-            check(b.lib.pysdr_mean_power(ctypes.c_void_p(b._d_in.data_ptr()), n, ctypes.c_void_p(b.scratch1().data_ptr()),
+            d_in = ctypes.c_void_p()
+            check(b.lib.pysdr_bank_host_chunk_ptr(b.h, ctypes.byref(d_in)))
+            check(b.lib.pysdr_mean_power(d_in, n, ctypes.c_void_p(b.scratch1().data_ptr()),
                                          ctypes.c_void_p(torch.cuda.current_stream(b.device).cuda_stream)))
             self._pw = float(b.scratch1().item())
         return self._pw

@@ -67,7 +67,7 @@ class _Lo:
 
     def change_freq(self, f):
         if self._rx._wfm is not None:
-            self._rx._wfm.vbank.set_freq(0, f)
+            self._rx._wfm.set_freq(f)
         return self._rx._bank.set_freq(self._rx._slot, f)
 
 
@@ -508,20 +508,53 @@ class _WfmChain:
         self.rx = rx
         self.stereo = bool(stereo)
         self.lib = _lib.load()
-        vid = _NS()
-        vid.SRATE, vid.UP, vid.DOWN, vid.FS_OUT = P.SRATE, 1, 1, int(P.SRATE)
-        vid.IN_CHUNK_SIZE, vid.FILT_LEN, vid.VIDEO_BW = P.IN_CHUNK_SIZE, P.FILT_LEN, P.VIDEO_BW
-        vid.MODE, vid.AF_BW, vid.AF_FILTER_NUM, vid.BFO, vid.VIDEO_FILTER_NUM = 'RAW', 0, 0, 0, None
         # P.WFM_MAX_CHUNKS (default 1 = the reference's chunk-at-a-time calls) lets a resident capture go through in one call
         self.max_in = int(P.IN_CHUNK_SIZE) * max(1, int(getattr(P, 'WFM_MAX_CHUNKS', 1)))
-        self.vbank = ReceiverBank(vid, [rx._bank.fo[0]], max_in=self.max_in)
-        check(self.lib.pysdr_bank_set_k1_only(self.vbank.h, 1))
         self.filter_bank = design.wfm_video_bank(P.SRATE, P.FILT_LEN, design.VIDEO_BWs, P.VIDEO_BW)
+        dev = rx._bank.device
+        self.L = int(P.FILT_LEN)
+        # video stage: LO + FIR + discriminator as ONE overlap-save FFT-convolution kernel (pysdr_wfm_video_disc); filters too
+        # long for the 4096-point transform keep the r01 route (direct-form FIR through a K1-only bank, then pysdr_fm_disc)
+        self.fast_video = 2 <= self.L <= 2045 and not getattr(P, 'WFM_DIRECT_VIDEO', False)
+        self.vbank = None
+        if self.fast_video:
+            self.inc = design.freq_to_phase_inc(rx._bank.fo[0], P.SRATE)
+            self.acc = 0
+            self.vhist = torch.zeros(self.L + 1, dtype=torch.complex64, device=dev)
+            self.vprev2 = torch.zeros((2, 2), dtype=torch.complex64, device=dev)
+            self.vslot = 0
+            self.vH = torch.empty(4096, dtype=torch.complex64, device=dev)
+            self._vdirty = True
+        else:
+            vid = _NS()
+            vid.SRATE, vid.UP, vid.DOWN, vid.FS_OUT = P.SRATE, 1, 1, int(P.SRATE)
+            vid.IN_CHUNK_SIZE, vid.FILT_LEN, vid.VIDEO_BW = P.IN_CHUNK_SIZE, P.FILT_LEN, P.VIDEO_BW
+            vid.MODE, vid.AF_BW, vid.AF_FILTER_NUM, vid.BFO, vid.VIDEO_FILTER_NUM = 'RAW', 0, 0, 0, None
+            self.vbank = ReceiverBank(vid, [rx._bank.fo[0]], max_in=self.max_in)
+            check(self.lib.pysdr_bank_set_k1_only(self.vbank.h, 1))
+            self.prev2 = torch.zeros(2, dtype=torch.complex64, device=dev)
         self.set_video(self.filter_bank[design.video_index(P)])
-        dev = self.vbank.device
-        self.prev2 = torch.zeros(2, dtype=torch.complex64, device=dev)
         self.fm = torch.empty(self.max_in, dtype=torch.complex64, device=dev)
         self.stage2(stereo)
+
+    def set_freq(self, f):
+        """rx.lo.change_freq(f) for the video stage (phase continuous at the current sample)."""
+        if self.vbank is not None:
+            return self.vbank.set_freq(0, f)
+        self.inc = design.freq_to_phase_inc(f, self.rx.P.SRATE)
+        self._vdirty = True
+        return design.phase_inc_to_freq(self.inc, self.rx.P.SRATE)
+
+    def _refresh_video_spectrum(self):
+        """G[j] = h[j] e^{+j 2 pi frac(inc j / 2^64)} (the LO folded into the taps in float64, as K1 does) -> spectrum."""
+        j = np.arange(len(self.h), dtype=np.uint64)
+        with np.errstate(over='ignore'):
+            ph = (np.uint64(self.inc) * j).view(np.int64).astype(np.float64) / 18446744073709551616.0
+        g = (self.h.astype(np.float64) * np.exp(2j * np.pi * ph)).astype(np.complex64)
+        gd = torch.from_numpy(g).to(self.vH.device)
+        check(self.lib.pysdr_fir_spectrum(ctypes.c_void_p(gd.data_ptr()), len(g), ctypes.c_void_p(self.vH.data_ptr()), _stream_ptr()))
+        torch.cuda.current_stream(self.vH.device).synchronize()      # gd is a temporary
+        self._vdirty = False
 
     def stage2(self, stereo):
         P = self.rx.P
@@ -537,16 +570,22 @@ class _WfmChain:
             check(self.lib.pysdr_bank_set_stereo(self.rbank.h, 1, float(getattr(P, 'WFM_PILOT_MIN', 0.0))))
         else:
             self.rbank = ReceiverBank(res, [0.0], max_in=self.max_in)
+        check(self.lib.pysdr_bank_set_real_input(self.rbank.h, 1))   # the discriminator output is real (stored as complex64)
         self._res_key = None
         self.deemph = None
 
     def set_video(self, h):
         self.h = np.asarray(h, np.float32)
-        self.vbank.set_dec_taps(0, self.h)
+        if self.vbank is not None:
+            self.vbank.set_dec_taps(0, self.h)
+        else:
+            if len(self.h) != self.L:
+                raise PysdrError("wfm_video.h must have FILT_LEN=%d taps" % self.L)
+            self._vdirty = True
 
     def demod(self, x):
         """Host chunk in, host audio out (what rx.demod_data returns in WFM / WFM2 mode)."""
-        xd = torch.from_numpy(np.ascontiguousarray(x, np.complex64)).to(self.vbank.device)
+        xd = torch.from_numpy(np.ascontiguousarray(x, np.complex64)).to(self.fm.device)
         out, iq = self.demod_dev(xd)
         if self.stereo:
             a = out[0].cpu().numpy() + 1j * out[1].cpu().numpy()
@@ -557,10 +596,21 @@ class _WfmChain:
         """Device samples (whole chunks, at most max_in) -> ([audio] or [L, R], baseband iq), device tensors."""
         P, rx = self.rx.P, self.rx
         n = xd.numel()
-        _, y, _ = self.vbank.process(xd, want_dc=False)
         fm = self.fm[:n]
-        check(self.lib.pysdr_fm_disc(ctypes.c_void_p(y[0].data_ptr()), n, ctypes.c_void_p(self.prev2.data_ptr()),
-                                     ctypes.c_void_p(fm.data_ptr()), _stream_ptr()))
+        if self.vbank is None:
+            if self._vdirty:
+                self._refresh_video_spectrum()
+            check(self.lib.pysdr_wfm_video_disc(ctypes.c_void_p(xd.data_ptr()), n, ctypes.c_void_p(self.vhist.data_ptr()),
+                                                ctypes.c_void_p(self.vprev2.data_ptr()), self.vslot,
+                                                ctypes.c_void_p(self.vH.data_ptr()), self.L, ctypes.c_uint64(self.acc),
+                                                ctypes.c_uint64(self.inc), ctypes.c_void_p(fm.data_ptr()), _stream_ptr()))
+            self.acc = (self.acc + self.inc * n) & ((1 << 64) - 1)
+            if n > 0:
+                self.vslot ^= 1
+        else:
+            _, y, _ = self.vbank.process(xd, want_dc=False)
+            check(self.lib.pysdr_fm_disc(ctypes.c_void_p(y[0].data_ptr()), n, ctypes.c_void_p(self.prev2.data_ptr()),
+                                         ctypes.c_void_p(fm.data_ptr()), _stream_ptr()))
         af_bw = float(design.per_rx(getattr(P, 'AF_BW', 0), rx.irx) or 0)
         if af_bw != self._res_key:
             taps = design.wfm_resampler_taps(P.SRATE, P.UP, P.FILT_LEN, af_bw)

@@ -200,14 +200,15 @@ def test_three_box_compute_matches_plotting_py_algebra():
     assert np.abs(rgba.astype(int) - want.astype(int)).max() <= 8
 
 
-@pytest.mark.parametrize("deemph", [0, 75])
-def test_wfm_demod_first_then_resample(deemph):
+@pytest.mark.parametrize("deemph,direct", [(0, False), (75, False), (0, True)])
+def test_wfm_demod_first_then_resample(deemph, direct):
     """BASELINE config 4 geometry (2.4 MS/s replay rate, 1/50): WFM chain = video FIR @RF rate -> discriminator ->
     resampler (AF low-pass) -> AGC (-> de-emphasis), reference gui.py:1703-1704,1759-1762.  Mono."""
     import pysdr_b200.sig_proc as dsp
     P, Po = make_both(2.4, [100000], ['WFM'], foffset_khz=100, srate_hz=2.4e6, af_bw_khz=[15])
     assert (P.UP, P.DOWN, P.IN_CHUNK_SIZE, P.VIDEO_BW) == (1, 50, 51200, 200e3) == (Po.UP, Po.DOWN, Po.IN_CHUNK_SIZE, Po.VIDEO_BW)
     P.DEEMPH_US = Po.DEEMPH_US = deemph
+    P.WFM_DIRECT_VIDEO = direct                     # True: the r01 route (direct-form video FIR through K1 + pysdr_fm_disc)
     C = P.IN_CHUNK_SIZE
     n = np.arange(5 * C)
     ph = 2 * np.pi * P.FOFFSET * n / P.SRATE + (75e3 / 1e3) * np.sin(2 * np.pi * 1e3 * n / P.SRATE) \
@@ -221,8 +222,11 @@ def test_wfm_demod_first_then_resample(deemph):
             orx._demod_wfm(np.zeros(0, np.complex64)) if not hasattr(orx, 'wfm_vid') else None
             orx.demod.wfm_video.h = orx.demod.wfm_filter_bank[8]
             P.AF_BW = Po.AF_BW = 10e3
+        if c == 2:                                                  # retune: phase continuous, applied to the filter memory too
+            assert rx.lo.change_freq(P.FOFFSET + 2.5e3) == orx.lo.change_freq(Po.FOFFSET + 2.5e3)
         am = rx.demod_data(x[c * C:(c + 1) * C])
         ref = orx.demod_data(x[c * C:(c + 1) * C])
+        assert (rx._wfm.vbank is None) == (not direct)
         assert am.dtype == np.float32 and len(am) == len(ref) == 1024
         assert_parity(rx.iq, orx.iq, "wfm resampled chunk %d" % c)
         assert_parity(am, ref, "wfm audio chunk %d" % c)
