@@ -16,7 +16,8 @@
 extern "C" {
 #endif
 
-#define PYSDR_MAX_RX 8          /* reference MAX_RX = 6 (params.py:33) */
+#define PYSDR_MAX_RX 128        /* receivers per bank; the reference stops at MAX_RX = 6 (params.py:33), the many-channel
+                                   bank (BASELINE config 5) runs its audio-rate stages in groups of up to this many */
 #define PYSDR_AGC_NB 8
 
 /* demodulator kinds: reference Tables.py:34 MODES */

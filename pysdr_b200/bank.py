@@ -15,6 +15,9 @@ from . import _lib, design
 from ._lib import BankConfig, PysdrError, check
 
 
+MAX_RX_PER_BANK = 128           # include/pysdr_b200.h PYSDR_MAX_RX
+
+
 def _stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -45,8 +48,8 @@ class ReceiverBank:
         self.P = P
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.n_rx = len(freqs)
-        if self.n_rx < 1 or self.n_rx > 8:
-            raise PysdrError("1..8 receivers per bank (reference MAX_RX=6)")
+        if self.n_rx < 1 or self.n_rx > MAX_RX_PER_BANK:
+            raise PysdrError("1..%d receivers per bank (reference MAX_RX=6)" % MAX_RX_PER_BANK)
         self.af_len = int(P.FILT_LEN)
         self.max_in = int(max_in if max_in is not None else P.IN_CHUNK_SIZE)
         cfg = BankConfig(float(P.SRATE), int(P.UP), int(P.DOWN), int(P.IN_CHUNK_SIZE), self.n_rx, int(P.FILT_LEN),

@@ -1,7 +1,7 @@
 """Many-channel receiver bank (BASELINE config 5: 1024 simultaneous channel receivers on one 10 MS/s stream).
 
 The reference's surface stops at MAX_RX = 6 (params.py:33); this is the north-star extension.  Channels are served in
-groups of up to 8 receivers, one ReceiverBank (= one set of K1/K2 launches) per group, all groups reading the SAME
+groups of up to 128 receivers, one ReceiverBank (= one set of K1/K2 launches) per group, all groups reading the SAME
 device-resident block of IQ.  Every number still comes from libpysdr_b200.so; this class is only the loop over
 groups.  At 3/625 the contraction is compute-bound (13 kFLOP per input sample for 1024 channels, 474 flop/B): the
 tap-stationary K1 runs it at its FP32-FMA rate; a tensor-core formulation is the named next step."""
@@ -15,9 +15,9 @@ from .bank import ReceiverBank
 
 
 class ChannelBank:
-    GROUP = 8
+    GROUP = 128          # receivers per ReceiverBank (PYSDR_MAX_RX): 1024 channels = 8 sets of audio-rate launches per block
 
-    def __init__(self, P, offsets_hz, modes, af_bw=0.0, bfo=0.0, max_in=None, device=None, raster=None):
+    def __init__(self, P, offsets_hz, modes, af_bw=0.0, bfo=0.0, max_in=None, device=None, raster=None, group=None):
         """raster=(f0_hz, df_hz): the offsets are f0 + c*df on a raster wola.cu serves (df/fs = a/3125): the baseband of all
         channels then comes from ONE RasterChannelizer pass per block, written straight into the groups' (shared) complex
         memory, and the groups only run their audio-rate stages."""
@@ -28,6 +28,8 @@ class ChannelBank:
         if not (len(modes) == len(af_bw) == len(bfo) == n):
             raise ValueError("one mode / AF bandwidth / BFO per channel")
         self.P, self.n_ch = P, n
+        if group is not None:
+            self.GROUP = int(group)
         self.banks, self.slices = [], []
         for g0 in range(0, n, self.GROUP):
             g1 = min(n, g0 + self.GROUP)
@@ -127,20 +129,50 @@ class ShardedChannelBank:
 
     def step(self, xbuf):
         """xbuf: device samples [first_sample, start+n) of this rank's shard.  Returns (am, iq) lists over channels."""
-        from .dist import exchange_agc_peaks
+        import ctypes
+        import torch.distributed as dist
+        from ._lib import check
+        from .bank import _stream_ptr
+        from .dist import AGC_SUMMARY_LEN, exchange_agc_peaks
         cb = self.cb
         if cb.raster is not None:                                        # K1 of every channel for shard + warm-up in one pass
             p = self.plan
             C = int(cb.P.IN_CHUNK_SIZE)
             n0 = p['start'] - p['warm_chunks'] * C
             cb.raster.process(xbuf[p['halo']:], n0=n0, hist=xbuf[:p['halo']], out=cb._C, out_col=cb._hc)
-        own = torch.cat([sh.front(xbuf) for sh in self.shards])          # [n_ch, n_blocks]
-        prev = exchange_agc_peaks(own, self.rank, self.world)            # one collective for every channel
         am, iq = [], []
-        for sh, (g0, g1) in zip(self.shards, self.cb.slices):
-            a, q, _ = sh.back(None if prev is None else prev[g0:g1].contiguous())
-            am.extend(a)
-            iq.extend(q)
+        if not self.shards[0].o1:                                        # short shards: gather every block peak
+            own = torch.cat([sh.front(xbuf) for sh in self.shards])      # [n_ch, n_blocks]
+            prev = exchange_agc_peaks(own, self.rank, self.world)
+            for sh, (g0, g1) in zip(self.shards, cb.slices):
+                a, q, _ = sh.back(None if prev is None else prev[g0:g1].contiguous())
+                am.extend(a)
+                iq.extend(q)
+            return am, iq
+        # O(1) carry: one all-gather of 19 doubles per channel per rank (152 KB per rank at 1024 channels, whatever the shard
+        # length; the peak gather was 691 MB at config-5 scale), then every bank enters from the summaries of the earlier ranks
+        G = cb.GROUP
+        if getattr(self, '_sum', None) is None:
+            dev = cb.device
+            self._sum = torch.zeros((len(cb.banks), G, AGC_SUMMARY_LEN), dtype=torch.float64, device=dev)
+            self._all = torch.zeros((self.world, len(cb.banks), G, AGC_SUMMARY_LEN), dtype=torch.float64, device=dev)
+        w = self.plan['warm_chunks']
+        for k, sh in enumerate(self.shards):
+            sh.front(xbuf, copy_own=False)
+            check(sh.bank.lib.pysdr_bank_agc_summary(sh.bank.h, w, ctypes.c_void_p(self._sum[k].data_ptr()), _stream_ptr()))
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._all, self._sum)            # the one collective, for every channel
+            per_bank = self._all.permute(1, 0, 2, 3).contiguous()        # [bank][rank][G][19]
+        else:
+            per_bank = self._sum.unsqueeze(1)
+        for k, sh in enumerate(self.shards):
+            b = sh.bank
+            # rows of a bank's summary block are its n_rx receivers followed by unused rows: compact to [rank][n_rx][19]
+            sums = per_bank[k][:, :b.n_rx, :].contiguous() if b.n_rx != G else per_bank[k]
+            a, q, _ = b.process_back_carry(sums, self.rank, want_dc=False, skip_blocks=w)
+            ks = sh.skip_out
+            am.extend(v[ks:] for v in a)
+            iq.extend(v[ks:] for v in q)
         return am, iq
 
 

@@ -1523,7 +1523,7 @@ static int back_impl(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, i
     if (enter) b->lazy_reset_agc = false;          // an explicit entry state replaces the restart a seek(0) asked for
     if (n_out == 0) {                        // nothing was emitted: the AGC does not advance (like the reference's empty am)
         if (enter) {
-            agc_enter_kernel<<<1, 32, 0, st>>>(b->d_agc, d_sums, n_before, c.n_rx);
+            agc_enter_kernel<<<1, PYSDR_MAX_RX, 0, st>>>(b->d_agc, d_sums, n_before, c.n_rx);
             LAUNCH_CHECK();
             b->launches++;
         }
@@ -1606,7 +1606,7 @@ static int back_impl(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, i
             b->peaks_deferred = false;
         }
         if (enter) {
-            agc_enter_kernel<<<1, 32, 0, st>>>(b->d_agc, d_sums, n_before, c.n_rx);
+            agc_enter_kernel<<<1, PYSDR_MAX_RX, 0, st>>>(b->d_agc, d_sums, n_before, c.n_rx);
             LAUNCH_CHECK();
             b->launches++;
         }
@@ -1680,7 +1680,7 @@ extern "C" int pysdr_bank_agc_enter(pysdr_bank *b, const double *d_summaries, in
     if (!b || n_before < 0 || (n_before > 0 && !d_summaries)) { pysdr_set_error("agc_enter: bad arguments"); return PYSDR_ERR_ARG; }
     b->lazy_reset_agc = false;               // this entry state replaces the restart a seek(0) asked for ...
     { int rc = flush_seek(b, (cudaStream_t)stream); if (rc) return rc; }     // ... and a pending seek must not undo it afterwards
-    agc_enter_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(b->d_agc, d_summaries, n_before, b->cfg.n_rx);
+    agc_enter_kernel<<<1, PYSDR_MAX_RX, 0, (cudaStream_t)stream>>>(b->d_agc, d_summaries, n_before, b->cfg.n_rx);
     LAUNCH_CHECK();
     b->launches++;
     return PYSDR_OK;
@@ -1801,7 +1801,7 @@ static int flush_seek(pysdr_bank *b, cudaStream_t st) {
         b->lazy_seek = false;
         b->lazy_reset_agc = false;
     } else if (b->lazy_reset_agc) {              // the seek itself was folded into a front call; the AGC restart is still due
-        agc_enter_kernel<<<1, 32, 0, st>>>(b->d_agc, nullptr, 0, b->cfg.n_rx);
+        agc_enter_kernel<<<1, PYSDR_MAX_RX, 0, st>>>(b->d_agc, nullptr, 0, b->cfg.n_rx);
         LAUNCH_CHECK();
         b->launches++;
         b->lazy_reset_agc = false;

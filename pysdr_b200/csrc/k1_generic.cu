@@ -12,7 +12,8 @@
 // for every geometry; k1_fast.cu is the tuned tap-stationary kernel for the common ones.
 #include "common.cuh"
 
-__global__ void __launch_bounds__(256) k1_generic_kernel(K1Args a) {
+#define K1G_RX 8             /* receivers per launch (register-resident accumulators); banks with more launch in groups */
+__global__ void __launch_bounds__(256) k1_generic_kernel(const K1Args a, const int rx0) {
     const int lane = threadIdx.x & 31;
     const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
@@ -24,9 +25,9 @@ __global__ void __launch_bounds__(256) k1_generic_kernel(K1Args a) {
         const i64 nm = t / a.up;
         const int ph = (int)(t - nm * a.up);
         const i64 r0 = nm - a.n0;                       // newest input of this output, relative to x[0]
-        float sr[PYSDR_MAX_RX], si[PYSDR_MAX_RX];
+        float sr[K1G_RX], si[K1G_RX];
 #pragma unroll
-        for (int r = 0; r < PYSDR_MAX_RX; ++r) { sr[r] = 0.f; si[r] = 0.f; }
+        for (int r = 0; r < K1G_RX; ++r) { sr[r] = 0.f; si[r] = 0.f; }
         const float2 *gp = a.g + (size_t)ph * a.lp_pad;
         for (int j = lane; j < a.lp; j += 32) {
             const i64 idx = r0 - j;
@@ -35,9 +36,9 @@ __global__ void __launch_bounds__(256) k1_generic_kernel(K1Args a) {
             else if (idx >= -(i64)a.need && a.hist) xv = a.hist[a.need + idx];
             else xv = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int r = 0; r < PYSDR_MAX_RX; ++r) {
-                if (r < a.n_rx) {
-                    const float2 gv = __ldg(gp + r * rx_pitch + j);
+            for (int r = 0; r < K1G_RX; ++r) {
+                if (rx0 + r < a.n_rx) {
+                    const float2 gv = __ldg(gp + (rx0 + r) * rx_pitch + j);
                     sr[r] = fmaf(gv.x, xv.x, sr[r]);
                     sr[r] = fmaf(-gv.y, xv.y, sr[r]);
                     si[r] = fmaf(gv.x, xv.y, si[r]);
@@ -46,8 +47,8 @@ __global__ void __launch_bounds__(256) k1_generic_kernel(K1Args a) {
             }
         }
 #pragma unroll
-        for (int r = 0; r < PYSDR_MAX_RX; ++r) {
-            if (r < a.n_rx) {
+        for (int r = 0; r < K1G_RX; ++r) {
+            if (rx0 + r < a.n_rx) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     sr[r] += __shfl_xor_sync(0xffffffffu, sr[r], o);
@@ -56,14 +57,15 @@ __global__ void __launch_bounds__(256) k1_generic_kernel(K1Args a) {
             }
         }
 #pragma unroll
-        for (int r = 0; r < PYSDR_MAX_RX; ++r) {
-            if (r < a.n_rx && lane == r) {
-                const float2 cs = nco_cs(a.acc[r] + a.inc[r] * (u64)r0);
+        for (int r = 0; r < K1G_RX; ++r) {
+            if (rx0 + r < a.n_rx && lane == r) {
+                const int rr = rx0 + r;
+                const float2 cs = nco_cs(a.acc[rr] + a.inc[rr] * (u64)r0);
                 float2 y;
                 y.x = sr[r] * cs.x + si[r] * cs.y;      // (sr + j si) * (cos - j sin)
                 y.y = si[r] * cs.x - sr[r] * cs.y;
-                a.c_out[(size_t)r * a.c_stride + a.hc + i] = y;
-                if (a.bb_out) a.bb_out[(size_t)r * a.bb_stride + i] = y;
+                a.c_out[(size_t)rr * a.c_stride + a.hc + i] = y;
+                if (a.bb_out) a.bb_out[(size_t)rr * a.bb_stride + i] = y;
             }
         }
     }
@@ -74,7 +76,9 @@ int k1_launch_generic(const K1Args &a, cudaStream_t st) {
     i64 blocks = (a.n_out + 7) / 8;
     const i64 cap = (i64)pysdr_sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    k1_generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
-    LAUNCH_CHECK();
+    for (int rx0 = 0; rx0 < a.n_rx; rx0 += K1G_RX) {
+        k1_generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, rx0);
+        LAUNCH_CHECK();
+    }
     return PYSDR_OK;
 }

@@ -76,8 +76,8 @@ def test_error_codes_are_loud():
         bank.process(torch.zeros(16, dtype=torch.float32, device="cuda"))          # wrong dtype
     with pytest.raises(PysdrError, match="multiple"):
         bank.seek(12345)
-    with pytest.raises(PysdrError, match="1..8"):
-        ReceiverBank(P, [0.0] * 9)
+    with pytest.raises(PysdrError, match="1..128"):
+        ReceiverBank(P, [0.0] * 129)
     P.MODE = 'WFM'
     with pytest.raises(PysdrError, match="WFM"):
         bank.process(torch.zeros(P.IN_CHUNK_SIZE, dtype=torch.complex64, device="cuda"))
@@ -385,7 +385,7 @@ def test_many_channel_bank_cfg5_geometry():
     for k, f in enumerate(offs):
         x = x + 0.02 * (1 + 0.5 * np.sin(2 * np.pi * (300.0 + 40 * k) * n / P.SRATE)) * np.exp(2j * np.pi * (f + 700.0) * n / P.SRATE)
     x = x.astype(np.complex64)
-    cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=2 * C)
+    cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=2 * C, group=8)
     am, iq = cb.process(torch.from_numpy(x).cuda())
     assert len(am) == n_ch and cb.n_out == odsp.n_out_total(2 * C, P.UP, P.DOWN)
     for k in range(n_ch):

@@ -81,7 +81,7 @@ def test_two_gpu_time_shard_equals_single_gpu(tmp_path, CPR):
         assert_parity(got_am, ref_am[r], "sharded vs single rx%d" % r, rel_tol=2e-5, snr_min=90)
 
 
-def _chan_worker(rank, world, port, outdir, raster):
+def _chan_worker(rank, world, port, outdir, raster, cpr=3):
     import torch.distributed as dist
     from pysdr_b200.channelizer import ChannelBank, ShardedChannelBank, raster_offsets
     from pysdr_b200.params import RUN_TIME_PARAMS
@@ -95,9 +95,9 @@ def _chan_worker(rank, world, port, outdir, raster):
         P = RUN_TIME_PARAMS(['-fs', '10', '-fc', '7000', '-mode', 'USB', '-af_bw', '2'])
         offs, modes, afs = _chan_cfg()
         C = P.IN_CHUNK_SIZE
-        cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=5 * C, device=dev,
-                         raster=(offs[0], 9600.0) if raster else None)
-        sh = ShardedChannelBank(cb, rank, world, 3)
+        cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=(cpr + 2) * C, device=dev,
+                         raster=(offs[0], 9600.0) if raster else None, group=8)
+        sh = ShardedChannelBank(cb, rank, world, cpr)
         pl = sh.plan
         xbuf = synth_iq(pl['lead'] + pl['n'], P.SRATE, offs[:4], modes[:4], seed=78, device=dev, n0=pl['first_sample'], block=1 << 16)
         am, iq = sh.step(xbuf)
@@ -116,8 +116,8 @@ def _chan_cfg():
     return offs, modes, afs
 
 
-@pytest.mark.parametrize("raster", [False, True])
-def test_two_gpu_many_channel_time_shard(tmp_path, raster):
+@pytest.mark.parametrize("raster,cpr", [(False, 3), (True, 3), (True, 9)])
+def test_two_gpu_many_channel_time_shard(tmp_path, raster, cpr):
     """Config 5's shape at test size: 20 channels (3 groups) on a 10 MS/s stream, time-sharded over 2 ranks with one
     all-gather of every channel's AGC peaks, equals the single-GPU single-stream result."""
     if torch.cuda.device_count() < 2:
@@ -127,12 +127,12 @@ def test_two_gpu_many_channel_time_shard(tmp_path, raster):
     from pysdr_b200.params import RUN_TIME_PARAMS
     from pysdr_b200.synth import synth_iq
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_chan_worker, args=(2, port, str(tmp_path), raster), nprocs=2, join=True)
+    mp.spawn(_chan_worker, args=(2, port, str(tmp_path), raster, cpr), nprocs=2, join=True)
     P = RUN_TIME_PARAMS(['-fs', '10', '-fc', '7000', '-mode', 'USB', '-af_bw', '2'])
     offs, modes, afs = _chan_cfg()
     C = P.IN_CHUNK_SIZE
-    x = synth_iq(6 * C, P.SRATE, offs[:4], modes[:4], seed=78, device="cuda:0", block=1 << 16)
-    cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=6 * C, device="cuda:0")
+    x = synth_iq(2 * cpr * C, P.SRATE, offs[:4], modes[:4], seed=78, device="cuda:0", block=1 << 16)
+    cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=2 * cpr * C, device="cuda:0")
     am, _ = cb.process(x)
     parts = [np.load(os.path.join(str(tmp_path), "chan%d.npz" % r)) for r in range(2)]
     for r in range(len(offs)):
