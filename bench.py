@@ -286,7 +286,7 @@ def cpu_baseline_single(seconds_target=12.0):
 
 
 # ------------------------------------------------------------------------------------------------------
-def parity_check(P, offs, rank, world, dev, cpr=9):
+def parity_check(P, offs, rank, world, dev, cpr=9, carry="peer"):
     """Correctness carried by the bench line itself: on a small capture of world x 9 blocks every rank compares the audio
     of ITS time shard (the timed code path: filter warm-up, halo in place, O(1) AGC carry over the collective) with the same
     blocks taken from a single-stream pass it runs locally.  N = 1: whole-capture call against chunk-at-a-time calls.
@@ -319,11 +319,11 @@ def parity_check(P, offs, rank, world, dev, cpr=9):
         how = "whole-capture call vs %d chunk-at-a-time calls" % cpr
     else:
         b = ReceiverBank(P, offs, max_in=(cpr + 1) * C, device=dev)
-        sh = ShardedCapture(b, P, rank, world, cpr)
+        sh = ShardedCapture(b, P, rank, world, cpr, carry=carry)
         pl = sh.plan
         am, _, _ = sh.step(x[pl['first_sample']:pl['start'] + pl['n']])
         got = [a.clone() for a in am]
-        how = "each rank's time shard (%d blocks, O(1) AGC carry over the collective) vs a local single-stream pass" % cpr
+        how = "each rank's time shard (%d blocks, O(1) AGC carry: %s) vs a local single-stream pass" % (cpr, sh.carry_how)
     worst_rel, worst_snr = 0.0, 1e9
     for g, r in zip(got, ref):
         assert g.shape == r.shape, (g.shape, r.shape)
@@ -370,13 +370,14 @@ def run_own(args):
     offs = receiver_offsets(P)
     from pysdr_b200.dist import ShardedCapture
     bank = ReceiverBank(P, offs, max_in=n + (C if rank > 0 else 0), device=dev)
-    shard = ShardedCapture(bank, P, rank, world, n_chunks)          # plan: warm-up chunk + K1 halo for rank > 0
+    shard = ShardedCapture(bank, P, rank, world, n_chunks, carry=args.carry)   # plan: warm-up chunk + K1 halo for rank > 0
     plan = shard.plan
     warm = plan['warm_chunks']
     xbuf = synth_iq(plan['lead'] + n, P.SRATE, offs, MODES, seed=1234, device=dev, n0=plan['first_sample'])
     x_main = xbuf[plan['lead']:]
 
-    parity = parity_check(P, offs, rank, world, dev)                # sharded == single stream, before anything is timed
+    # sharded == single stream, before anything is timed (skipped only for profiler passes, whose lines are never bench values)
+    parity = None if args.no_parity else parity_check(P, offs, rank, world, dev, carry=args.carry)
 
     def step():
         shard.step(xbuf)                                            # front -> AGC summary exchange (N > 1) -> back
@@ -431,6 +432,25 @@ def run_own(args):
             h_am, _ = streamer.run(hx)                                      # each GPU replays its own host capture
             return float(h_am[0, 0, 0])                                     # host read of the step's result
 
+        # the ceiling of this box: the same pinned capture copied to the device and nothing else, all ranks at once
+        dcap = torch.empty(64 * C, dtype=torch.complex64, device=dev)
+        def bare_h2d():
+            for s0 in range(0, n - 64 * C + 1, 64 * C):
+                dcap.copy_(hx[s0:s0 + 64 * C], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        bare_h2d()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            bare_h2d()
+        barrier()
+        dt_h2d = (time.perf_counter() - t0) / 3
+        if world > 1:
+            t = torch.tensor([dt_h2d], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_h2d = float(t.item())
+        h2d_bytes = (n // (64 * C)) * 64 * C * 8
+        del dcap
         for _ in range(2):
             e2e_step()
         barrier()
@@ -448,7 +468,12 @@ def run_own(args):
         e2e = {"value": world * n * ksteps / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(n * 8),
                "d2h_bytes_per_step": int(4 * n_out_tot * 4), "steps": ksteps,
                "how": "pinned host complex64 capture -> 64-chunk segments double-buffered H2D on a copy stream -> "
-                      "bank.process -> audio D2H to pinned host, per GPU"}
+                      "bank.process -> audio D2H to pinned host, per GPU",
+               "h2d_ceiling": {"GBps_per_gpu": h2d_bytes / dt_h2d / 1e9, "GBps_all_gpus": world * h2d_bytes / dt_h2d / 1e9,
+                               "Msamples_per_s_all_gpus": world * h2d_bytes / 8 / dt_h2d / 1e6,
+                               "how": "the same pinned capture copied host->device in the same 64-chunk pieces with no kernels, "
+                                      "all ranks simultaneously (max over ranks)"}}
+        e2e["frac_of_h2d_ceiling"] = e2e["value"] / e2e["h2d_ceiling"]["Msamples_per_s_all_gpus"]
         del streamer
         # the call the reference's own loop makes (receiver.py:724-725): one IN_CHUNK_SIZE chunk per call, host numpy in,
         # host numpy out, all four receivers of the chunk served from one upload (ReceiverBank.process_host)
@@ -520,8 +545,8 @@ def run_own(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (complex64 samples; f64/u64 phase; f64 AGC)", "data": "synthetic",
             "config": workload_config(n_chunks),
-            "arm": {"parallelism": "time-sharded x%d (filter-memory warm-up chunk + ONE all-gather of a 152-byte AGC summary per "
-                                   "receiver per rank)" % world if world > 1 else "single GPU, all 4 receivers share one read",
+            "arm": {"parallelism": ("time-sharded x%d (filter-memory warm-up chunk + a 152-byte AGC summary per receiver per rank, %s)"
+                                    % (world, shard.carry_how)) if world > 1 else "single GPU, all 4 receivers share one read",
                     "timed_region": "inputs resident in HBM; CUDA events on the launch stream; max over ranks"},
             "parity_check": parity,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
@@ -561,6 +586,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="profiler passes only: skip the pre-timing parity check")
+    ap.add_argument("--carry", default="peer", choices=["peer", "nccl"],
+                    help="N>1: AGC carry over NVLink peer memory written by our own kernels (default) or one NCCL all-gather")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "own":
         args.warmup = 3

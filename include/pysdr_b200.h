@@ -159,12 +159,30 @@ int pysdr_bank_process_back(pysdr_bank *b, const float *d_prev_peaks, int64_t n_
  *              the n_before earlier shards (d_summaries[n_before][n_rx][LEN], device, in stream order) from the reset
  *              state: 7 plain updates + one composed step per shard.  n_before = 0 gives the reset state. */
 #define PYSDR_AGC_SUMMARY_LEN 19
+#define PYSDR_XCHG_DEPTH 16      /* ring depth of the peer-memory exchange buffer (steps a fast rank may run ahead) */
+#define PYSDR_XCHG_MAX_WORLD 16
 int pysdr_bank_agc_summary(pysdr_bank *b, int64_t skip_blocks, double *d_summary, void *stream);
 int pysdr_bank_agc_enter(pysdr_bank *b, const double *d_summaries, int n_before, void *stream);
 /* process_back with the entry state taken from the summaries of the n_before earlier shards (agc_enter fused into the same
  * launch as the scan and the gain application). */
 int pysdr_bank_process_back_carry(pysdr_bank *b, const double *d_summaries, int n_before, int64_t skip_blocks,
                                   float *d_am, float *d_am_dc, int64_t out_stride, void *stream);
+/* The same carry over NVLink PEER MEMORY instead of a collective library call: every rank owns one buffer of
+ * pysdr_xchg_bytes(world, n_rx) bytes that is mapped into all peers (torch.distributed._symmetric_memory), zero-initialised.
+ * peer_bases[q] = device address of rank q's buffer as mapped into THIS process (q = rank: the local buffer).
+ *   agc_summary_push : after process_front; computes this rank's summaries and stores them into slot seq % PYSDR_XCHG_DEPTH of
+ *                      every LATER rank's buffer, then raises this rank's flag for step seq there.  seq = 1, 2, 3, ... on
+ *                      all ranks, every value exactly once per buffer.  Before reusing a slot the kernel waits for the later
+ *                      ranks' acknowledgement of step seq - PYSDR_XCHG_DEPTH, so a fast rank runs at most DEPTH steps ahead.
+ *   process_back_xchg: process_back whose scanner CTAs wait (in the kernel) for the flags of the ranks < rank, enter from
+ *                      their summaries in the local buffer and acknowledge the step in the earlier ranks' buffers.
+ * A rank waits for earlier ranks' data and later ranks' acknowledgements of older steps only (no cycle); a wait that lasts
+ * 10 s traps (dead peer) instead of hanging the GPU.  No host synchronisation and no collective library on this path. */
+int64_t pysdr_xchg_bytes(int world, int n_rx);
+int pysdr_bank_agc_summary_push(pysdr_bank *b, int64_t skip_blocks, const uint64_t *peer_bases, int world, int rank, uint64_t seq,
+                                void *stream);
+int pysdr_bank_process_back_xchg(pysdr_bank *b, const uint64_t *peer_bases, int world, int rank, uint64_t seq, int64_t skip_blocks,
+                                 float *d_am, float *d_am_dc, int64_t out_stride, void *stream);
 /* Testing: on != 0 runs the tail as stand-alone kernels (block peaks, AGC scan, gain application, seek reset) instead of the
  * fused back kernel (one co-resident grid, two grid barriers). */
 int pysdr_bank_force_unfused(pysdr_bank *b, int on);

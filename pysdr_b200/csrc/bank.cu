@@ -513,12 +513,12 @@ __global__ void __launch_bounds__(AGC_THREADS) agc_scan_kernel(AgcScanArgs p) { 
 // One CTA per receiver: ordered reduction (composition is associative, not commutative) of the block functions of
 // blocks 7 .. n-1; every w_b there depends on the shard's own peaks only.
 #define SUM_THREADS 256
-__global__ void __launch_bounds__(SUM_THREADS) agc_summary_kernel(const AgcState *__restrict__ state, const float *__restrict__ peaks,
-                                                                  i64 peaks_stride, i64 skip, i64 n_blocks, double *__restrict__ out) {
-    const int rx = blockIdx.x, tid = threadIdx.x;
+// summary of receiver rx into o[LEN] (o may be shared or global memory); block-wide, ends with a barrier
+__device__ void agc_summary_rx(const AgcState *__restrict__ state, const float *__restrict__ peaks, i64 peaks_stride, i64 skip,
+                               i64 n_blocks, const int rx, double *o) {
+    const int tid = threadIdx.x;
     const float *own = peaks + (size_t)rx * peaks_stride + skip;
     const i64 n = n_blocks - skip;
-    double *o = out + (size_t)rx * PYSDR_AGC_SUMMARY_LEN;
     const double ref = state[rx].ref, beta = state[rx].beta, D = 1.0 - beta;
     __shared__ AgcFn s_fn[SUM_THREADS];
     // thread t owns the contiguous run [lo, hi) of blocks 7 .. n-1
@@ -527,9 +527,9 @@ __global__ void __launch_bounds__(SUM_THREADS) agc_summary_kernel(const AgcState
     const i64 lo = 7 + (i64)tid * per, hi = (lo + per < n) ? lo + per : n;
     AgcFn f; f.A = 1.0e300; f.C = 0.0; f.D = 1.0;
     for (i64 b = lo; b < hi; ++b) {
-        float mb = own[b];
+        float mb = __ldcg(own + b);
 #pragma unroll
-        for (int j = 1; j < 8; ++j) mb = fmaxf(mb, own[b - j]);
+        for (int j = 1; j < 8; ++j) mb = fmaxf(mb, __ldcg(own + b - j));
         const double w = fmin(ref / fmax((double)mb, 1.0e-9), 1.0e4);
         AgcFn g; g.A = w; g.C = beta * w; g.D = D;
         f = agc_compose(f, g);
@@ -541,23 +541,126 @@ __global__ void __launch_bounds__(SUM_THREADS) agc_summary_kernel(const AgcState
         __syncthreads();
     }
     if (tid == 0) { o[0] = s_fn[0].A; o[1] = s_fn[0].C; o[2] = s_fn[0].D; o[18] = (double)n; }
-    if (tid < 7) o[3 + tid] = tid < n ? (double)own[tid] : 0.0;
-    if (tid < 8) { const i64 e = n - 8 + tid; o[10 + tid] = e >= 0 ? (double)own[e] : 0.0; }
+    if (tid < 7) o[3 + tid] = tid < n ? (double)__ldcg(own + tid) : 0.0;
+    if (tid < 8) { const i64 e = n - 8 + tid; o[10 + tid] = e >= 0 ? (double)__ldcg(own + e) : 0.0; }
+    __syncthreads();
 }
 
+__global__ void __launch_bounds__(SUM_THREADS) agc_summary_kernel(const AgcState *__restrict__ state, const float *__restrict__ peaks,
+                                                                  i64 peaks_stride, i64 skip, i64 n_blocks, double *__restrict__ out) {
+    agc_summary_rx(state, peaks, peaks_stride, skip, n_blocks, blockIdx.x, out + (size_t)blockIdx.x * PYSDR_AGC_SUMMARY_LEN);
+}
+
+// ---- the carry exchange over NVLink peer memory (no NCCL on the data path) ------------------------------------------------
+// Every rank owns one symmetric buffer (torch.distributed._symmetric_memory: the same allocation mapped into every peer):
+//     slots  double [DEPTH][world][n_rx][LEN]     summaries, slot = seq % DEPTH, row = the WRITING rank
+//     flags  u64    [DEPTH][world]                flags[slot][q] = seq once rank q's summaries of step seq have landed here
+//     acks   u64    [world]                       acks[q] = last step whose summaries rank q has finished reading
+//     count  u64    [2]                           local: CTAs of the push kernel / readers of the back kernel that are done
+// agc_summary_push_kernel computes this rank's summaries and STORES them straight into the slots of the LATER ranks (only
+// they read them), fences system-wide, and the last CTA to finish raises the rank's flag in those peers.  The consumer is the
+// fused back kernel: the scanner CTA of a receiver spins on the flags of the ranks before it, reads their summaries from its
+// own copy and — last reader of the step — stores its ack into the earlier ranks' buffers.  A rank only ever waits for
+// EARLIER ranks' data and for LATER ranks' acks of step seq - DEPTH (slot reuse), so the waits cannot form a cycle.
+#define XCHG_DEPTH PYSDR_XCHG_DEPTH
+struct XchgPeers { double *base[PYSDR_XCHG_MAX_WORLD]; };
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// bounded spin: a peer that never shows up (dead rank) must not hang this GPU — trap after 10 s, the context reports an error
+__device__ __forceinline__ void xchg_wait_ge(const unsigned long long *p, unsigned long long v) {
+    if (ld_acquire_sys_u64(p) >= v) return;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys_u64(p) < v) {
+        __nanosleep(100);
+        if (global_ns() - t0 > 10000000000ull) __trap();
+    }
+}
+__host__ __device__ __forceinline__ size_t xchg_slot_doubles(int world, int n_rx) { return (size_t)world * n_rx * PYSDR_AGC_SUMMARY_LEN; }
+__host__ __device__ __forceinline__ size_t xchg_flags_off(int world, int n_rx) { return (size_t)XCHG_DEPTH * xchg_slot_doubles(world, n_rx); }
+__device__ __forceinline__ unsigned long long *xchg_flags(double *base, int world, int n_rx) {
+    return (unsigned long long *)(base + xchg_flags_off(world, n_rx));
+}
+__device__ __forceinline__ unsigned long long *xchg_acks(double *base, int world, int n_rx) {
+    return xchg_flags(base, world, n_rx) + (size_t)XCHG_DEPTH * world;
+}
+__device__ __forceinline__ unsigned long long *xchg_counts(double *base, int world, int n_rx) {
+    return xchg_acks(base, world, n_rx) + world;
+}
+
+__global__ void __launch_bounds__(SUM_THREADS) agc_summary_push_kernel(const AgcState *__restrict__ state, const float *__restrict__ peaks,
+                                                                       i64 peaks_stride, i64 skip, i64 n_blocks, const XchgPeers peers,
+                                                                       int world, int rank, int n_rx, unsigned long long seq) {
+    __shared__ double s_o[PYSDR_AGC_SUMMARY_LEN];
+    const int rx = blockIdx.x, tid = threadIdx.x;
+    agc_summary_rx(state, peaks, peaks_stride, skip, n_blocks, rx, s_o);        // block-wide; s_o valid after the barrier inside
+    const int slot = (int)(seq % XCHG_DEPTH);
+    const size_t off = (size_t)slot * xchg_slot_doubles(world, n_rx) + ((size_t)rank * n_rx + rx) * PYSDR_AGC_SUMMARY_LEN;
+    const int n_later = world - 1 - rank;
+    if (seq > XCHG_DEPTH && tid < n_later)                                      // slot reuse: the later ranks are done with step seq - DEPTH
+        xchg_wait_ge(xchg_acks(peers.base[rank], world, n_rx) + rank + 1 + tid, seq - XCHG_DEPTH);
+    __syncthreads();
+    for (int e = tid; e < n_later * PYSDR_AGC_SUMMARY_LEN; e += SUM_THREADS) {
+        const int q = rank + 1 + e / PYSDR_AGC_SUMMARY_LEN, i = e % PYSDR_AGC_SUMMARY_LEN;
+        peers.base[q][off + i] = s_o[i];                                       // NVLink store into peer q's memory
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence_system();                                                // this CTA's peer stores before the count
+        const unsigned long long prev = atomicAdd(xchg_counts(peers.base[rank], world, n_rx), 1ull);
+        if (prev + 1 == seq * (unsigned long long)n_rx) {                      // every receiver's summary has been stored everywhere
+            __threadfence_system();
+            for (int q = rank + 1; q < world; ++q)
+                st_release_sys_u64(xchg_flags(peers.base[q], world, n_rx) + (size_t)slot * world + rank, seq);
+        }
+    }
+}
+
+// consumer side, one thread per receiver: wait for the earlier ranks' flags of step seq in the LOCAL buffer
+struct XchgWait { XchgPeers peers; int world, rank; unsigned long long seq; };
+__device__ __forceinline__ const double *xchg_wait_summaries(const XchgWait &x, int n_rx) {
+    const int slot = (int)(x.seq % XCHG_DEPTH);
+    double *base = x.peers.base[x.rank];
+    const unsigned long long *fl = xchg_flags(base, x.world, n_rx) + (size_t)slot * x.world;
+    for (int q = 0; q < x.rank; ++q) xchg_wait_ge(fl + q, x.seq);
+    return base + (size_t)slot * xchg_slot_doubles(x.world, n_rx);
+}
+// ... and once its reads are done: the last of the n_rx readers of the step tells the earlier ranks the slot is free
+__device__ __forceinline__ void xchg_ack(const XchgWait &x, int n_rx) {
+    __threadfence_system();
+    const unsigned long long prev = atomicAdd(xchg_counts(x.peers.base[x.rank], x.world, n_rx) + 1, 1ull);
+    if (prev + 1 == x.seq * (unsigned long long)n_rx)
+        for (int q = 0; q < x.rank; ++q) st_release_sys_u64(xchg_acks(x.peers.base[q], x.world, n_rx) + x.rank, x.seq);
+}
+
+// SYS: the summaries were written into this GPU's memory by PEER GPUs over NVLink (pysdr_bank_agc_summary_push): read them
+// with volatile (ld.volatile -> system-coherent) loads.
+template <bool SYS>
+__device__ __forceinline__ double ld_sum(const double *p) { return SYS ? *(const volatile double *)p : __ldcg(p); }
+template <bool SYS = false>
 __device__ void agc_enter_rx(AgcState *state, const double *sums, int n_before, int n_rx, int rx) {
     AgcState s = state[rx];
     for (int i = 0; i < PYSDR_AGC_NB; ++i) s.ring[i] = 0.0;
     s.k = 0; s.gain = 1.0; s.maxbuf = 0.0; s.err = 0.0;
     for (int q = 0; q < n_before; ++q) {
         const double *o = sums + ((size_t)q * n_rx + rx) * PYSDR_AGC_SUMMARY_LEN;
-        const i64 n = (i64)__ldcg(o + 18);
+        const i64 n = (i64)ld_sum<SYS>(o + 18);
         const int head = n < 7 ? (int)n : 7;
-        for (int j = 0; j < head; ++j) agc_update(s, o[3 + j]);
+        for (int j = 0; j < head; ++j) agc_update(s, ld_sum<SYS>(o + 3 + j));
         if (n > 7) {
             const double g_in = s.gain;
-            s.gain = fmin(o[0], fma(o[2], g_in, o[1]));
-            for (int t = 0; t < 8; ++t) s.ring[(int)((s.k + (n - 7) - 1 - t) & 7)] = o[17 - t];
+            s.gain = fmin(ld_sum<SYS>(o), fma(ld_sum<SYS>(o + 2), g_in, ld_sum<SYS>(o + 1)));
+            for (int t = 0; t < 8; ++t) s.ring[(int)((s.k + (n - 7) - 1 - t) & 7)] = ld_sum<SYS>(o + 17 - t);
             s.k += n - 7;
             double mb = 0.0;
             for (int i = 0; i < PYSDR_AGC_NB; ++i) mb = fmax(mb, s.ring[i]);
@@ -567,8 +670,14 @@ __device__ void agc_enter_rx(AgcState *state, const double *sums, int n_before, 
     }
     state[rx] = s;
 }
+__global__ void agc_enter_xchg_kernel(AgcState *state, int n_rx, const XchgWait x) {
+    if ((int)threadIdx.x >= n_rx) return;
+    const double *sums = xchg_wait_summaries(x, n_rx);
+    agc_enter_rx<true>(state, sums, x.rank, n_rx, threadIdx.x);
+    xchg_ack(x, n_rx);
+}
 __global__ void agc_enter_kernel(AgcState *__restrict__ state, const double *__restrict__ sums, int n_before, int n_rx) {
-    if ((int)threadIdx.x < n_rx) agc_enter_rx(state, sums, n_before, n_rx, threadIdx.x);
+    if ((int)threadIdx.x < n_rx) agc_enter_rx<false>(state, sums, n_before, n_rx, threadIdx.x);
 }
 
 // K2e: am = a*gain ; am_dc = am - mean_block(am) for AM/USB.  grid (n_blocks, n_rx); IQ rows are skipped.
@@ -667,6 +776,7 @@ struct BackArgs {
     float *am, *am_dc; i64 am_row;
     ApplyKinds kinds;
     unsigned long long *bar; unsigned long long bar_base;
+    XchgWait x;                                      // do_enter == 2: the peer-memory exchange buffers and the step number
 };
 
 #define BACK_THREADS AGC_THREADS
@@ -690,7 +800,15 @@ __global__ void __launch_bounds__(BACK_THREADS) agc_back_fused_kernel(const Back
     }
     if ((int)blockIdx.x < p.n_rx) {
         if (p.do_enter) {
-            if (threadIdx.x == 0) agc_enter_rx(p.scan.state, p.sums, p.n_before, p.n_rx, blockIdx.x);
+            if (threadIdx.x == 0) {
+                if (p.do_enter == 2) {               // summaries pushed by the earlier ranks over NVLink: wait for their flags
+                    const double *sums = xchg_wait_summaries(p.x, p.n_rx);
+                    agc_enter_rx<true>(p.scan.state, sums, p.x.rank, p.n_rx, blockIdx.x);
+                    xchg_ack(p.x, p.n_rx);
+                } else {
+                    agc_enter_rx<false>(p.scan.state, p.sums, p.n_before, p.n_rx, blockIdx.x);
+                }
+            }
             __syncthreads();
         }
         agc_scan_rx(p.scan, blockIdx.x);
@@ -1514,7 +1632,8 @@ static int launch_block_peaks(pysdr_bank *b, float *d_peaks, const StateArgs &sa
 // back = AGC entry state (optional) -> [deferred block peaks] -> scan -> gain / DC removal.  One fused launch unless the
 // bank is the stereo WFM2 resampler (its L/R peaks are linked between the stages) or the stand-alone kernels are forced.
 static int back_impl(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, int64_t skip_blocks, const double *d_sums,
-                     int n_before, bool enter, float *d_am, float *d_am_dc, int64_t out_stride, cudaStream_t st) {
+                     int n_before, bool enter, float *d_am, float *d_am_dc, int64_t out_stride, cudaStream_t st,
+                     const XchgWait *xw = nullptr) {
     if (!b || !b->pending) { pysdr_set_error("process_back without process_front"); return PYSDR_ERR_STATE; }
     if (!d_am) { pysdr_set_error("process_back: d_am is null"); return PYSDR_ERR_ARG; }
     const pysdr_bank_config &c = b->cfg;
@@ -1523,7 +1642,8 @@ static int back_impl(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, i
     if (enter) b->lazy_reset_agc = false;          // an explicit entry state replaces the restart a seek(0) asked for
     if (n_out == 0) {                        // nothing was emitted: the AGC does not advance (like the reference's empty am)
         if (enter) {
-            agc_enter_kernel<<<1, PYSDR_MAX_RX, 0, st>>>(b->d_agc, d_sums, n_before, c.n_rx);
+            if (xw) agc_enter_xchg_kernel<<<1, PYSDR_MAX_RX, 0, st>>>(b->d_agc, c.n_rx, *xw);
+            else agc_enter_kernel<<<1, PYSDR_MAX_RX, 0, st>>>(b->d_agc, d_sums, n_before, c.n_rx);
             LAUNCH_CHECK();
             b->launches++;
         }
@@ -1581,7 +1701,8 @@ static int back_impl(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, i
         BackArgs p;
         memset(&p, 0, sizeof(p));
         p.do_peaks = b->peaks_deferred ? 1 : 0;
-        p.do_enter = enter ? 1 : 0; p.n_before = n_before; p.sums = d_sums; p.n_rx = c.n_rx;
+        p.do_enter = enter ? (xw ? 2 : 1) : 0; p.n_before = n_before; p.sums = d_sums; p.n_rx = c.n_rx;
+        if (xw) p.x = *xw;
         p.a = (const float *)b->d_a; p.a_row = 2 * b->a_stride;
         p.peaks = (float *)b->pend_peaks; p.peaks_row = n_blocks;
         p.n_blocks = n_blocks; p.B0 = b->pend_B0; p.in_chunk = c.in_chunk; p.m0 = b->pend_m0; p.n_out = n_out;
@@ -1606,7 +1727,8 @@ static int back_impl(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, i
             b->peaks_deferred = false;
         }
         if (enter) {
-            agc_enter_kernel<<<1, PYSDR_MAX_RX, 0, st>>>(b->d_agc, d_sums, n_before, c.n_rx);
+            if (xw) agc_enter_xchg_kernel<<<1, PYSDR_MAX_RX, 0, st>>>(b->d_agc, c.n_rx, *xw);
+            else agc_enter_kernel<<<1, PYSDR_MAX_RX, 0, st>>>(b->d_agc, d_sums, n_before, c.n_rx);
             LAUNCH_CHECK();
             b->launches++;
         }
@@ -1657,6 +1779,43 @@ extern "C" int pysdr_bank_process_back_carry(pysdr_bank *b, const double *d_summ
                                              float *d_am, float *d_am_dc, int64_t out_stride, void *stream) {
     if (n_before < 0 || (n_before > 0 && !d_summaries)) { pysdr_set_error("process_back_carry: bad arguments"); return PYSDR_ERR_ARG; }
     return back_impl(b, nullptr, 0, skip_blocks, d_summaries, n_before, true, d_am, d_am_dc, out_stride, (cudaStream_t)stream);
+}
+
+extern "C" int64_t pysdr_xchg_bytes(int world, int n_rx) {
+    if (world < 1 || world > PYSDR_XCHG_MAX_WORLD || n_rx < 1 || n_rx > PYSDR_MAX_RX) return -1;
+    return (int64_t)(sizeof(double) * xchg_flags_off(world, n_rx) + sizeof(unsigned long long) * ((size_t)XCHG_DEPTH * world + world + 8));
+}
+
+static int xchg_peers(const uint64_t *peer_bases, int world, int rank, uint64_t seq, XchgPeers *out, const char *who) {
+    if (!peer_bases || world < 1 || world > PYSDR_XCHG_MAX_WORLD || rank < 0 || rank >= world || seq == 0) {
+        pysdr_set_error("%s: bad arguments", who);
+        return PYSDR_ERR_ARG;
+    }
+    for (int q = 0; q < PYSDR_XCHG_MAX_WORLD; ++q) out->base[q] = q < world ? (double *)(uintptr_t)peer_bases[q] : nullptr;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_agc_summary_push(pysdr_bank *b, int64_t skip_blocks, const uint64_t *peer_bases, int world, int rank,
+                                           uint64_t seq, void *stream) {
+    XchgPeers peers;
+    if (!b) return PYSDR_ERR_ARG;
+    if (int rc = xchg_peers(peer_bases, world, rank, seq, &peers, "agc_summary_push")) return rc;
+    if (!b->pending || !b->pend_peaks) { pysdr_set_error("agc_summary_push: call process_front first"); return PYSDR_ERR_STATE; }
+    if (skip_blocks < 0 || skip_blocks >= b->pend_blocks) { pysdr_set_error("agc_summary_push: bad skip_blocks"); return PYSDR_ERR_ARG; }
+    agc_summary_push_kernel<<<b->cfg.n_rx, SUM_THREADS, 0, (cudaStream_t)stream>>>(b->d_agc, b->pend_peaks, b->pend_blocks, skip_blocks,
+                                                                                   b->pend_blocks, peers, world, rank, b->cfg.n_rx, seq);
+    LAUNCH_CHECK();
+    b->launches++;
+    return PYSDR_OK;
+}
+
+extern "C" int pysdr_bank_process_back_xchg(pysdr_bank *b, const uint64_t *peer_bases, int world, int rank, uint64_t seq,
+                                            int64_t skip_blocks, float *d_am, float *d_am_dc, int64_t out_stride, void *stream) {
+    XchgWait xw;
+    if (!b) return PYSDR_ERR_ARG;
+    if (int rc = xchg_peers(peer_bases, world, rank, seq, &xw.peers, "process_back_xchg")) return rc;
+    xw.world = world; xw.rank = rank; xw.seq = seq;
+    return back_impl(b, nullptr, 0, skip_blocks, nullptr, rank, true, d_am, d_am_dc, out_stride, (cudaStream_t)stream, &xw);
 }
 
 extern "C" int pysdr_bank_force_unfused(pysdr_bank *b, int on) {

@@ -109,13 +109,52 @@ def agc_summary_reference(peaks, ref=0.25, beta=0.1, gmax=1.0e4, floor=1.0e-9):
     return o
 
 
+class PeerCarry:
+    """The AGC carry between time shards over NVLink peer memory (include/pysdr_b200.h: pysdr_bank_agc_summary_push,
+    pysdr_bank_process_back_xchg).  Owns one symmetric-memory buffer per rank (torch.distributed._symmetric_memory supplies
+    the allocation and the peer mappings; every byte on it is written and read by OUR kernels).  All ranks must call
+    push_and_back the same number of times (the step number is the protocol's sequence number)."""
+
+    def __init__(self, bank, rank, world, group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        self.bank, self.rank, self.world = bank, rank, world
+        nbytes = bank.lib.pysdr_xchg_bytes(world, bank.n_rx)
+        if nbytes <= 0:
+            raise ValueError("peer carry: unsupported world size %d / receiver count %d" % (world, bank.n_rx))
+        self.buf = symm.empty((nbytes + 7) // 8, dtype=torch.float64, device=bank.device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        torch.cuda.synchronize(bank.device)
+        dist.barrier(group=group)                                          # every buffer is zero before anyone's first store
+        self.bases = (ctypes.c_uint64 * world)(*[int(p) for p in self.handle.buffer_ptrs])
+        self.seq = 0
+
+    def push_and_back(self, skip_blocks, want_dc=False):
+        import ctypes
+        from ._lib import check
+        from .bank import _stream_ptr
+        b = self.bank
+        self.seq += 1
+        if self.rank < self.world - 1:                                     # the last shard has no reader
+            check(b.lib.pysdr_bank_agc_summary_push(b.h, int(skip_blocks), self.bases, self.world, self.rank, self.seq, _stream_ptr()))
+        check(b.lib.pysdr_bank_process_back_xchg(b.h, self.bases, self.world, self.rank, self.seq, int(skip_blocks),
+                                                 ctypes.c_void_p(b._am.data_ptr()),
+                                                 ctypes.c_void_p(b._am_dc.data_ptr()) if want_dc else None, b.max_out,
+                                                 _stream_ptr()))
+        return b.views()
+
+
 class ShardedCapture:
     """Per-rank driver of one time shard on the GPU bank (used by bench.py for N>1 and by receiver-level tools).
 
     The warm-up chunk(s) that rebuild the audio-rate filter memory are processed in the SAME call as the shard
     (one K1 launch over [start - warm*C, start + n)); their outputs are simply not returned."""
 
-    def __init__(self, bank, P, rank, world, chunks_per_rank):
+    def __init__(self, bank, P, rank, world, chunks_per_rank, carry="nccl"):
+        """carry = "nccl": one all-gather of the AGC summaries per step; "peer": our own kernels store the summaries straight
+        into the later ranks' memory over NVLink and the fused back kernel waits on their flags (PeerCarry) — no collective
+        library call on the data path.  "peer" falls back to "nccl" where symmetric memory is not available (CPU/gloo)."""
         self.bank, self.P, self.rank, self.world = bank, P, rank, world
         self.plan = shard_plan(P, rank, world, chunks_per_rank)
         if world > 1 and any(bank._mode_of(r) == 'AM-Synch' for r in range(bank.n_rx)):
@@ -135,6 +174,12 @@ class ShardedCapture:
         self.o1 = self.plan['n_blocks'] >= 8
         self.summary = torch.zeros((bank.n_rx, AGC_SUMMARY_LEN), dtype=torch.float64, device=dev)
         self.all_sum = torch.zeros((world, bank.n_rx, AGC_SUMMARY_LEN), dtype=torch.float64, device=dev)
+        self.peer = None
+        self.carry_how = "ONE NCCL all-gather"
+        if carry == "peer" and world > 1 and self.o1 and dev.type == "cuda":
+            self.peer = PeerCarry(bank, rank, world)
+            self.carry_how = ("stored by the summary kernel into the later ranks' HBM over NVLink peer memory, flag-waited "
+                              "inside the fused back kernel; no collective call")
 
     def front(self, xbuf, copy_own=True):
         """K1 + audio-rate filters + block peaks of this shard (and its warm-up).  xbuf: device tensor holding samples
@@ -174,6 +219,10 @@ class ShardedCapture:
             return b.process(xbuf[self.plan['lead']:], want_dc=want_dc)
         self.front(xbuf, copy_own=False)
         w = self.plan['warm_chunks']
+        if self.peer is not None:
+            am, iq, dc = self.peer.push_and_back(w, want_dc)
+            k = self.skip_out
+            return [a[k:] for a in am], [a[k:] for a in iq], [a[k:] for a in dc]
         check(b.lib.pysdr_bank_agc_summary(b.h, w, ctypes.c_void_p(self.summary.data_ptr()), _stream_ptr()))
         exchange_agc_summaries(self.summary, self.all_sum, self.world)       # the one collective of the path
         am, iq, dc = b.process_back_carry(self.all_sum, self.rank, want_dc=want_dc, skip_blocks=w)

@@ -24,7 +24,7 @@ def _P():
                            ['-foffset', '100', '-af_bw', '5', '10', '2', '0.5'])
 
 
-def _worker(rank, world, port, outdir, CPR):
+def _worker(rank, world, port, outdir, CPR, carry="nccl", steps=2):
     import torch.distributed as dist
     from pysdr_b200.bank import ReceiverBank
     from pysdr_b200.dist import ShardedCapture
@@ -40,10 +40,11 @@ def _worker(rank, world, port, outdir, CPR):
         offs = receiver_offsets(P)
         C = P.IN_CHUNK_SIZE
         bank = ReceiverBank(P, offs, max_in=(CPR + 1) * C, device=dev)
-        sh = ShardedCapture(bank, P, rank, world, CPR)
+        sh = ShardedCapture(bank, P, rank, world, CPR, carry=carry)
+        assert (sh.peer is not None) == (carry == "peer" and CPR >= 8)
         pl = sh.plan
         xbuf = synth_iq(pl['lead'] + pl['n'], P.SRATE, offs, MODES, seed=77, device=dev, n0=pl['first_sample'], block=1 << 16)
-        for _ in range(2):                                        # twice: the step must be repeatable
+        for _ in range(steps):                                    # repeatable; > 16 steps reuse the exchange ring's slots
             am, iq, dc = sh.step(xbuf, want_dc=True)
         torch.cuda.synchronize()
         np.savez(os.path.join(outdir, "rank%d.npz" % rank), **{"am%d" % r: am[r].cpu().numpy() for r in range(4)},
@@ -52,8 +53,11 @@ def _worker(rank, world, port, outdir, CPR):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("CPR", CPRS)
-def test_two_gpu_time_shard_equals_single_gpu(tmp_path, CPR):
+@pytest.mark.parametrize("CPR,carry,steps", [(c, "nccl", 2) for c in CPRS] + [(9, "peer", 2), (9, "peer", 40)])
+def test_two_gpu_time_shard_equals_single_gpu(tmp_path, CPR, carry, steps):
+    """carry = "peer": the AGC summaries travel through NVLink peer memory written by agc_summary_push_kernel and are
+    flag-waited inside the fused back kernel (no NCCL call on the data path); 40 steps wrap the 16-deep slot ring twice,
+    so the acknowledgement path (slot reuse) is exercised too."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -62,7 +66,7 @@ def test_two_gpu_time_shard_equals_single_gpu(tmp_path, CPR):
     from pysdr_b200.synth import synth_iq
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     world = 2
-    mp.spawn(_worker, args=(world, port, str(tmp_path), CPR), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), CPR, carry, steps), nprocs=world, join=True)
     P = _P()
     offs = receiver_offsets(P)
     C = P.IN_CHUNK_SIZE
