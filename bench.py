@@ -93,7 +93,7 @@ def measured_peak():
 
 
 def ncu_traffic():
-    """dram bytes per K1 launch from the committed ncu --set full capture, if one exists."""
+    """dram bytes per K1 launch from the committed ncu --set full captures, keyed by kernel name."""
     p = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(p):
         try:
@@ -305,25 +305,36 @@ def parity_check(P, offs, rank, world, dev, cpr=9, carry="peer"):
     env[2 * C:3 * C] = 4.0                                          # a burst whose AGC recovery crosses shard boundaries
     x = x * env
     single = ReceiverBank(P, offs, max_in=(rank + 1) * cpr * C, device=dev)
+    single.set_k1_mma(0)                                            # reference side: the FP32 tap-stationary K1
     ref_am, _, _ = single.process(x[:(rank + 1) * cpr * C], want_dc=False)
     m0 = -((-int(P.UP) * rank * cpr * C) // int(P.DOWN))
     ref = [a[m0:].clone() for a in ref_am]
     if world == 1:
-        b = ReceiverBank(P, offs, max_in=C, device=dev)
+        b = ReceiverBank(P, offs, max_in=cpr * C, device=dev)
+        b.set_k1_mma(2)                                             # the timed code path: tensor-core K1 (forced at this small size)
+        am, _, _ = b.process(x[:cpr * C], want_dc=False)
+        got = [a.clone() for a in am]
+        k1_kernels = [b.k1_last]
+        b2 = ReceiverBank(P, offs, max_in=C, device=dev)
         parts = [[] for _ in offs]
         for c in range(cpr):
-            am, _, _ = b.process(x[c * C:(c + 1) * C], want_dc=False)
+            am, _, _ = b2.process(x[c * C:(c + 1) * C], want_dc=False)
             for r in range(len(offs)):
                 parts[r].append(am[r].clone())
-        got = [torch.cat(p) for p in parts]
-        how = "whole-capture call vs %d chunk-at-a-time calls" % cpr
+        ref = [torch.cat(p) for p in parts]
+        k1_kernels.append(b2.k1_last)
+        del b2
+        how = ("whole-capture call (tensor-core K1, k1_last=%d) vs %d chunk-at-a-time calls (FP32 tap-stationary K1, k1_last=%d)"
+               % (k1_kernels[0], cpr, k1_kernels[1]))
     else:
         b = ReceiverBank(P, offs, max_in=(cpr + 1) * C, device=dev)
+        b.set_k1_mma(2)                                             # the timed code path: tensor-core K1 (forced at this small size)
         sh = ShardedCapture(b, P, rank, world, cpr, carry=carry)
         pl = sh.plan
         am, _, _ = sh.step(x[pl['first_sample']:pl['start'] + pl['n']])
         got = [a.clone() for a in am]
-        how = "each rank's time shard (%d blocks, O(1) AGC carry: %s) vs a local single-stream pass" % (cpr, sh.carry_how)
+        how = ("each rank's time shard (%d blocks, tensor-core K1 k1_last=%d, O(1) AGC carry: %s) vs a local single-stream pass "
+               "(FP32 tap-stationary K1)" % (cpr, b.k1_last, sh.carry_how))
     worst_rel, worst_snr = 0.0, 1e9
     for g, r in zip(got, ref):
         assert g.shape == r.shape, (g.shape, r.shape)
@@ -531,7 +542,12 @@ def run_own(args):
     k1_ms = tm["k1_ms"] / tm["calls"] if tm["calls"] else None      # rank 0 has no warm-up call: calls == steps
     achieved = ALGO_BYTES_PER_SAMPLE * n / (k1_ms * 1e-3) / 1e9 if k1_ms else None
     tr = ncu_traffic()
-    roof = {"bound": "hbm", "kernel": "k1_fast_kernel<4,11> (fused mix + polyphase decimate, 4 RX)",
+    k1_last = bank.k1_last
+    tr = (tr or {}).get({2: "k1_mma_kernel", 1: "k1_fast_kernel<4,11>"}.get(k1_last, ""), None) if tr else None
+    roof = {"bound": "hbm",
+            "kernel": {2: "k1_mma_kernel (fused mix + polyphase decimate of 4 RX as a split-TF32 GEMM on tcgen05: TMA -> tensor "
+                          "memory A operand, taps resident in shared memory; stream edges on one FP32 warp per CTA)",
+                       1: "k1_fast_kernel<4,11> (fused mix + polyphase decimate, 4 RX, FP32 tap-stationary)"}.get(k1_last, "k1_generic_kernel"),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
             "peak_source": which + ", burst figure",
             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * n, "k1_ms_per_launch": k1_ms,

@@ -199,6 +199,14 @@ int pysdr_bank_set_state(pysdr_bank *b, const void *host_blob, int64_t size, voi
 
 /* Which K1 variant the next process() will use: 0 generic, 1 tap-stationary fast path. */
 int pysdr_bank_k1_variant(const pysdr_bank *b);
+/* Tensor-core K1 (k1_mma.cu: the mix + polyphase decimation as a split-TF32 GEMM on tcgen05, samples streamed by TMA into
+ * tensor memory).  mode 0: never; 1 (default): calls whose interior has at least 8192 super-periods (whole captures, long
+ * segments) — short per-chunk calls keep the tap-stationary FP32 kernel; 2: whenever the geometry and alignment allow.
+ * The two kernels agree to ~1e-6 of peak, not bit for bit: pin mode 0 where chunked and whole-capture K1 outputs must be
+ * identical.  k1_last: the kernel the last call ran (0 generic, 1 tap-stationary, 2 tensor-core interior + edge tiles). */
+int pysdr_bank_set_k1_mma(pysdr_bank *b, int mode);
+int pysdr_bank_k1_mma_available(const pysdr_bank *b);
+int pysdr_bank_k1_last(const pysdr_bank *b);
 int pysdr_bank_force_generic(pysdr_bank *b, int on);
 /* K1-only bank (WFM video stage: LO + FIR at the RF rate, UP = DOWN = 1): process() stops after K1; its output is the
  * new-sample part of the complex memory (pysdr_bank_c_memory) and, when given, d_iq_bb. */

@@ -67,6 +67,9 @@ SIGNATURES = {
     "pysdr_bank_get_state": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "pysdr_bank_set_state": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "pysdr_bank_k1_variant": (c_int, [c_vp]),
+    "pysdr_bank_set_k1_mma": (c_int, [c_vp, c_int]),
+    "pysdr_bank_k1_mma_available": (c_int, [c_vp]),
+    "pysdr_bank_k1_last": (c_int, [c_vp]),
     "pysdr_bank_force_generic": (c_int, [c_vp, c_int]),
     "pysdr_bank_set_k1_only": (c_int, [c_vp, c_int]),
     "pysdr_bank_set_real_input": (c_int, [c_vp, c_int]),

@@ -195,6 +195,19 @@ class ReceiverBank:
     def force_generic(self, on=True):
         check(self.lib.pysdr_bank_force_generic(self.h, 1 if on else 0))
 
+    def set_k1_mma(self, mode):
+        """0: never use the tensor-core K1; 1 (default): for calls with >= 8192 interior super-periods; 2: whenever possible."""
+        check(self.lib.pysdr_bank_set_k1_mma(self.h, int(mode)))
+
+    @property
+    def k1_mma_available(self):
+        return bool(self.lib.pysdr_bank_k1_mma_available(self.h))
+
+    @property
+    def k1_last(self):
+        """Kernel of the last call: 0 generic, 1 tap-stationary FP32, 2 tensor-core interior + tap-stationary edge tiles."""
+        return self.lib.pysdr_bank_k1_last(self.h)
+
     @property
     def k1_variant(self):
         return self.lib.pysdr_bank_k1_variant(self.h)

@@ -883,6 +883,7 @@ __global__ void __launch_bounds__(256) seek_reset_kernel(float2 *C, i64 c_stride
 }
 
 // ------------------------------------------------------------------------------------------------
+#define K1_MMA_MIN_ROWS 8192                 /* interior super-periods from which the tensor-core K1 takes a call (mode 1) */
 struct pysdr_bank {
     pysdr_bank_config cfg;
     int lp, lp_pad, need, hc;
@@ -916,6 +917,9 @@ struct pysdr_bank {
     const float *pend_peaks;
     bool pending;
     bool force_generic;
+    K1MmaPlan *mma;                          // tensor-core K1 (k1_mma.cu); null when the geometry does not fit
+    int mma_mode;                            // 0 never, 1 calls of at least K1_MMA_MIN_ROWS interior super-periods, 2 whenever possible
+    int k1_last;                             // kernel of the last call: 0 generic, 1 tap-stationary, 2 tensor-core interior + edges
     // fused back (agc_back_fused_kernel): block peaks deferred from front into the back launch; grid barrier counter
     bool force_unfused;                      // testing: the stand-alone tail kernels
     bool defer_peaks, peaks_deferred;
@@ -1014,6 +1018,9 @@ extern "C" int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out)
     b->a_stride = (b->max_out + 1) / 2 * 2;
     b->g_dirty = true;
     b->force_generic = false;
+    b->mma = k1_fast_supported(cfg->up, cfg->down, b->lp, cfg->n_rx) ? k1_mma_plan_create(cfg->up, cfg->down, b->lp, cfg->n_rx) : nullptr;
+    b->mma_mode = 1; b->k1_last = -1;
+    if (const char *e = getenv("PYSDR_K1_MMA")) b->mma_mode = atoi(e);
     b->force_direct_fir = false;
     b->k1_only = false;
     b->k1_external = false; b->c_external = false; b->real_input = false;
@@ -1052,6 +1059,7 @@ extern "C" int pysdr_bank_destroy(pysdr_bank *b) {
     if (b->hc_h_out) cudaFreeHost(b->hc_h_out);
     cudaFree(b->hc_d_in); cudaFree(b->hc_d_iq); cudaFree(b->hc_d_am); cudaFree(b->hc_d_dc);
     if (!b->c_external) cudaFree(b->d_C);
+    k1_mma_plan_destroy(b->mma);
     cudaFree(b->d_hist); cudaFree(b->d_g); cudaFree(b->d_af); cudaFree(b->d_R);
     cudaFree(b->d_a); cudaFree(b->d_peaks); cudaFree(b->d_gains); cudaFree(b->d_agc); cudaFree(b->d_pll); cudaFree(b->d_bar);
     delete b;
@@ -1347,6 +1355,13 @@ extern "C" int pysdr_bank_force_generic(pysdr_bank *b, int on) {
     b->force_generic = on != 0;
     return PYSDR_OK;
 }
+extern "C" int pysdr_bank_set_k1_mma(pysdr_bank *b, int mode) {
+    if (!b || mode < 0 || mode > 2) { pysdr_set_error("set_k1_mma: mode 0 (never), 1 (large calls) or 2 (whenever possible)"); return PYSDR_ERR_ARG; }
+    b->mma_mode = mode;
+    return PYSDR_OK;
+}
+extern "C" int pysdr_bank_k1_mma_available(const pysdr_bank *b) { return (b && b->mma) ? 1 : 0; }
+extern "C" int pysdr_bank_k1_last(const pysdr_bank *b) { return b ? b->k1_last : -1; }
 extern "C" int pysdr_bank_k1_variant(const pysdr_bank *b) {
     if (!b) return -1;
     return (!b->force_generic && k1_fast_supported(b->cfg.up, b->cfg.down, b->lp, b->cfg.n_rx)) ? 1 : 0;
@@ -1380,6 +1395,7 @@ static int upload_folded_taps(pysdr_bank *b, cudaStream_t st) {
     }
     CUDA_TRY(cudaMemcpyAsync(b->d_g, g.data(), sizeof(float2) * g.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));      // g is a stack-owned staging vector
+    if (b->mma) { int rc = k1_mma_upload_taps(b->mma, g.data(), b->lp_pad, st); if (rc) return rc; }
     b->g_dirty = false;
     return PYSDR_OK;
 }
@@ -1486,11 +1502,21 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
     if (b->k1_external) {
         rc = PYSDR_OK;                       // C[r][hc .. hc+n_out) was written by the caller on this stream
     } else if (!b->force_generic && k1_fast_supported(c.up, c.down, b->lp, c.n_rx)) {
-        rc = k1_launch_fast(a, st);
-        b->launches += k1_fast_groups(b->lp, c.n_rx);
+        int used = 0, nl = 0;
+        rc = PYSDR_OK;
+        if (b->mma && b->mma_mode > 0) {
+            rc = k1_launch_mma(b->mma, a, b->mma_mode >= 2 ? 1 : K1_MMA_MIN_ROWS, st, &used, &nl);
+            b->launches += nl;
+        }
+        if (!rc && !used) {
+            rc = k1_launch_fast(a, st);
+            b->launches += k1_fast_groups(b->lp, c.n_rx);
+        }
+        b->k1_last = used ? 2 : 1;
     } else {
         rc = k1_launch_generic(a, st);
         b->launches++;
+        b->k1_last = 0;
     }
     if (rc) return rc;
     if ((rc = mark())) return rc;
@@ -1865,6 +1891,7 @@ extern "C" int pysdr_bank_get_timing(pysdr_bank *b, double out4[4], void *stream
         CUDA_TRY(cudaEventElapsedTime(&fr, b->evs[5 * i + 1], b->evs[5 * i + 2]));
         CUDA_TRY(cudaEventElapsedTime(&bk, b->evs[5 * i + 3], b->evs[5 * i + 4]));
         out4[0] += k1; out4[1] += fr; out4[2] += bk; out4[3] += 1.0;
+        if (getenv("PYSDR_TIMING_TRACE")) fprintf(stderr, "timing step %zu: k1 %.4f front_rest %.4f back %.4f ms\n", i, k1, fr, bk);
     }
     for (cudaEvent_t e : b->evs) cudaEventDestroy(e);
     b->evs.clear();

@@ -105,6 +105,17 @@ int k1_fast_lp_pad(int lp);
 // # of kernel launches the fast path needs for n_rx receivers (receiver groups of 1/2/4)
 int k1_fast_groups(int lp, int n_rx);
 
+// ---- K1 tensor-core variant (k1_mma.cu): tcgen05 TF32 split GEMM, interior of large calls ------------------------------
+struct K1MmaPlan;
+int k1_mma_supported(int up, int down, int lp, int n_rx);
+K1MmaPlan *k1_mma_plan_create(int up, int down, int lp, int n_rx);
+void k1_mma_plan_destroy(K1MmaPlan *p);
+// g_host: the folded taps [n_rx][up][lp_pad] exactly as uploaded for k1_fast
+int k1_mma_upload_taps(K1MmaPlan *p, const float2 *g_host, int lp_pad, cudaStream_t st);
+// Runs the call through the tensor-core kernel.  *used = 0 and nothing launched when the call is too small or its
+// geometry/alignment does not fit; the caller then takes the tap-stationary path.
+int k1_launch_mma(K1MmaPlan *p, const K1Args &a, i64 min_rows, cudaStream_t st, int *used, int *launches);
+
 // ---- K2 fast path (k2_fftconv.cu) ---------------------------------------------------------------------
 struct FftConvArgs {
     const float2 *C;          // complex memory + new samples, rows of c_stride: C[rx][0..hc+n_out)

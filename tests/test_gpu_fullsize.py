@@ -27,6 +27,7 @@ def cfg2():
     x = synth_iq(n, P.SRATE, offs, MODES, seed=31, device="cuda")
     bank = ReceiverBank(P, offs, max_in=n)
     am, iq, _ = bank.process(x, want_dc=False)
+    assert bank.k1_last == 2, "the whole-capture call should run the tensor-core K1"
     out = dict(P=P, Po=Po, x=x, n=n, offs=offs, n_out=bank.n_out, am=[a.clone() for a in am], iq=[q.clone() for q in iq],
                trace=bank.agc_trace())
     del bank
@@ -54,23 +55,45 @@ def test_cfg2_full_size_k1_is_exactly_linear_under_power_of_two_scaling(cfg2):
         assert torch.equal(iq[r], cfg2['iq'][r] * 4.0)     # scaling by 2^k commutes with every rounding in K1
 
 
-def test_cfg2_full_size_segments_equal_whole(cfg2):
+@pytest.mark.parametrize("k1_mma", [0, 1])
+def test_cfg2_full_size_segments_equal_whole(cfg2, k1_mma):
+    """k1_mma = 0 (tap-stationary FP32 K1 pinned): the baseband of uneven segments equals the whole-capture call BIT FOR BIT
+    (the per-output arithmetic does not depend on how the stream is cut).  k1_mma = 1 (default: tensor-core K1 on calls of
+    >= 8192 interior super-periods, so the long segments take it and the single-chunk segment does not): the two K1 kernels
+    and the two row alignments round differently, agreement is 5e-6 of peak (split-TF32 products, fp32 accumulation)."""
     from pysdr_b200.bank import ReceiverBank
     P = cfg2['P']
     C = P.IN_CHUNK_SIZE
     cuts = [0, 700, 701, 1999, N_CHUNKS]                   # uneven segments, one of them a single chunk
+    if k1_mma == 0:
+        whole = ReceiverBank(P, cfg2['offs'], max_in=cfg2['n'])
+        whole.set_k1_mma(0)
+        w_am, w_iq, _ = whole.process(cfg2['x'], want_dc=False)
+        assert whole.k1_last == 1
+        ref_am, ref_iq = [a.clone() for a in w_am], [q.clone() for q in w_iq]
+        del whole
+    else:
+        ref_am, ref_iq = cfg2['am'], cfg2['iq']
     bank = ReceiverBank(P, cfg2['offs'], max_in=1300 * C)
+    bank.set_k1_mma(k1_mma)
     pos = 0
+    used = []
     for a, b in zip(cuts[:-1], cuts[1:]):
         am, iq, _ = bank.process(cfg2['x'][a * C:b * C], want_dc=False)
+        used.append(bank.k1_last)
         k = bank.n_out
         for r in range(4):
-            assert torch.equal(iq[r], cfg2['iq'][r][pos:pos + k])                     # K1: bit-exact
-            ref = cfg2['am'][r][pos:pos + k]
+            if k1_mma == 0:
+                assert torch.equal(iq[r], ref_iq[r][pos:pos + k])                        # K1: bit-exact
+            else:
+                e = (iq[r] - ref_iq[r][pos:pos + k]).abs().max().item() / ref_iq[r].abs().max().item()
+                assert e < 5e-6, (r, a, b, e)
+            ref = ref_am[r][pos:pos + k]
             err = (am[r] - ref).abs().max().item() / ref.abs().max().item()
             assert err < 2e-5, (r, a, b, err)                                            # K2: FFT block alignment differs
         pos += k
     assert pos == cfg2['n_out']
+    assert used == ([1, 1, 1, 1] if k1_mma == 0 else [2, 1, 2, 2]), used
 
 
 @pytest.mark.parametrize("blk", [1, 1406, 2805])
