@@ -183,6 +183,12 @@ int pysdr_bank_agc_summary_push(pysdr_bank *b, int64_t skip_blocks, const uint64
                                 void *stream);
 int pysdr_bank_process_back_xchg(pysdr_bank *b, const uint64_t *peer_bases, int world, int rank, uint64_t seq, int64_t skip_blocks,
                                  float *d_am, float *d_am_dc, int64_t out_stride, void *stream);
+/* A whole time shard in the same three launches as a single-GPU step: process_front, then ONE back kernel that computes the
+ * block peaks, pushes this rank's summaries (agc_summary_push), waits for the earlier ranks' (process_back_xchg), scans and
+ * applies the gains.  skip_blocks = warm-up blocks at the head of d_iq whose outputs rebuild the filter memories only. */
+int pysdr_bank_process_shard_xchg(pysdr_bank *b, const void *d_iq, int64_t n_in, int halo_in_place, void *d_iq_bb,
+                                  const uint64_t *peer_bases, int world, int rank, uint64_t seq, int64_t skip_blocks,
+                                  float *d_am, float *d_am_dc, int64_t out_stride, int64_t *n_out, void *stream);
 /* Testing: on != 0 runs the tail as stand-alone kernels (block peaks, AGC scan, gain application, seek reset) instead of the
  * fused back kernel (one co-resident grid, two grid barriers). */
 int pysdr_bank_force_unfused(pysdr_bank *b, int on);

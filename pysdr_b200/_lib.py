@@ -88,6 +88,8 @@ SIGNATURES = {
     "pysdr_xchg_bytes": (c_i64, [c_int, c_int]),
     "pysdr_bank_agc_summary_push": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, c_u64, c_vp]),
     "pysdr_bank_process_back_xchg": (c_int, [c_vp, c_vp, c_int, c_int, c_u64, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "pysdr_bank_process_shard_xchg": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_int, c_u64, c_i64, c_vp, c_vp, c_i64,
+                                              ctypes.POINTER(c_i64), c_vp]),
     "pysdr_bank_agc_trace": (c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),
     "pysdr_lfilter_set_mode": (c_int, [c_int]),
     "pysdr_lfilter": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),

@@ -598,11 +598,11 @@ __device__ __forceinline__ unsigned long long *xchg_counts(double *base, int wor
     return xchg_acks(base, world, n_rx) + world;
 }
 
-__global__ void __launch_bounds__(SUM_THREADS) agc_summary_push_kernel(const AgcState *__restrict__ state, const float *__restrict__ peaks,
-                                                                       i64 peaks_stride, i64 skip, i64 n_blocks, const XchgPeers peers,
-                                                                       int world, int rank, int n_rx, unsigned long long seq) {
+// block-wide (SUM_THREADS threads): summary of receiver rx -> the later ranks' slots; the last receiver's CTA raises the flags
+__device__ void agc_summary_push_rx(const AgcState *__restrict__ state, const float *__restrict__ peaks, i64 peaks_stride, i64 skip,
+                                    i64 n_blocks, const XchgPeers &peers, int world, int rank, int n_rx, unsigned long long seq, int rx) {
     __shared__ double s_o[PYSDR_AGC_SUMMARY_LEN];
-    const int rx = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     agc_summary_rx(state, peaks, peaks_stride, skip, n_blocks, rx, s_o);        // block-wide; s_o valid after the barrier inside
     const int slot = (int)(seq % XCHG_DEPTH);
     const size_t off = (size_t)slot * xchg_slot_doubles(world, n_rx) + ((size_t)rank * n_rx + rx) * PYSDR_AGC_SUMMARY_LEN;
@@ -624,6 +624,13 @@ __global__ void __launch_bounds__(SUM_THREADS) agc_summary_push_kernel(const Agc
                 st_release_sys_u64(xchg_flags(peers.base[q], world, n_rx) + (size_t)slot * world + rank, seq);
         }
     }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SUM_THREADS) agc_summary_push_kernel(const AgcState *__restrict__ state, const float *__restrict__ peaks,
+                                                                       i64 peaks_stride, i64 skip, i64 n_blocks, const XchgPeers peers,
+                                                                       int world, int rank, int n_rx, unsigned long long seq) {
+    agc_summary_push_rx(state, peaks, peaks_stride, skip, n_blocks, peers, world, rank, n_rx, seq, blockIdx.x);
 }
 
 // consumer side, one thread per receiver: wait for the earlier ranks' flags of step seq in the LOCAL buffer
@@ -777,6 +784,7 @@ struct BackArgs {
     ApplyKinds kinds;
     unsigned long long *bar; unsigned long long bar_base;
     XchgWait x;                                      // do_enter == 2: the peer-memory exchange buffers and the step number
+    int do_push; i64 push_skip;                      // also compute this shard's summaries (blocks >= push_skip) and push them first
 };
 
 #define BACK_THREADS AGC_THREADS
@@ -799,6 +807,9 @@ __global__ void __launch_bounds__(BACK_THREADS) agc_back_fused_kernel(const Back
         grid_barrier(p.bar, p.bar_base + gridDim.x);
     }
     if ((int)blockIdx.x < p.n_rx) {
+        if (p.do_push && p.x.rank < p.x.world - 1)    // the later ranks wait for this: before anything this rank waits for
+            agc_summary_push_rx(p.scan.state, p.peaks, p.peaks_row, p.push_skip, p.n_blocks, p.x.peers, p.x.world, p.x.rank, p.n_rx,
+                                p.x.seq, blockIdx.x);
         if (p.do_enter) {
             if (threadIdx.x == 0) {
                 if (p.do_enter == 2) {               // summaries pushed by the earlier ranks over NVLink: wait for their flags
@@ -1659,7 +1670,7 @@ static int launch_block_peaks(pysdr_bank *b, float *d_peaks, const StateArgs &sa
 // bank is the stereo WFM2 resampler (its L/R peaks are linked between the stages) or the stand-alone kernels are forced.
 static int back_impl(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, int64_t skip_blocks, const double *d_sums,
                      int n_before, bool enter, float *d_am, float *d_am_dc, int64_t out_stride, cudaStream_t st,
-                     const XchgWait *xw = nullptr) {
+                     const XchgWait *xw = nullptr, bool push = false) {
     if (!b || !b->pending) { pysdr_set_error("process_back without process_front"); return PYSDR_ERR_STATE; }
     if (!d_am) { pysdr_set_error("process_back: d_am is null"); return PYSDR_ERR_ARG; }
     const pysdr_bank_config &c = b->cfg;
@@ -1729,6 +1740,7 @@ static int back_impl(pysdr_bank *b, const float *d_prev_peaks, int64_t n_prev, i
         p.do_peaks = b->peaks_deferred ? 1 : 0;
         p.do_enter = enter ? (xw ? 2 : 1) : 0; p.n_before = n_before; p.sums = d_sums; p.n_rx = c.n_rx;
         if (xw) p.x = *xw;
+        p.do_push = (push && xw) ? 1 : 0; p.push_skip = skip_blocks;
         p.a = (const float *)b->d_a; p.a_row = 2 * b->a_stride;
         p.peaks = (float *)b->pend_peaks; p.peaks_row = n_blocks;
         p.n_blocks = n_blocks; p.B0 = b->pend_B0; p.in_chunk = c.in_chunk; p.m0 = b->pend_m0; p.n_out = n_out;
@@ -1842,6 +1854,24 @@ extern "C" int pysdr_bank_process_back_xchg(pysdr_bank *b, const uint64_t *peer_
     if (int rc = xchg_peers(peer_bases, world, rank, seq, &xw.peers, "process_back_xchg")) return rc;
     xw.world = world; xw.rank = rank; xw.seq = seq;
     return back_impl(b, nullptr, 0, skip_blocks, nullptr, rank, true, d_am, d_am_dc, out_stride, (cudaStream_t)stream, &xw);
+}
+
+// One time shard in three launches (K1, AF filter, fused back): the back kernel computes the block peaks, pushes this rank's
+// AGC summaries to the later ranks, waits for the earlier ranks' summaries, scans and applies the gains.
+extern "C" int pysdr_bank_process_shard_xchg(pysdr_bank *b, const void *d_iq, int64_t n_in, int halo_in_place, void *d_iq_bb,
+                                             const uint64_t *peer_bases, int world, int rank, uint64_t seq, int64_t skip_blocks,
+                                             float *d_am, float *d_am_dc, int64_t out_stride, int64_t *n_out, void *stream) {
+    XchgWait xw;
+    if (!b) { pysdr_set_error("null bank"); return PYSDR_ERR_ARG; }
+    if (int rc = xchg_peers(peer_bases, world, rank, seq, &xw.peers, "process_shard_xchg")) return rc;
+    xw.world = world; xw.rank = rank; xw.seq = seq;
+    if (b->stereo || b->force_unfused) { pysdr_set_error("process_shard_xchg needs the fused back kernel"); return PYSDR_ERR_STATE; }
+    b->defer_peaks = true;
+    int rc = pysdr_bank_process_front(b, d_iq, n_in, halo_in_place, d_iq_bb, out_stride, b->d_peaks, n_out, stream);
+    b->defer_peaks = false;
+    if (rc) return rc;
+    if (b->pend_n_out == 0) { pysdr_set_error("process_shard_xchg: the shard produced no output"); return PYSDR_ERR_ARG; }
+    return back_impl(b, nullptr, 0, skip_blocks, nullptr, rank, true, d_am, d_am_dc, out_stride, (cudaStream_t)stream, &xw, true);
 }
 
 extern "C" int pysdr_bank_force_unfused(pysdr_bank *b, int on) {

@@ -144,6 +144,24 @@ class PeerCarry:
                                                  _stream_ptr()))
         return b.views()
 
+    def shard(self, x, skip_blocks, halo_in_place, want_dc=False):
+        """front + push + back in the three launches of a single-GPU step (pysdr_bank_process_shard_xchg)."""
+        import ctypes
+        from ._lib import check
+        from .bank import _stream_ptr
+        b = self.bank
+        b._check_input(x)
+        b.sync_demod()
+        self.seq += 1
+        n_out = ctypes.c_int64(0)
+        check(b.lib.pysdr_bank_process_shard_xchg(b.h, ctypes.c_void_p(x.data_ptr()), x.numel(), 1 if halo_in_place else 0,
+                                                  b._iq_copy_ptr(), self.bases, self.world, self.rank, self.seq, int(skip_blocks),
+                                                  ctypes.c_void_p(b._am.data_ptr()),
+                                                  ctypes.c_void_p(b._am_dc.data_ptr()) if want_dc else None, b.max_out,
+                                                  ctypes.byref(n_out), _stream_ptr()))
+        b.n_out = n_out.value
+        return b.views()
+
 
 class ShardedCapture:
     """Per-rank driver of one time shard on the GPU bank (used by bench.py for N>1 and by receiver-level tools).
@@ -217,12 +235,18 @@ class ShardedCapture:
         if self.world == 1:                                                  # nothing to exchange: the plain whole-capture call
             b.seek(0)
             return b.process(xbuf[self.plan['lead']:], want_dc=want_dc)
-        self.front(xbuf, copy_own=False)
         w = self.plan['warm_chunks']
         if self.peer is not None:
-            am, iq, dc = self.peer.push_and_back(w, want_dc)
+            p = self.plan
+            if w:
+                b.seek(p['start'] - w * int(self.P.IN_CHUNK_SIZE))
+                am, iq, dc = self.peer.shard(xbuf[p['halo']:], w, p['halo'] > 0, want_dc)
+            else:
+                b.seek(0)
+                am, iq, dc = self.peer.shard(xbuf[p['lead']:], 0, False, want_dc)
             k = self.skip_out
             return [a[k:] for a in am], [a[k:] for a in iq], [a[k:] for a in dc]
+        self.front(xbuf, copy_own=False)
         check(b.lib.pysdr_bank_agc_summary(b.h, w, ctypes.c_void_p(self.summary.data_ptr()), _stream_ptr()))
         exchange_agc_summaries(self.summary, self.all_sum, self.world)       # the one collective of the path
         am, iq, dc = b.process_back_carry(self.all_sum, self.rank, want_dc=want_dc, skip_blocks=w)
