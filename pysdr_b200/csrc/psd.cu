@@ -10,6 +10,7 @@
 #include "common.cuh"
 #define FFT_PACKED 0                     /* see fft_smem.cuh: this kernel sits at its register limit */
 #include "fft_smem.cuh"
+#include "psd_fast.cuh"
 
 struct pysdr_psd {
     int chunk, nfft, hop;
@@ -21,6 +22,7 @@ struct pysdr_psd {
     int sub;               // frame f starts at (f / sub) * hop + sub_off[f % sub]   (sub = 1, sub_off = {0}: plain hop)
     int sub_off[8];
     int flags;             // PYSDR_PSD_RAW | PYSDR_PSD_FLIP
+    float2 *d_tw;          // twiddle tables of the fast path (psd_fast.cu), or null
 };
 
 struct PsdSteps { int sub; int off[8]; };
@@ -81,8 +83,19 @@ psd_frames_kernel(const void *__restrict__ xv, const float *__restrict__ win, in
     }
 }
 
-// out[line][fftshift(bin(p))] = dB( sum_split part[p] / (navg * wsum2) )
+// position -> bin of the fast path's pass order (radix-16 passes first, the odd radix last: psd_fast.cu)
 template <int N>
+__device__ __forceinline__ int fast_pos_to_freq(int p) {
+    constexpr int LG = FftPlan<N>::LOG2;
+    constexpr int A = (LG % 4 == 0) ? LG / 4 - 1 : LG / 4;
+    int k = 0, mul = 1, len = N;
+#pragma unroll
+    for (int i = 0; i < A; ++i) { len /= 16; k += (p / len) * mul; p %= len; mul *= 16; }
+    return k + p * mul;
+}
+
+// out[line][fftshift(bin(p))] = dB( sum_split part[p] / (navg * wsum2) )
+template <int N, bool FAST = false>
 __global__ void psd_finalize_kernel(const float *__restrict__ part, int n_split, float scale, int dB, int flags,
                                     float *__restrict__ out) {
     const int line = blockIdx.y;
@@ -93,7 +106,7 @@ __global__ void psd_finalize_kernel(const float *__restrict__ part, int n_split,
     for (int sp = 0; sp < n_split; ++sp) sum += q[(size_t)sp * N];
     float v = sum * scale;
     if (dB) v = 10.f * log10f((flags & PYSDR_PSD_RAW) ? v : fmaxf(v, 1.0e-30f));
-    const int k = fft_pos_to_freq<N>(p);
+    const int k = FAST ? fast_pos_to_freq<N>(p) : fft_pos_to_freq<N>(p);
     int col = (k + N / 2) % N;                                           // fftshift
     if (flags & PYSDR_PSD_FLIP) col = N - 1 - col;                       // np.flipud of the shifted line (rtty.py:843)
     out[(size_t)line * N + col] = v;
@@ -111,6 +124,7 @@ extern "C" int pysdr_psd_create(int32_t chunk, int32_t nfft, int32_t hop, const 
     for (int i = 0; i < chunk; ++i) p->wsum2 += (double)window[i] * (double)window[i];
     p->d_part = nullptr; p->part_cap = 0; p->launches = 0;
     p->sub = 1; p->flags = 0;
+    p->d_tw = nullptr;
     for (int i = 0; i < 8; ++i) p->sub_off[i] = 0;
     if (cudaMalloc(&p->d_win, sizeof(float) * chunk) != cudaSuccess) {
         pysdr_set_error("psd_create: cudaMalloc failed");
@@ -118,13 +132,19 @@ extern "C" int pysdr_psd_create(int32_t chunk, int32_t nfft, int32_t hop, const 
         return PYSDR_ERR_CUDA;
     }
     CUDA_TRY(cudaMemcpy(p->d_win, window, sizeof(float) * chunk, cudaMemcpyHostToDevice));
+    if (psd_fast_supported(nfft)) {
+        std::vector<float2> tw(psd_fast_table_elems(nfft));
+        psd_fast_fill_table(nfft, tw.data());
+        CUDA_TRY(cudaMalloc(&p->d_tw, sizeof(float2) * tw.size()));
+        CUDA_TRY(cudaMemcpy(p->d_tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
+    }
     *out = p;
     return PYSDR_OK;
 }
 
 extern "C" int pysdr_psd_destroy(pysdr_psd *p) {
     if (!p) return PYSDR_OK;
-    cudaFree(p->d_win); cudaFree(p->d_part);
+    cudaFree(p->d_win); cudaFree(p->d_part); cudaFree(p->d_tw);
     delete p;
     return PYSDR_OK;
 }
@@ -152,6 +172,17 @@ static int psd_launch(pysdr_psd *p, const void *d_x, int is_complex, int navg, i
     if (smem > 48 * 1024) {
         CUDA_TRY(cudaFuncSetAttribute(psd_frames_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(psd_frames_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (n_split == 1 && p->d_tw && p->sub == 1 && N >= 512 && N <= 8192 && !getenv("PYSDR_PSD_GENERIC")) {
+        // fast path (psd_fast.cu): enough lines to fill the GPU with one CTA per line, plain hop stepping
+        int rc = psd_fast_launch(N, d_x, is_complex, p->d_win, p->chunk, p->hop, navg, n_lines, p->d_tw, p->d_part, st);
+        if (rc) return rc;
+        const float scale = (p->flags & PYSDR_PSD_RAW) ? 1.0f / (float)navg : (float)(1.0 / ((double)navg * p->wsum2));
+        dim3 g2((unsigned)((N + 255) / 256), (unsigned)n_lines);
+        psd_finalize_kernel<N, true><<<g2, 256, 0, st>>>(p->d_part, 1, scale, dB, p->flags, d_out);
+        LAUNCH_CHECK();
+        p->launches += 2;
+        return PYSDR_OK;
     }
     dim3 grid((unsigned)n_split, (unsigned)n_lines);
     PsdSteps steps;

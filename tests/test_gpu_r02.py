@@ -216,3 +216,41 @@ def test_fused_back_kernel_equals_standalone_tail_kernels(modes):
     for r in range(n_rx):
         assert torch.equal(banks[0]._keep[r], banks[1]._keep[r])
     assert banks[0].get_state() == banks[1].get_state()
+
+
+@pytest.mark.parametrize("nfft,chunk,overlap,cplx", [(8192, 8192, 0.5, True), (8192, 4096, 0.5, False), (4096, 4096, 0.5, True),
+                                                      (2048, 1500, 0.25, True), (1024, 1024, 0.0, True), (512, 512, 0.75, False)])
+def test_psd_fast_path_many_lines(nfft, chunk, overlap, cplx):
+    """The waterfall of a long capture (>= 296 lines: one persistent CTA per line, psd_fast.cu: first radix-16 pass on the
+    loaded registers, table twiddles, last radix fused with |X|^2) against numpy (reference Plotting.py:376-377,462 /
+    sigs/iq.py:75-79: periodic Hann, |FFT|^2 / sum w^2, mean over the line's frames, 10 log10, fftshift) and against the
+    generic kernel."""
+    import os
+    from pysdr_b200 import sig_proc as dsp
+    navg, lines = 3, 320
+    sp = dsp.spectrum(48., chunk, nfft, overlap)
+    hop = sp.new_samps
+    n = chunk + hop * (navg * lines - 1)
+    rng = np.random.default_rng(nfft + chunk)
+    t = np.arange(n)
+    x = (rng.normal(size=n) + 1j * rng.normal(size=n)) * 0.05 + np.exp(2j * np.pi * 0.1234 * t) + 0.3 * np.exp(-2j * np.pi * 0.31 * t)
+    if not cplx:
+        x = x.real
+    xd = torch.from_numpy(x.astype(np.complex64)).cuda()
+    got = sp.waterfall(xd, navg, dB=False)
+    assert got.shape == (lines, nfft)
+    os.environ["PYSDR_PSD_GENERIC"] = "1"
+    try:
+        gen = sp.waterfall(xd, navg, dB=False)
+    finally:
+        del os.environ["PYSDR_PSD_GENERIC"]
+    w = sp.win.astype(np.float64)
+    xs = x.astype(np.complex64).astype(np.complex128)
+    for line in (0, 1, lines // 2, lines - 1):
+        ref = np.zeros(nfft)
+        for f in range(navg):
+            s0 = (line * navg + f) * hop
+            ref += np.abs(np.fft.fft(xs[s0:s0 + chunk] * w, nfft)) ** 2
+        ref = np.fft.fftshift(ref / (navg * np.sum(w * w)))
+        assert_parity(got[line], ref.astype(np.float32), "fast psd line %d" % line)
+        assert_parity(got[line], gen[line], "fast vs generic psd line %d" % line, rel_tol=2e-5, snr_min=90)
