@@ -327,6 +327,13 @@ int pysdr_waterfall_push(float *d_wf, int32_t nfft, int32_t ncols, int32_t cnt, 
                          int32_t npsd, int32_t roll_bins, float pan_dr, float *d_img, float *d_bkgnd,
                          float *d_scratch, void *stream);
 
+/* Peak picker of the panadapter (reference Plotting.py:594: scipy.signal.find_peaks(PSD2, distance=PEAK_DIST/df,
+ * height=bkgnd+10)) on the device: strict local maxima (plateaus at their middle), height >= *d_bkgnd + height_above_bkgnd
+ * (d_bkgnd = the median pysdr_waterfall_push left on the device; NULL: height >= min_height), then the distance rule from the
+ * highest peak down.  d_peaks receives at most 4096 ascending indices, d_count[0] their number.  One small launch, no host
+ * round trip between the waterfall update and the peak list. */
+int pysdr_find_peaks(const float *d_x, int32_t n, const float *d_bkgnd, float height_above_bkgnd, float min_height, float distance,
+                     int32_t *d_peaks, int32_t *d_count, void *stream);
 /* Colour mapping of the waterfall image (reference Plotting.py:139-142: 256-entry 'jet' lookup table on the image
  * item): d_rgba[i] = lut[round(255*(img[i]-lo)/(hi-lo))], [lo,hi] = [max-pan_dr, max] as left by
  * pysdr_waterfall_push in d_scratch/d_bkgnd.  d_lut256: 256 x RGBA8, d_rgba: n x RGBA8. */

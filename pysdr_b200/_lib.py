@@ -90,6 +90,7 @@ SIGNATURES = {
     "pysdr_bank_process_back_xchg": (c_int, [c_vp, c_vp, c_int, c_int, c_u64, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "pysdr_bank_process_shard_xchg": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_int, c_u64, c_i64, c_vp, c_vp, c_i64,
                                               ctypes.POINTER(c_i64), c_vp]),
+    "pysdr_find_peaks": (c_int, [c_vp, ctypes.c_int32, c_vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp]),
     "pysdr_bank_agc_trace": (c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),
     "pysdr_lfilter_set_mode": (c_int, [c_int]),
     "pysdr_lfilter": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),

@@ -328,6 +328,93 @@ __global__ void wf_rgba_kernel(const float *__restrict__ img, i64 n, const float
     }
 }
 
+// ---- peak picker (reference Plotting.py:594: scipy.signal.find_peaks(PSD2, distance=dist, height=bkgnd+10)) ------------------
+// One CTA.  (1) strict local maxima, a plateau reported at the middle of its flat top (scipy _local_maxima_1d);
+// (2) height >= min_height; (3) distance: from the highest peak down, a kept peak removes every candidate closer than
+// ceil(distance) samples (scipy _select_by_peak_distance; equal heights: the one at the higher index wins, which is what a
+// stable ascending argsort walked from the top gives).  Candidates are sorted by (height, index) with a bitonic sort in
+// shared memory; the greedy sweep is the only sequential part (one thread, a few hundred candidates at display rate).
+#define PK_MAX 4096
+__global__ void __launch_bounds__(1024) find_peaks_kernel(const float *__restrict__ x, int n, const float *__restrict__ bk, float height_above_bk,
+                                                          float min_height_abs, int use_bk, int distance, int *__restrict__ peaks,
+                                                          int *__restrict__ count) {
+    __shared__ float s_h[PK_MAX];
+    __shared__ int s_i[PK_MAX];
+    __shared__ unsigned char s_keep[PK_MAX];
+    __shared__ int s_n;
+    const int tid = threadIdx.x;
+    const float hmin = use_bk ? bk[0] + height_above_bk : min_height_abs;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    for (int i = 1 + tid; i < n - 1; i += blockDim.x) {
+        const float v = x[i];
+        if (!(x[i - 1] < v)) continue;
+        int ahead = i + 1;
+        while (ahead < n - 1 && x[ahead] == v) ++ahead;
+        if (x[ahead] < v) {
+            const int mid = (i + ahead - 1) / 2;
+            if (v >= hmin) {
+                const int k = atomicAdd(&s_n, 1);
+                if (k < PK_MAX) { s_h[k] = v; s_i[k] = mid; }
+            }
+        }
+    }
+    __syncthreads();
+    const int m = s_n < PK_MAX ? s_n : PK_MAX;
+    int m2 = 1;
+    while (m2 < m) m2 <<= 1;
+    for (int k = m + tid; k < m2; k += blockDim.x) { s_h[k] = 3.0e38f; s_i[k] = 0x7fffffff; }      // padding sorts to the end
+    __syncthreads();
+    // ascending by index first (the candidates were appended in arbitrary order), used for the neighbour walks
+    for (int size = 2; size <= m2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < m2; t += blockDim.x) {
+                const int partner = t ^ stride;
+                if (partner > t) {
+                    const bool up = (t & size) == 0;
+                    const bool gt = s_i[t] > s_i[partner];
+                    if (gt == up) {
+                        const float th = s_h[t]; s_h[t] = s_h[partner]; s_h[partner] = th;
+                        const int ti = s_i[t]; s_i[t] = s_i[partner]; s_i[partner] = ti;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (int k = tid; k < m; k += blockDim.x) s_keep[k] = 1;
+    __syncthreads();
+    if (tid == 0) {
+        // greedy by priority: repeatedly take the highest remaining candidate.  m is small; a selection loop keeps the
+        // index-sorted order intact (no second sort, no permutation array).
+        if (distance > 1) {
+            for (int round = 0; round < m; ++round) {
+                int best = -1;
+                float bh = -3.0e38f;
+                for (int k = 0; k < m; ++k)
+                    if (s_keep[k] == 1 && s_h[k] >= bh) { bh = s_h[k]; best = k; }      // >= : ties go to the higher index
+                if (best < 0) break;
+                s_keep[best] = 2;                                                       // kept for good
+                for (int k = best - 1; k >= 0 && s_i[best] - s_i[k] < distance; --k) if (s_keep[k] == 1) s_keep[k] = 0;
+                for (int k = best + 1; k < m && s_i[k] - s_i[best] < distance; ++k) if (s_keep[k] == 1) s_keep[k] = 0;
+            }
+        }
+        int c = 0;
+        for (int k = 0; k < m; ++k)
+            if (s_keep[k]) peaks[c++] = s_i[k];
+        count[0] = c;
+    }
+}
+
+extern "C" int pysdr_find_peaks(const float *d_x, int32_t n, const float *d_bkgnd, float height_above_bkgnd, float min_height,
+                                float distance, int32_t *d_peaks, int32_t *d_count, void *stream) {
+    if (!d_x || !d_peaks || !d_count || n < 3) { pysdr_set_error("find_peaks: bad arguments"); return PYSDR_ERR_ARG; }
+    int dist = distance > 1.0f ? (int)ceilf(distance) : 1;
+    find_peaks_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_x, n, d_bkgnd, height_above_bkgnd, min_height, d_bkgnd ? 1 : 0, dist, d_peaks,
+                                                            d_count);
+    LAUNCH_CHECK();
+    return PYSDR_OK;
+}
+
 extern "C" int pysdr_waterfall_rgba(const float *d_img, int64_t n, const float *d_bkgnd, const float *d_scratch, int32_t nfft,
                                     int32_t ncols, float pan_dr, const void *d_lut256, void *d_rgba, void *stream) {
     if (!d_img || !d_bkgnd || !d_scratch || !d_lut256 || !d_rgba || n < 0) { pysdr_set_error("waterfall_rgba: bad arguments"); return PYSDR_ERR_ARG; }

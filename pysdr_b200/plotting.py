@@ -7,7 +7,6 @@ import ctypes
 
 import numpy as np
 import torch
-from scipy import signal
 
 from . import _lib, sig_proc as dsp
 from ._lib import check
@@ -64,6 +63,8 @@ class three_box_compute:
         self.pk_frqs = np.zeros(0)
         self.lut = torch.from_numpy(lookup_table(jet(64), 256)).to(dev)                # Plotting.py:139-141
         self.rgba = torch.empty((n, ncols, 4), dtype=torch.uint8, device=dev)
+        self.pk_idx = torch.zeros(4096, dtype=torch.int32, device=dev)
+        self.pk_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def image_rgba(self, npsd=None):
         """RGBA8 waterfall image of the last plot() through the jet lookup table, on the device."""
@@ -98,9 +99,15 @@ class three_box_compute:
                                             ctypes.c_void_p(line.data_ptr()), len(PSD), nbins, float(P.PAN_DR),
                                             ctypes.c_void_p(self.img.data_ptr()), ctypes.c_void_p(self.bk.data_ptr()),
                                             ctypes.c_void_p(self.scratch.data_ptr()), _stream_ptr()))
-        bkgnd = float(self.bk.item())
-        PSD2 = self.scratch[n * self.ncols:n * self.ncols + n].cpu().numpy()            # row means over the last wf_cnt lines
+        # Plotting.py:594 find_peaks(PSD2, distance=PEAK_DIST/df, height=bkgnd+10) on the device: PSD2 (row means over the last
+        # wf_cnt lines) and the median never leave it; only the peak indices come back, with the background, in one read
+        PSD2 = self.scratch[n * self.ncols:n * self.ncols + n]
         dist = P.PEAK_DIST / self.psd.df
-        peaks, _ = signal.find_peaks(PSD2, distance=dist, height=bkgnd + 10)            # Plotting.py:594
+        check(self.lib.pysdr_find_peaks(ctypes.c_void_p(PSD2.data_ptr()), n, ctypes.c_void_p(self.bk.data_ptr()), 10.0, 0.0,
+                                        float(dist), ctypes.c_void_p(self.pk_idx.data_ptr()), ctypes.c_void_p(self.pk_cnt.data_ptr()),
+                                        _stream_ptr()))
+        cnt = int(self.pk_cnt.item())
+        peaks = self.pk_idx[:cnt].cpu().numpy().astype(np.int64)
+        bkgnd = float(self.bk.item())
         self.pk_frqs = frq[peaks]
         return dict(frq=frq, PSD=PSD, image=self.img[:len(PSD)], bkgnd=bkgnd, peaks=peaks, pk_frqs=self.pk_frqs)

@@ -254,3 +254,37 @@ def test_psd_fast_path_many_lines(nfft, chunk, overlap, cplx):
         ref = np.fft.fftshift(ref / (navg * np.sum(w * w)))
         assert_parity(got[line], ref.astype(np.float32), "fast psd line %d" % line)
         assert_parity(got[line], gen[line], "fast vs generic psd line %d" % line, rel_tol=2e-5, snr_min=90)
+
+
+def _dev_find_peaks(x, height, distance):
+    import ctypes
+    from pysdr_b200 import _lib
+    from pysdr_b200._lib import check
+    lib = _lib.load()
+    xd = torch.from_numpy(np.ascontiguousarray(x, np.float32)).cuda()
+    idx = torch.zeros(4096, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    check(lib.pysdr_find_peaks(ctypes.c_void_p(xd.data_ptr()), xd.numel(), None, 0.0, float(height), float(distance),
+                               ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(cnt.data_ptr()), None))
+    torch.cuda.synchronize()
+    return idx[:int(cnt.item())].cpu().numpy()
+
+
+@pytest.mark.parametrize("seed,n,dist", [(1, 8192, 41.7), (2, 2048, 3.0), (3, 8192, 1.0), (4, 500, 120.2), (5, 16384, 17.0)])
+def test_device_peak_picker_equals_scipy_find_peaks(seed, n, dist):
+    """pysdr_find_peaks against scipy.signal.find_peaks(x, distance=, height=) — the call of reference Plotting.py:594 — on
+    PSD-like lines: noise floor + carriers, flat-topped plateaus (clipped display lines) and distinct heights (with equal
+    heights scipy's own argsort order is unspecified, so the fixture avoids exact ties between different peaks)."""
+    from scipy import signal
+    rng = np.random.default_rng(seed)
+    x = (-100.0 + 6.0 * rng.normal(size=n)).astype(np.float32)
+    for k in range(25):
+        c = int(rng.integers(5, n - 5))
+        x[max(0, c - 3):c + 4] += np.float32(20.0 + 30.0 * rng.random()) * np.hanning(9)[1:8].astype(np.float32)[:len(x[max(0, c - 3):c + 4])]
+    for k in range(6):                                        # plateaus of width 2..5
+        c = int(rng.integers(10, n - 10))
+        x[c:c + 2 + k % 4] = np.float32(-40.0 + k)
+    h = float(np.median(x) + 10.0)
+    ref, _ = signal.find_peaks(x, distance=dist, height=h)
+    got = _dev_find_peaks(x, h, dist)
+    np.testing.assert_array_equal(got, ref)
