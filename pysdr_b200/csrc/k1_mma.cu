@@ -69,11 +69,11 @@ __device__ __forceinline__ void km_mbar_wait(unsigned bar, unsigned parity) {
         "{\n"
         ".reg .pred p;\n"
         "KM_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"      // suspend-time hint: sleep in hardware, do not poll
         "@p bra KM_DONE;\n"
         "bra KM_WAIT;\n"
         "KM_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity)
+        "}\n" ::"r"(bar), "r"(parity), "r"(20000u)
         : "memory");
 }
 __device__ __forceinline__ void km_mbar_arrive(unsigned bar) {

@@ -201,23 +201,7 @@ static int psd_launch(pysdr_psd *p, const void *d_x, int is_complex, int navg, i
     return PYSDR_OK;
 }
 
-extern "C" int pysdr_psd_lines(pysdr_psd *p, const void *d_x, int64_t n, int is_complex, int32_t navg, int dB, float *d_out,
-                               int64_t *n_lines_p, void *stream) {
-    if (!p || !d_x || !d_out || navg < 1) { pysdr_set_error("psd_lines: bad arguments"); return PYSDR_ERR_ARG; }
-    cudaStream_t st = (cudaStream_t)stream;
-    i64 n_frames = 0;
-    if (p->sub == 1) {
-        n_frames = n < p->chunk ? 0 : 1 + (n - p->chunk) / p->hop;
-    } else if (n >= p->chunk) {                                    // frames with start(f) + chunk <= n (offsets ascending, < hop)
-        const i64 g = (n - p->chunk) / p->hop;
-        n_frames = g * p->sub;
-        for (int i = 0; i < p->sub; ++i)
-            if (g * p->hop + p->sub_off[i] + p->chunk <= n) n_frames = g * p->sub + i + 1;
-    }
-    const i64 n_lines = n_frames / navg;
-    if (n_lines_p) *n_lines_p = n_lines;
-    if (n_lines == 0) return PYSDR_OK;
-    if (n_lines > 65535) { pysdr_set_error("psd_lines: more than 65535 lines per call"); return PYSDR_ERR_CAPACITY; }
+static int psd_lines_batch(pysdr_psd *p, const void *d_x, int is_complex, int navg, i64 n_lines, int dB, float *d_out, cudaStream_t st) {
     int n_split = 1;
     if (n_lines < 296) {
         n_split = (int)((296 + n_lines - 1) / n_lines);
@@ -242,6 +226,37 @@ extern "C" int pysdr_psd_lines(pysdr_psd *p, const void *d_x, int64_t n, int is_
     }
     pysdr_set_error("psd_lines: unsupported nfft %d", p->nfft);
     return PYSDR_ERR_ARG;
+}
+
+extern "C" int pysdr_psd_lines(pysdr_psd *p, const void *d_x, int64_t n, int is_complex, int32_t navg, int dB, float *d_out,
+                               int64_t *n_lines_p, void *stream) {
+    if (!p || !d_x || !d_out || navg < 1) { pysdr_set_error("psd_lines: bad arguments"); return PYSDR_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    i64 n_frames = 0;
+    if (p->sub == 1) {
+        n_frames = n < p->chunk ? 0 : 1 + (n - p->chunk) / p->hop;
+    } else if (n >= p->chunk) {                                    // frames with start(f) + chunk <= n (offsets ascending, < hop)
+        const i64 g = (n - p->chunk) / p->hop;
+        n_frames = g * p->sub;
+        for (int i = 0; i < p->sub; ++i)
+            if (g * p->hop + p->sub_off[i] + p->chunk <= n) n_frames = g * p->sub + i + 1;
+    }
+    const i64 n_lines = n_frames / navg;
+    if (n_lines_p) *n_lines_p = n_lines;
+    if (n_lines == 0) return PYSDR_OK;
+    // a launch covers at most 65535 lines (grid.y of the finalize kernel); a whole capture may have more (e.g. NFFT 64 lines
+    // of a 60 s capture): batches of whole lines, whose first frame starts at a multiple of navg frames.  Sub-step plans keep
+    // the single-launch limit (their frame starts are not a plain multiple of the hop).
+    const i64 BATCH = 65535;
+    if (p->sub != 1 && n_lines > BATCH) { pysdr_set_error("psd_lines: more than 65535 lines per call with sub-step frame starts"); return PYSDR_ERR_CAPACITY; }
+    const size_t elem = is_complex ? sizeof(float2) : sizeof(float);
+    for (i64 l0 = 0; l0 < n_lines; l0 += BATCH) {
+        const i64 nl = n_lines - l0 < BATCH ? n_lines - l0 : BATCH;
+        const char *xb = (const char *)d_x + (size_t)(l0 * navg) * (size_t)p->hop * elem;
+        int rc = psd_lines_batch(p, xb, is_complex, navg, nl, dB, d_out + (size_t)l0 * p->nfft, st);
+        if (rc) return rc;
+    }
+    return PYSDR_OK;
 }
 
 // ---- waterfall (reference Plotting.py) ---------------------------------------------------------------

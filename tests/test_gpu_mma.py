@@ -121,3 +121,24 @@ def test_mma_k1_many_tiles_per_cta_is_stable():
         for r in range(4):
             e = (iq2[r] - ref[r]).abs().max().item() / ref[r].abs().max().item()
             assert e < 5e-6, (rep, r, e)
+
+
+@pytest.mark.parametrize("nfilt", [501, 751, 301, 1001, 1401])
+def test_mma_k1_other_filter_lengths(nfilt):
+    """The piece planner on other tap counts at 8 MS/s -> 48 kHz (3/500): FILT_LEN 501 and 301 give three windows that all lie
+    inside the row (no continuation piece), 751 and 1001 split the last window, 1401 (467 taps per phase) makes two windows
+    cross — five pieces, more than the kernel's four column groups: the bank must fall back to the FP32 kernel by itself."""
+    P, Po = make_both(8, [1000, 1300, 870, 1210], ['IQ'] * 4, nfilt=nfilt)
+    from pysdr_b200.receiver import receiver_offsets
+    C = P.IN_CHUNK_SIZE
+    k = 5
+    x = _sig(k * C, P, receiver_offsets(P), nfilt)
+    xd = torch.from_numpy(x).cuda()
+    b2 = _bank(P, k * C, 2)
+    _, iq2, _ = b2.process(xd)
+    expect = 1 if nfilt == 1401 else 2
+    assert b2.k1_last == expect and b2.k1_mma_available == (expect == 2), (nfilt, b2.k1_last, b2.k1_mma_available)
+    rxo.create_receivers(Po)
+    for r in range(4):
+        ref = np.concatenate([Po.rx[r].dec.resamp(x[c * C:(c + 1) * C], Po.rx[r].lo) for c in range(k)])
+        assert_parity(iq2[r].cpu().numpy(), ref, "nfilt %d rx%d" % (nfilt, r))

@@ -288,3 +288,18 @@ def test_device_peak_picker_equals_scipy_find_peaks(seed, n, dist):
     ref, _ = signal.find_peaks(x, distance=dist, height=h)
     got = _dev_find_peaks(x, h, dist)
     np.testing.assert_array_equal(got, ref)
+
+
+def test_psd_more_than_65535_lines_in_one_call():
+    """A whole-capture call may ask for more lines than one launch's grid covers (r01: a silent capacity cliff): 70 000 lines
+    of a 256-point spectrum come back in batches and equal the same lines computed piecewise."""
+    from pysdr_b200 import sig_proc as dsp
+    sp = dsp.spectrum(48., 256, 256, 0.0)
+    n = 256 * 70000
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.view_as_complex(torch.randn((n, 2), generator=g, device="cuda", dtype=torch.float32))
+    full = sp.waterfall(x, 1, dB=True, to_host=False)
+    assert full.shape == (70000, 256)
+    for l0 in (0, 65534, 65535, 69990):
+        part = sp.waterfall(x[l0 * 256:(l0 + 5) * 256], 1, dB=True, to_host=False)
+        assert torch.allclose(part, full[l0:l0 + 5], rtol=0, atol=1e-4)
