@@ -66,28 +66,23 @@ class ChannelBank:
         """x: device complex64 block (whole IN_CHUNK_SIZE chunks).  Returns (am, iq): lists of n_ch device views, valid
         until the next call."""
         am, iq = [], []
+        self.banks[0]._check_input(x)                                 # dtype / device / contiguity / capacity, once per call
         if self.raster is not None:                                   # K1 of every channel in one pass, into the shared memory
             self.raster.process(x, n0=self._n0, hist=self._x_hist, out=self._C, out_col=self._hc)
-            keep = self._x_hist.numel()
-            if x.numel() >= keep:
-                self._x_hist.copy_(x[x.numel() - keep:])
-            else:
-                self._x_hist.copy_(torch.cat((self._x_hist[x.numel():], x)))
-            self._n0 += x.numel()
         if want_dc or self.raster is None:
             for b in self.banks:
                 a, q, _ = b.process(x, want_dc=want_dc)
                 am.extend(a)
                 iq.extend(q)
             self.n_out = self.banks[0].n_out
+            self._advance(x)
             return am, iq
         # raster mode, audio only: the groups are driven with prepared arguments (one ctypes call each: the host loop over
         # 128 groups is otherwise the bottleneck once K1 is a single launch) and the views are built once per output length
         import ctypes
         from ._lib import check
-        if getattr(self, '_fast_args', None) is None:
+        if getattr(self, '_fast_args', None) is None:                   # (re)built after construction and after invalidate()
             for b in self.banks:
-                b._check_input(x)
                 b.sync_demod()
                 b._iq_copy_ptr()
             self._fast_args = [(b.lib.pysdr_bank_process, b.h, ctypes.c_void_p(b._am.data_ptr()), b.max_out) for b in self.banks]
@@ -98,6 +93,7 @@ class ChannelBank:
         for fn, h, am_p, max_out in self._fast_args:
             check(fn(h, xp, n_in, 0, None, am_p, None, max_out, ctypes.byref(n_out), st))
         self.n_out = n_out.value
+        self._advance(x)                                              # only once every bank has taken the block
         if self._views_for != self.n_out:
             self._views = ([], [])
             for b in self.banks:
@@ -107,6 +103,23 @@ class ChannelBank:
                 self._views[1].extend(q)
             self._views_for = self.n_out
         return self._views
+
+    def _advance(self, x):
+        """Raster mode: the channelizer's own stream position and raw history move once all banks have processed the block, so
+        a failing bank call leaves the two in step."""
+        if self.raster is None:
+            return
+        keep = self._x_hist.numel()
+        if x.numel() >= keep:
+            self._x_hist.copy_(x[x.numel() - keep:])
+        else:
+            self._x_hist.copy_(torch.cat((self._x_hist[x.numel():], x)))
+        self._n0 += x.numel()
+
+    def invalidate(self):
+        """Call after changing MODE / AF_BW / BFO on the banks' parameter objects: the raster fast path caches the per-bank
+        call arguments and re-reads the parameters (ReceiverBank.sync_demod) only when they are rebuilt."""
+        self._fast_args = None
 
     def launch_count(self):
         return sum(b.lib.pysdr_bank_launch_count(b.h) for b in self.banks)
