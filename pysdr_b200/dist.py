@@ -15,8 +15,20 @@ import torch
 import torch.distributed as dist
 
 
-def shard_plan(P, rank, world, chunks_per_rank):
-    """Where rank's shard starts and what it must read before it.  All quantities in input samples."""
+def pll_settle_chunks(P, rel=1.0e-6, bn=50.0, zeta=0.70710678118654752440):
+    """Chunks after which the AM-Synch carrier loop (bank.cu: second-order PLL at the audio rate, noise bandwidth bn, damping
+    zeta) has forgotten its start-up state to `rel`: the transient decays like exp(-zeta*wn*t), wn = bn / (zeta + 1/(4 zeta))
+    per second (the kernel's theta = wn / FS_OUT per sample)."""
+    fs_out = float(P.SRATE) * int(P.UP) / int(P.DOWN)
+    wn = bn / (zeta + 1.0 / (4.0 * zeta))
+    t = -math.log(rel) / (zeta * wn)                                    # seconds
+    out_per_chunk = int(P.IN_CHUNK_SIZE) * int(P.UP) / int(P.DOWN)
+    return int(math.ceil(t * fs_out / out_per_chunk))
+
+
+def shard_plan(P, rank, world, chunks_per_rank, min_warm_chunks=0):
+    """Where rank's shard starts and what it must read before it.  All quantities in input samples.  min_warm_chunks: warm-up
+    chunks wanted beyond what the filter memories need (AM-Synch: the carrier loop's settling time)."""
     C = int(P.IN_CHUNK_SIZE)
     need = (int(P.FILT_LEN) + int(P.UP) - 1) // int(P.UP) - 1           # K1 halo (raw samples)
     hist_out = int(P.FILT_LEN) + 1                                      # AF memory (baseband samples)
@@ -25,7 +37,7 @@ def shard_plan(P, rank, world, chunks_per_rank):
         warm_chunks, halo = 0, 0
     else:
         warm_in = math.ceil(hist_out * int(P.DOWN) / int(P.UP))         # inputs that produce >= hist_out outputs
-        warm_chunks = max(1, math.ceil(warm_in / C))
+        warm_chunks = max(1, math.ceil(warm_in / C), int(min_warm_chunks))
         halo = need
         if warm_chunks * C >= start:                                    # the warm-up reaches back to the stream start:
             warm_chunks, halo = start // C, 0                           # x[<0] = 0, exactly what seek(0) gives
@@ -174,10 +186,12 @@ class ShardedCapture:
         into the later ranks' memory over NVLink and the fused back kernel waits on their flags (PeerCarry) — no collective
         library call on the data path.  "peer" falls back to "nccl" where symmetric memory is not available (CPU/gloo)."""
         self.bank, self.P, self.rank, self.world = bank, P, rank, world
-        self.plan = shard_plan(P, rank, world, chunks_per_rank)
-        if world > 1 and any(bank._mode_of(r) == 'AM-Synch' for r in range(bank.n_rx)):
-            raise ValueError("AM-Synch carries a PLL state that has no exact hand-off between time shards; "
-                             "shard AM-Synch receivers by receiver (SURVEY 8(e) axis 1), not by time")
+        # AM-Synch: the carrier loop is a nonlinear recurrence with no closed-form hand-off, but it FORGETS: a shard whose
+        # warm-up covers the loop's settling time (rel 1e-6: 20 chunks at cfg2's rates) tracks the single-stream loop to the
+        # parity tolerance (converged-loop assumption: the carrier is inside the loop's pull-in range, as it is whenever
+        # AM-Synch is usable at all; the phase agrees modulo 2 pi, which the detector output does not see).
+        self.pll_warm = pll_settle_chunks(P) if any(bank._mode_of(r) == 'AM-Synch' for r in range(bank.n_rx)) else 0
+        self.plan = shard_plan(P, rank, world, chunks_per_rank, min_warm_chunks=self.pll_warm)
         dev = bank.device
         w = self.plan['warm_chunks']
         self.peaks_ext = torch.zeros((bank.n_rx, w + self.plan['n_blocks']), dtype=torch.float32, device=dev)

@@ -303,3 +303,48 @@ def test_psd_more_than_65535_lines_in_one_call():
     for l0 in (0, 65534, 65535, 69990):
         part = sp.waterfall(x[l0 * 256:(l0 + 5) * 256], 1, dB=True, to_host=False)
         assert torch.allclose(part, full[l0:l0 + 5], rtol=0, atol=1e-4)
+
+
+def test_am_synch_time_shards_after_loop_settling_warmup():
+    """AM-Synch under time sharding (r01 refused it): the carrier loop has no closed-form hand-off but it forgets its start-up
+    state — a shard warmed up over the loop's settling time (dist.pll_settle_chunks: 20 chunks for rel 1e-6) tracks the
+    single-stream loop to the parity gate.  Two shards of 32 chunks played on one device (the O(1) AGC summaries carried as in
+    the multi-GPU run); carrier 11 Hz off the receiver centre, inside the 50 Hz loop's pull-in range."""
+    import ctypes
+    from pysdr_b200._lib import check
+    from pysdr_b200.bank import _stream_ptr
+    from pysdr_b200.dist import AGC_SUMMARY_LEN, ShardedCapture, pll_settle_chunks
+    from pysdr_b200.receiver import receiver_offsets
+    world, cpr = 2, 32
+    P, _ = make_both(2.048, [1000, 1020], ['AM-Synch', 'AM'], foffset_khz=100, af_bw_khz=[5, 5])
+    C = P.IN_CHUNK_SIZE
+    warm = pll_settle_chunks(P)
+    assert 10 <= warm < cpr
+    n = world * cpr * C
+    t = np.arange(n)
+    x = _noise(n, 33, 0.002).astype(np.complex128)
+    for k, off in enumerate(receiver_offsets(P)):
+        env = 1.0 + 0.5 * np.sin(2 * np.pi * (700.0 + 300 * k) * t / P.SRATE)
+        x = x + 0.1 * env * np.exp(2j * np.pi * (off + 11.0) * t / P.SRATE)
+    xd = torch.from_numpy(x.astype(np.complex64)).cuda()
+    single = _bank(P, n)
+    am, _, _ = single.process(xd)
+    ref = [a.cpu().numpy().copy() for a in am]
+    all_sum = torch.zeros((world, 2, AGC_SUMMARY_LEN), dtype=torch.float64, device="cuda")
+    shards = []
+    for r in range(world):
+        b = _bank(P, (cpr + warm) * C)
+        sh = ShardedCapture(b, P, r, world, cpr)
+        pl = sh.plan
+        assert pl['warm_chunks'] == (warm if r else 0)
+        sh.front(xd[pl['first_sample']:pl['start'] + pl['n']], copy_own=False)
+        check(b.lib.pysdr_bank_agc_summary(b.h, pl['warm_chunks'], ctypes.c_void_p(all_sum[r].data_ptr()), _stream_ptr()))
+        shards.append(sh)
+    for r in range(world):
+        sh, b = shards[r], shards[r].bank
+        check(b.lib.pysdr_bank_agc_enter(b.h, ctypes.c_void_p(all_sum.data_ptr()), r, _stream_ptr()))
+        got, _, _ = sh.back(None)
+        m0 = odsp.n_out_total(r * cpr * C, P.UP, P.DOWN)
+        for k in range(2):
+            g = got[k].cpu().numpy()
+            assert_parity(g, ref[k][m0:m0 + len(g)], "AM-Synch shard %d rx%d vs single stream" % (r, k))
