@@ -806,8 +806,16 @@ __global__ void __launch_bounds__(BACK_THREADS) agc_back_fused_kernel(const Back
         }
         grid_barrier(p.bar, p.bar_base + gridDim.x);
     }
+    // The summaries for the later ranks are pushed by CTAs n_rx .. 2 n_rx - 1 while CTAs 0 .. n_rx - 1 enter and scan: the
+    // NVLink stores and their system-scope fences (~15 us) stay off this rank's critical path.  (A grid too small for that —
+    // a handful of blocks — pushes from the scanner CTAs first.)
+    const bool push_here = p.do_push && p.x.rank < p.x.world - 1;
+    const bool push_apart = push_here && (int)gridDim.x >= 2 * p.n_rx;
+    if (push_apart && (int)blockIdx.x >= p.n_rx && (int)blockIdx.x < 2 * p.n_rx)
+        agc_summary_push_rx(p.scan.state, p.peaks, p.peaks_row, p.push_skip, p.n_blocks, p.x.peers, p.x.world, p.x.rank, p.n_rx,
+                            p.x.seq, (int)blockIdx.x - p.n_rx);
     if ((int)blockIdx.x < p.n_rx) {
-        if (p.do_push && p.x.rank < p.x.world - 1)    // the later ranks wait for this: before anything this rank waits for
+        if (push_here && !push_apart)
             agc_summary_push_rx(p.scan.state, p.peaks, p.peaks_row, p.push_skip, p.n_blocks, p.x.peers, p.x.world, p.x.rank, p.n_rx,
                                 p.x.seq, blockIdx.x);
         if (p.do_enter) {

@@ -209,9 +209,20 @@ class ShardedCapture:
         self.peer = None
         self.carry_how = "ONE NCCL all-gather"
         if carry == "peer" and world > 1 and self.o1 and dev.type == "cuda":
-            self.peer = PeerCarry(bank, rank, world)
-            self.carry_how = ("stored by the summary kernel into the later ranks' HBM over NVLink peer memory, flag-waited "
-                              "inside the fused back kernel; no collective call")
+            # every rank must take the same path: agree on whether the peer mapping came up everywhere
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+            try:
+                self.peer = PeerCarry(bank, rank, world)
+            except Exception as e:                                           # no peer access / symmetric memory on this box
+                self.peer_error = "%s: %s" % (type(e).__name__, e)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 1:
+                self.carry_how = ("stored by the summary kernel into the later ranks' HBM over NVLink peer memory, flag-waited "
+                                  "inside the fused back kernel; no collective call")
+            else:
+                self.peer = None
+                self.carry_how = "ONE NCCL all-gather (peer-memory mapping unavailable on this box)"
 
     def front(self, xbuf, copy_own=True):
         """K1 + audio-rate filters + block peaks of this shard (and its warm-up).  xbuf: device tensor holding samples
