@@ -7,9 +7,11 @@
 
 Workload (config.workload): BASELINE.json configs[1] — 4 independent receivers AM/NFM/USB/CW on a 60 s, 8 MS/s
 synthetic complex64 capture (2812 whole IN_CHUNK_SIZE blocks = 479 912 792 samples per GPU).  One step = one pass of
-the whole capture through all four receivers.  N>1: one process per GPU, the capture is N x 60 s long and sharded in
-time (weak scaling); each rank warms its filter memories on the chunk preceding its shard, and the only collective
-is the all-gather of per-block AGC peaks (n_rx x 2812 floats per rank).
+the whole capture through all four receivers (three launches: tensor-core K1, AF filter, fused AGC back kernel).  N>1: one
+process per GPU, the capture is N x 60 s long and sharded in time (weak scaling); each rank warms its filter memories on the
+chunk preceding its shard and the AGC state crosses the shard boundaries as 19 doubles per receiver per rank, stored by our
+own kernels into the later ranks' HBM over NVLink peer memory (--carry nccl: one all-gather of the same bytes instead).
+Before anything is timed every rank checks its shard against a single-stream pass (parity_check in the JSON line).
 """
 import argparse
 import json
