@@ -209,11 +209,24 @@ int pysdr_bank_k1_variant(const pysdr_bank *b);
  * tensor memory).  mode 0: never; 1 (default): calls whose interior has at least 8192 super-periods (whole captures, long
  * segments) — short per-chunk calls keep the tap-stationary FP32 kernel; 2: whenever the geometry and alignment allow.
  * The two kernels agree to ~1e-6 of peak, not bit for bit: pin mode 0 where chunked and whole-capture K1 outputs must be
- * identical.  k1_last: the kernel the last call ran (0 generic, 1 tap-stationary, 2 tensor-core interior + edge tiles). */
+ * identical.  k1_last: the kernel the last call ran (0 generic, 1 tap-stationary, 2 tensor-core interior + edge tiles).
+ *
+ * Banks of 16 or more receivers (the many-channel receivers of BASELINE config 5, any set of offsets) have a second
+ * tensor-core kernel, k1_chan.cu: channels are the GEMM's columns, the output instants of one polyphase class its rows, the
+ * channels' folded taps stream from L2 as the B operand.  The same mode switch governs it (mode 1: calls with at least 2048
+ * interior super-periods); k1_last reports 3 when it ran. */
 int pysdr_bank_set_k1_mma(pysdr_bank *b, int mode);
 int pysdr_bank_k1_mma_available(const pysdr_bank *b);
 int pysdr_bank_k1_last(const pysdr_bank *b);
 int pysdr_bank_force_generic(pysdr_bank *b, int on);
+/* Test hook of k1_chan.cu (host arithmetic only, no device): the plan, the per-call geometry and the tap images exactly as
+ * the kernel gets them, so that the CPU suite can emulate the contraction in numpy.  g_host: folded taps
+ * complex64[n_rx][up][lp_pad]; x_addr: the device address the capture would have (alignment only).  out[0..15]: used, q_a,
+ * out_lo, out_hi, n_steps, ngroups, nch, N, ncls, S, n_tiles; out[16 + 8 cls ..]: phase, parity, sample offset, image, rows,
+ * first sample of row 0.  Returns the image's float count (copied into img when img_cap allows) or a negative error code. */
+int64_t pysdr_k1chan_debug_plan(int up, int down, int lp, int n_rx, const float *g_host, int lp_pad, int64_t n0, int64_t n_in,
+                                int64_t m0, int64_t n_out, uint64_t x_addr, int64_t min_rows, int64_t *out, float *img,
+                                int64_t img_cap);
 /* K1-only bank (WFM video stage: LO + FIR at the RF rate, UP = DOWN = 1): process() stops after K1; its output is the
  * new-sample part of the complex memory (pysdr_bank_c_memory) and, when given, d_iq_bb. */
 int pysdr_bank_set_k1_only(pysdr_bank *b, int on);

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpysdr_b200.so")
-SOURCES = ["bank.cu", "k1_generic.cu", "k1_fast.cu", "k1_mma.cu", "k2_fftconv.cu", "lfilter.cu", "psd.cu", "psd_fast.cu", "czt.cu", "wola.cu"]
+SOURCES = ["bank.cu", "k1_generic.cu", "k1_fast.cu", "k1_mma.cu", "k1_chan.cu", "k2_fftconv.cu", "lfilter.cu", "psd.cu", "psd_fast.cu", "czt.cu", "wola.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 

@@ -70,6 +70,7 @@ SIGNATURES = {
     "pysdr_bank_set_k1_mma": (c_int, [c_vp, c_int]),
     "pysdr_bank_k1_mma_available": (c_int, [c_vp]),
     "pysdr_bank_k1_last": (c_int, [c_vp]),
+    "pysdr_k1chan_debug_plan": (c_i64, [c_int, c_int, c_int, c_int, c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_u64, c_i64, c_vp, c_vp, c_i64]),
     "pysdr_bank_force_generic": (c_int, [c_vp, c_int]),
     "pysdr_bank_set_k1_only": (c_int, [c_vp, c_int]),
     "pysdr_bank_set_real_input": (c_int, [c_vp, c_int]),

@@ -196,7 +196,8 @@ class ReceiverBank:
         check(self.lib.pysdr_bank_force_generic(self.h, 1 if on else 0))
 
     def set_k1_mma(self, mode):
-        """0: never use the tensor-core K1; 1 (default): for calls with >= 8192 interior super-periods; 2: whenever possible."""
+        """0: never use the tensor-core K1 kernels; 1 (default): for calls with >= 8192 interior super-periods (banks of 16 or more
+        receivers: 2048, many-channel kernel); 2: whenever possible."""
         check(self.lib.pysdr_bank_set_k1_mma(self.h, int(mode)))
 
     @property
@@ -205,7 +206,8 @@ class ReceiverBank:
 
     @property
     def k1_last(self):
-        """Kernel of the last call: 0 generic, 1 tap-stationary FP32, 2 tensor-core interior + tap-stationary edge tiles."""
+        """Kernel of the last call: 0 generic, 1 tap-stationary FP32, 2 tensor-core interior + tap-stationary edge tiles, 3 the
+        many-channel tensor-core kernel (k1_chan.cu, banks of 16 or more receivers)."""
         return self.lib.pysdr_bank_k1_last(self.h)
 
     @property

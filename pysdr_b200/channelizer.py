@@ -3,8 +3,9 @@
 The reference's surface stops at MAX_RX = 6 (params.py:33); this is the north-star extension.  Channels are served in
 groups of up to 128 receivers, one ReceiverBank (= one set of K1/K2 launches) per group, all groups reading the SAME
 device-resident block of IQ.  Every number still comes from libpysdr_b200.so; this class is only the loop over
-groups.  At 3/625 the contraction is compute-bound (13 kFLOP per input sample for 1024 channels, 474 flop/B): the
-tap-stationary K1 runs it at its FP32-FMA rate; a tensor-core formulation is the named next step."""
+groups.  At 3/625 the contraction is compute-bound (13 kFLOP per input sample for 1024 channels, 474 flop/B): banks of 16
+or more channels run it on the tensor cores (k1_chan.cu: split-TF32 GEMM on tcgen05, channels as columns, any offsets);
+on a uniform raster wola.cu replaces it by one windowing pass + one inverse DFT per output instant."""
 import copy
 
 import numpy as np
@@ -69,29 +70,30 @@ class ChannelBank:
         self.banks[0]._check_input(x)                                 # dtype / device / contiguity / capacity, once per call
         if self.raster is not None:                                   # K1 of every channel in one pass, into the shared memory
             self.raster.process(x, n0=self._n0, hist=self._x_hist, out=self._C, out_col=self._hc)
-        if want_dc or self.raster is None:
+        if want_dc:
             for b in self.banks:
-                a, q, _ = b.process(x, want_dc=want_dc)
+                a, q, _ = b.process(x, want_dc=True)
                 am.extend(a)
                 iq.extend(q)
             self.n_out = self.banks[0].n_out
             self._advance(x)
             return am, iq
-        # raster mode, audio only: the groups are driven with prepared arguments (one ctypes call each: the host loop over
-        # 128 groups is otherwise the bottleneck once K1 is a single launch) and the views are built once per output length
+        # audio only: the banks are driven with prepared arguments (one ctypes call each) and the per-channel views are built
+        # once per output length — with K1 on the tensor cores (k1_chan.cu, or wola.cu in raster mode) a block of 1024 channels
+        # is ~5 ms of GPU time, and building 3 x 1024 tensor views per block costs more than that on the host
         import ctypes
         from ._lib import check
         if getattr(self, '_fast_args', None) is None:                   # (re)built after construction and after invalidate()
+            self._fast_args = []
             for b in self.banks:
                 b.sync_demod()
-                b._iq_copy_ptr()
-            self._fast_args = [(b.lib.pysdr_bank_process, b.h, ctypes.c_void_p(b._am.data_ptr()), b.max_out) for b in self.banks]
+                self._fast_args.append((b.lib.pysdr_bank_process, b.h, b._iq_copy_ptr(), ctypes.c_void_p(b._am.data_ptr()), b.max_out))
             self._views_for = None
         xp, n_in = ctypes.c_void_p(x.data_ptr()), x.numel()
         n_out = ctypes.c_int64(0)
         st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        for fn, h, am_p, max_out in self._fast_args:
-            check(fn(h, xp, n_in, 0, None, am_p, None, max_out, ctypes.byref(n_out), st))
+        for fn, h, iq_p, am_p, max_out in self._fast_args:
+            check(fn(h, xp, n_in, 0, iq_p, am_p, None, max_out, ctypes.byref(n_out), st))
         self.n_out = n_out.value
         self._advance(x)                                              # only once every bank has taken the block
         if self._views_for != self.n_out:
@@ -117,8 +119,8 @@ class ChannelBank:
         self._n0 += x.numel()
 
     def invalidate(self):
-        """Call after changing MODE / AF_BW / BFO on the banks' parameter objects: the raster fast path caches the per-bank
-        call arguments and re-reads the parameters (ReceiverBank.sync_demod) only when they are rebuilt."""
+        """Call after changing MODE / AF_BW / BFO on the banks' parameter objects: the audio-only path (want_dc=False) caches
+        the per-bank call arguments and re-reads the parameters (ReceiverBank.sync_demod) only when they are rebuilt."""
         self._fast_args = None
 
     def launch_count(self):

@@ -902,6 +902,7 @@ __global__ void __launch_bounds__(256) seek_reset_kernel(float2 *C, i64 c_stride
 }
 
 // ------------------------------------------------------------------------------------------------
+#define K1_CHAN_MIN_ROWS 2048                /* the same for the many-channel kernel (k1_chan.cu) */
 #define K1_MMA_MIN_ROWS 8192                 /* interior super-periods from which the tensor-core K1 takes a call (mode 1) */
 struct pysdr_bank {
     pysdr_bank_config cfg;
@@ -937,6 +938,7 @@ struct pysdr_bank {
     bool pending;
     bool force_generic;
     K1MmaPlan *mma;                          // tensor-core K1 (k1_mma.cu); null when the geometry does not fit
+    K1ChanPlan *chan;                        // many-channel tensor-core K1 (k1_chan.cu); null below 16 receivers
     int mma_mode;                            // 0 never, 1 calls of at least K1_MMA_MIN_ROWS interior super-periods, 2 whenever possible
     int k1_last;                             // kernel of the last call: 0 generic, 1 tap-stationary, 2 tensor-core interior + edges
     // fused back (agc_back_fused_kernel): block peaks deferred from front into the back launch; grid barrier counter
@@ -1038,6 +1040,7 @@ extern "C" int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out)
     b->g_dirty = true;
     b->force_generic = false;
     b->mma = k1_fast_supported(cfg->up, cfg->down, b->lp, cfg->n_rx) ? k1_mma_plan_create(cfg->up, cfg->down, b->lp, cfg->n_rx) : nullptr;
+    b->chan = k1_chan_plan_create(cfg->up, cfg->down, b->lp, cfg->n_rx);
     b->mma_mode = 1; b->k1_last = -1;
     if (const char *e = getenv("PYSDR_K1_MMA")) b->mma_mode = atoi(e);
     b->force_direct_fir = false;
@@ -1079,6 +1082,7 @@ extern "C" int pysdr_bank_destroy(pysdr_bank *b) {
     cudaFree(b->hc_d_in); cudaFree(b->hc_d_iq); cudaFree(b->hc_d_am); cudaFree(b->hc_d_dc);
     if (!b->c_external) cudaFree(b->d_C);
     k1_mma_plan_destroy(b->mma);
+    k1_chan_plan_destroy(b->chan);
     cudaFree(b->d_hist); cudaFree(b->d_g); cudaFree(b->d_af); cudaFree(b->d_R);
     cudaFree(b->d_a); cudaFree(b->d_peaks); cudaFree(b->d_gains); cudaFree(b->d_agc); cudaFree(b->d_pll); cudaFree(b->d_bar);
     delete b;
@@ -1415,6 +1419,7 @@ static int upload_folded_taps(pysdr_bank *b, cudaStream_t st) {
     CUDA_TRY(cudaMemcpyAsync(b->d_g, g.data(), sizeof(float2) * g.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));      // g is a stack-owned staging vector
     if (b->mma) { int rc = k1_mma_upload_taps(b->mma, g.data(), b->lp_pad, st); if (rc) return rc; }
+    if (b->chan) { int rc = k1_chan_upload_taps(b->chan, g.data(), b->lp_pad, st); if (rc) return rc; }
     b->g_dirty = false;
     return PYSDR_OK;
 }
@@ -1518,8 +1523,18 @@ extern "C" int pysdr_bank_process_front(pysdr_bank *b, const void *d_iq, int64_t
         return PYSDR_OK;
     };
     if ((rc = mark())) return rc;
+    int chan_used = 0;
+    if (!b->k1_external && !b->force_generic && b->chan && b->mma_mode > 0) {      // a bank of many channels: dense tensor-core contraction
+        int nl = 0;
+        rc = k1_launch_chan(b->chan, a, b->mma_mode >= 2 ? 1 : K1_CHAN_MIN_ROWS, st, &chan_used, &nl);
+        if (rc) return rc;
+        b->launches += nl;
+    }
     if (b->k1_external) {
         rc = PYSDR_OK;                       // C[r][hc .. hc+n_out) was written by the caller on this stream
+    } else if (chan_used) {
+        rc = PYSDR_OK;
+        b->k1_last = 3;
     } else if (!b->force_generic && k1_fast_supported(c.up, c.down, b->lp, c.n_rx)) {
         int used = 0, nl = 0;
         rc = PYSDR_OK;

@@ -116,6 +116,15 @@ int k1_mma_upload_taps(K1MmaPlan *p, const float2 *g_host, int lp_pad, cudaStrea
 // geometry/alignment does not fit; the caller then takes the tap-stationary path.
 int k1_launch_mma(K1MmaPlan *p, const K1Args &a, i64 min_rows, cudaStream_t st, int *used, int *launches);
 
+// ---- K1 many-channel tensor-core variant (k1_chan.cu): banks of >= 16 receivers, any geometry with up * (1 or 2) <= 8 classes ----
+struct K1ChanPlan;
+int k1_chan_supported(int up, int down, int lp, int n_rx);
+K1ChanPlan *k1_chan_plan_create(int up, int down, int lp, int n_rx);
+void k1_chan_plan_destroy(K1ChanPlan *p);
+int k1_chan_upload_taps(K1ChanPlan *p, const float2 *g_host, int lp_pad, cudaStream_t st);
+// *used = 0 and nothing launched when the call has fewer than min_rows interior super-periods or its alignment does not fit
+int k1_launch_chan(K1ChanPlan *p, const K1Args &a, i64 min_rows, cudaStream_t st, int *used, int *launches);
+
 // ---- K2 fast path (k2_fftconv.cu) ---------------------------------------------------------------------
 struct FftConvArgs {
     const float2 *C;          // complex memory + new samples, rows of c_stride: C[rx][0..hc+n_out)

@@ -29,8 +29,7 @@
 //                                                                                piece of the next row, NCO de-rotation, store
 //   warp 3     stream edges: the few outputs whose rows reach before x[0] (carried history) or past its end, one plain
 //              FP32 dot product per output straight from global memory, spread over the CTAs and hidden under the pipeline
-#include "common.cuh"
-#include <cuda.h>
+#include "umma.cuh"
 #include <algorithm>
 
 #define KM_THREADS 512
@@ -60,61 +59,6 @@ struct KmGeom {
     const unsigned char *img;      // global: [KmStep table, KM_TAB_BYTES][B image]
 };
 
-__device__ __forceinline__ unsigned km_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void km_mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void km_mbar_wait(unsigned bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "KM_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"      // suspend-time hint: sleep in hardware, do not poll
-        "@p bra KM_DONE;\n"
-        "bra KM_WAIT;\n"
-        "KM_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity), "r"(20000u)
-        : "memory");
-}
-__device__ __forceinline__ void km_mbar_arrive(unsigned bar) {
-    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void km_mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void km_commit(unsigned bar) {          // arrives on bar when every MMA issued so far has completed
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void km_mma(unsigned d_tmem, unsigned a_tmem, unsigned long long bdesc, unsigned idesc) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
-        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(1u), "r"(0u)
-        : "memory");
-}
-__device__ __forceinline__ uint4 km_lds128(unsigned addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void km_tma_box(unsigned dst, const CUtensorMap *tmap, int c0, int c1, unsigned bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-                 "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
-                 : "memory");
-}
-#define KM_ST16(addr, r)                                                                                                        \
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(addr), \
-                 "r"((r)[0]), "r"((r)[1]), "r"((r)[2]), "r"((r)[3]), "r"((r)[4]), "r"((r)[5]), "r"((r)[6]), "r"((r)[7]), "r"((r)[8]),      \
-                 "r"((r)[9]), "r"((r)[10]), "r"((r)[11]), "r"((r)[12]), "r"((r)[13]), "r"((r)[14]), "r"((r)[15])                        \
-                 : "memory")
-#define KM_LD16(addr, r)                                                                                                        \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"          \
-                 : "=r"((r)[0]), "=r"((r)[1]), "=r"((r)[2]), "=r"((r)[3]), "=r"((r)[4]), "=r"((r)[5]), "=r"((r)[6]), "=r"((r)[7]),       \
-                   "=r"((r)[8]), "=r"((r)[9]), "=r"((r)[10]), "=r"((r)[11]), "=r"((r)[12]), "=r"((r)[13]), "=r"((r)[14]), "=r"((r)[15]) \
-                 : "r"(addr)                                                                                                     \
-                 : "memory")
 
 // shared memory map (dynamic, 1024-byte aligned base)
 #define KM_OFF_STAGES 0
@@ -318,12 +262,17 @@ __global__ void __launch_bounds__(KM_THREADS, 1) k1_mma_kernel(const __grid_cons
                 if (h == 0) {
                     km_mbar_wait(a_empty + 8 * grp, (unsigned)(((it >> 1) & 1) ^ 1));   // the MMAs that read this A stage last time are done
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                } else {
-                    __syncwarp();
-                    if (lane == 0) km_mbar_arrive(x_empty + 8 * s);             // both boxes of the stage are in registers
                 }
                 KM_ST16(at + h * 32, hi); KM_ST16(at + h * 32 + 16, hi + 16);
                 KM_ST16(at + 64 + h * 32, lo); KM_ST16(at + 64 + h * 32 + 16, lo + 16);
+                if (h == 1) {
+                    // the stage is released only after the tcgen05.st of box 1 have ISSUED: they read every register the loads
+                    // fill, so the loads have been performed.  (Arriving right after issuing the loads — the hi/lo arithmetic is
+                    // scheduled below the arrive — lets the next TMA box overwrite rows not yet read: k1_chan.cu measured one
+                    // wrong row in ~30 000 with that order under full load.)
+                    __syncwarp();
+                    if (lane == 0) km_mbar_arrive(x_empty + 8 * s);
+                }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -452,19 +401,6 @@ struct K1MmaPlan {
     bool attr_done[64];
 };
 
-typedef CUresult (*KmEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                               const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static KmEncodeFn km_encode_fn() {
-    static KmEncodeFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        cudaDriverEntryPointQueryResult q;
-        void *p = nullptr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (KmEncodeFn)p;
-    }
-    return fn;
-}
 
 struct KmPiece { int out, dr, t0, t1; };       // samples [t0, t1) of the row (dr = 1: the row AFTER the output's own)
 
@@ -510,14 +446,6 @@ int k1_mma_supported(int up, int down, int lp, int n_rx) {
     return 1;
 }
 
-static float km_tf32_hi(float v) {               // round to nearest tf32 (10-bit mantissa): the lo half carries the rest
-    uint32_t u;
-    memcpy(&u, &v, 4);
-    u += 0x00000FFFu + ((u >> 13) & 1u);
-    u &= 0xFFFFE000u;
-    memcpy(&v, &u, 4);
-    return v;
-}
 
 K1MmaPlan *k1_mma_plan_create(int up, int down, int lp, int n_rx) {
     if (!k1_mma_supported(up, down, lp, n_rx)) return nullptr;

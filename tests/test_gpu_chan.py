@@ -1,0 +1,171 @@
+"""Many-channel tensor-core K1 (pysdr_b200/csrc/k1_chan.cu): the NCO mix + polyphase decimation (reference receiver.py:235,822,866)
+of a whole bank of channel receivers as a dense split-TF32 contraction on tcgen05 — BASELINE config 5 with ANY set of channel
+offsets.  Checked against the oracle's resampler and against the FP32 tap-stationary kernel on the same inputs.  Mode 2 forces
+the tensor-core kernel on every call that has a few interior super-periods; mode 0 pins the FP32 kernel."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import receiver_oracle as rxo
+from oracle import sig_proc_oracle as odsp
+from tests.util import assert_parity, make_both
+
+pytestmark = pytest.mark.gpu
+
+
+def _sig(n, srate, offs, seed, amp=0.02):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n)
+    x = ((rng.normal(size=n) + 1j * rng.normal(size=n)) * 0.01).astype(np.complex128)
+    for k, f in enumerate(offs):
+        x += amp * (1 + 0.4 * np.sin(2 * np.pi * (300.0 + 23 * k) * t / srate)) * np.exp(2j * np.pi * (f + 500.0) * t / srate)
+    return x.astype(np.complex64)
+
+
+def _offsets(n_ch, span_hz, seed):
+    """Irregular offsets (no raster): what wola.cu cannot serve."""
+    rng = np.random.default_rng(seed)
+    return sorted((rng.uniform(-span_hz, span_hz, n_ch)).round(1).tolist())
+
+
+def _oracle_iq(Po, off, x):
+    dec = odsp.decimator(Po.SRATE, Po.UP, Po.DOWN, Po.FILT_LEN, odsp.VIDEO_BWs, Po.VIDEO_BW)
+    dec.h = dec.filter_bank[odsp._video_index(Po)]
+    lo = odsp.signal_generator(off, Po.IN_CHUNK_SIZE, Po.SRATE, True)
+    return dec.resamp_fast(x, lo)
+
+
+def _channel_bank(P, offs, max_in, mode, group):
+    from pysdr_b200.channelizer import ChannelBank
+    cb = ChannelBank(P, offs, 'IQ', max_in=max_in, group=group)
+    for b in cb.banks:
+        b.set_k1_mma(mode)
+    return cb
+
+
+@pytest.mark.parametrize("n_ch,shift", [(24, 0), (24, 1), (96, 0), (128, 1), (100, 0), (16, 0)])
+def test_chan_k1_cfg5_geometry_matches_oracle_and_fp32_kernel(n_ch, shift):
+    """10 MS/s -> 48 kHz (3/625: DOWN odd, so rows of a class are two super-periods apart and there are six classes), irregular
+    offsets, 4 chunks in one call.  96 channels = one column group of N = 192, 128 = two groups of 64, 100 = two groups of 56
+    (50 live), 16/24 = narrow tiles.  shift = 1: the capture starts at an odd sample of its allocation, so every class's 16-byte
+    alignment falls the other way (the other tap image)."""
+    P, Po = make_both(10, [7000], ['IQ'])
+    assert (P.UP, P.DOWN) == (3, 625)
+    C, k = P.IN_CHUNK_SIZE, 4
+    offs = _offsets(n_ch, 2.0e6, 100 + n_ch)
+    xh = _sig(k * C + 1, P.SRATE, offs[::7], 5 + n_ch)
+    x = xh[shift:shift + k * C]
+    xd = torch.from_numpy(xh).cuda()[shift:shift + k * C]
+    cb = _channel_bank(P, offs, k * C, 2, 128)
+    _, iq = cb.process(xd)
+    assert all(b.k1_last == 3 for b in cb.banks), [b.k1_last for b in cb.banks]
+    got = [v.cpu().numpy().copy() for v in iq]
+    cb0 = _channel_bank(P, offs, k * C, 0, 128)
+    _, iq0 = cb0.process(xd)
+    assert all(b.k1_last == 1 for b in cb0.banks)
+    for c in range(n_ch):
+        assert_parity(got[c], iq0[c].cpu().numpy(), "chan K1 vs fp32 K1, channel %d" % c, rel_tol=2e-5, snr_min=90)
+    for c in sorted({0, 1, n_ch // 2, n_ch - 9, n_ch - 1}):
+        assert_parity(got[c], _oracle_iq(Po, offs[c], x), "chan K1 vs oracle, channel %d" % c)
+
+
+def test_chan_k1_even_down_geometry():
+    """8 MS/s -> 48 kHz (3/500: DOWN even, one parity, three classes), 32 channels, 5 chunks."""
+    P, Po = make_both(8, [7000], ['IQ'])
+    assert (P.UP, P.DOWN) == (3, 500)
+    C, k, n_ch = P.IN_CHUNK_SIZE, 5, 32
+    offs = _offsets(n_ch, 1.5e6, 9)
+    x = _sig(k * C, P.SRATE, offs[::5], 17)
+    xd = torch.from_numpy(x).cuda()
+    cb = _channel_bank(P, offs, k * C, 2, 128)
+    _, iq = cb.process(xd)
+    assert cb.banks[0].k1_last == 3
+    got = [v.cpu().numpy().copy() for v in iq]
+    cb0 = _channel_bank(P, offs, k * C, 0, 128)
+    _, iq0 = cb0.process(xd)
+    for c in range(n_ch):
+        assert_parity(got[c], iq0[c].cpu().numpy(), "chan K1 vs fp32 K1 (3/500), channel %d" % c, rel_tol=2e-5, snr_min=90)
+    for c in (0, 13, 31):
+        assert_parity(got[c], _oracle_iq(Po, offs[c], x), "chan K1 vs oracle (3/500), channel %d" % c)
+
+
+def test_chan_k1_streaming_calls_full_chain():
+    """Two consecutive calls (3 + 2 chunks: the second call's first outputs read the carried raw history on the edge warp)
+    through the whole AM/NFM/USB/CW/LSB chain of 20 channels in ONE bank on the tensor-core kernel: every channel against its own
+    oracle receiver, chunk at a time."""
+    from pysdr_b200.channelizer import ChannelBank
+    P, Po = make_both(10, [7000], ['USB'], af_bw_khz=[2])
+    n_ch, C = 20, P.IN_CHUNK_SIZE
+    offs = _offsets(n_ch, 1.0e6, 3)
+    modes = [['AM', 'NFM', 'USB', 'CW', 'LSB'][k % 5] for k in range(n_ch)]
+    afs = [[5e3, 10e3, 2e3, 500., 3e3][k % 5] for k in range(n_ch)]
+    n = np.arange(5 * C)
+    rng = np.random.default_rng(78)
+    x = ((rng.normal(size=len(n)) + 1j * rng.normal(size=len(n))) * 0.01).astype(np.complex128)
+    for k, f in enumerate(offs):
+        x = x + 0.02 * (1 + 0.5 * np.sin(2 * np.pi * (300.0 + 40 * k) * n / P.SRATE)) * np.exp(2j * np.pi * (f + 700.0) * n / P.SRATE)
+    x = x.astype(np.complex64)
+    cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=3 * C, group=32)
+    cb.banks[0].set_k1_mma(2)
+    xd = torch.from_numpy(x).cuda()
+    outs = []
+    for a, b in ((0, 3 * C), (3 * C, 5 * C)):
+        am, _ = cb.process(xd[a:b])
+        assert cb.banks[0].k1_last == 3
+        outs.append([v.cpu().numpy().copy() for v in am])
+    for k in range(n_ch):
+        Pk = rxo.make_P(P.SRATE, [7000e3], modes[k], foffset=100e3, af_bw=afs[k], bfo=700.0)
+        orx = odsp.Receiver(Pk, offs[k], 0, str(k), fast=True)
+        ref = np.concatenate([np.array(orx.demod_data(x[c * C:(c + 1) * C])) for c in range(5)])
+        assert_parity(np.concatenate([o[k] for o in outs]), ref, "channel %d (%s)" % (k, modes[k]))
+
+
+def test_chan_k1_impulse_indexing():
+    """A unit impulse at a known sample: every tap of the polyphase response lands at the same output index as with the FP32
+    kernel, for an impulse in each of the six classes' windows."""
+    P, _ = make_both(10, [7000], ['IQ'])
+    C = P.IN_CHUNK_SIZE
+    n = 3 * C
+    offs = _offsets(16, 1.0e6, 21)
+    for pos in (70001, 2 * C - 7, C + 625 * 11 + 208, C + 625 * 12 + 416):
+        x = torch.zeros(n, dtype=torch.complex64, device="cuda")
+        x[pos] = 1.0 + 0.5j
+        outs = []
+        for mode in (2, 0):
+            cb = _channel_bank(P, offs, n, mode, 128)
+            _, iq = cb.process(x)
+            assert cb.banks[0].k1_last == (3 if mode else 1)
+            outs.append(torch.stack(list(iq)).cpu().numpy().copy())
+        for c in (0, 7, 15):
+            nz2, nz0 = np.nonzero(outs[0][c])[0], np.nonzero(outs[1][c])[0]
+            assert nz0.size > 0 and nz2.min() == nz0.min() and nz2.max() == nz0.max(), (pos, c, nz2.min(), nz0.min(), nz2.max(), nz0.max())
+            assert np.max(np.abs(outs[0][c] - outs[1][c])) <= 2e-6 * np.max(np.abs(outs[1][c]))
+
+
+def test_chan_k1_many_tiles_per_cta_is_stable_and_reproducible():
+    """One 4 s block of config 5 (188 chunks) through a bank of 96 channels: 1506 tiles on 148 persistent CTAs, the sample ring
+    wraps ~50 times and the tap ring ~70 times per CTA.  Three runs must agree BIT FOR BIT (one issuing thread, fixed summation
+    order) and match the FP32 kernel."""
+    P, _ = make_both(10, [7000], ['IQ'])
+    C = P.IN_CHUNK_SIZE
+    n = 188 * C
+    offs = _offsets(96, 2.0e6, 33)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.view_as_complex(torch.randn((n, 2), generator=g, device="cuda", dtype=torch.float32) * 0.05)
+    cb0 = _channel_bank(P, offs, n, 0, 128)
+    _, iq0 = cb0.process(x)
+    ref = torch.stack([iq0[c] for c in (0, 40, 95)]).clone()
+    del cb0, iq0
+    cb = _channel_bank(P, offs, n, 1, 128)                # default mode: a call this long takes the tensor-core kernel by itself
+    first = None
+    for rep in range(3):
+        cb.banks[0].reset()
+        _, iq = cb.process(x)
+        assert cb.banks[0].k1_last == 3
+        got = torch.stack([iq[c] for c in (0, 40, 95)])
+        e = ((got - ref).abs().amax(dim=1) / ref.abs().amax(dim=1)).max().item()
+        assert e < 2e-5, (rep, e)
+        if first is None:
+            first = got.clone()
+        else:
+            assert torch.equal(torch.view_as_real(got), torch.view_as_real(first)), "run %d differs from run 0" % rep

@@ -289,3 +289,76 @@ def test_raster_channelizer_tables_against_the_oracle_resampler():
         ref = dec.resamp(x, lo)
         assert len(ref) == n_out
         assert np.max(np.abs(got[c] - ref)) <= 2e-6 * np.max(np.abs(ref)), c      # complex64 taps
+
+
+@pytest.mark.parametrize("up,down,lp,n_rx,n0,n_in,x_odd", [(3, 625, 334, 20, 0, 40000, 0), (3, 625, 334, 20, 213333, 30000, 1),
+                                                         (3, 500, 334, 9, 1000, 21000, 0), (2, 7, 5, 3, 14, 700, 1),
+                                                         (4, 9, 12, 100, 9 * 50, 1500, 0)])
+def test_many_channel_tensor_core_plan_emulated_in_numpy(up, down, lp, n_rx, n0, n_in, x_odd):
+    """k1_chan.cu's host side without a device (pysdr_k1chan_debug_plan): the classes' rows as they lie in the capture, the
+    alignment shifts, the hi/lo tap images in the tensor core's canonical K-major layout and the output indexing, emulated as
+    the kernel computes them (A row = 8*n_steps raw floats from the class's row start, D = A @ (B_hi + B_lo)) and compared
+    with the polyphase sum y[m] = sum_j G[p_m][j] x[n_m - j] of receiver.py:866 / params.py:405 for every tensor-core output;
+    the outputs left to the edge warp are exactly the rest of the call."""
+    import ctypes
+    from pysdr_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(up * 1000 + down)
+    lp_pad = lp + 3
+    g = np.zeros((n_rx, up, lp_pad), np.complex64)
+    g[:, :, :lp] = (rng.normal(size=(n_rx, up, lp)) + 1j * rng.normal(size=(n_rx, up, lp))).astype(np.complex64)
+    x = (rng.normal(size=n_in) + 1j * rng.normal(size=n_in)).astype(np.complex64)
+    m0 = (up * n0 + down - 1) // down
+    n_out = (up * (n0 + n_in) + down - 1) // down - m0
+    x_addr = 0x7f0000000000 + 8 * x_odd
+    out = np.zeros(16 + 8 * 8, np.int64)
+    n_img = lib.pysdr_k1chan_debug_plan(up, down, lp, n_rx, g.ctypes.data, lp_pad, n0, n_in, m0, n_out, x_addr, 1, out.ctypes.data, None, 0)
+    assert n_img > 0
+    img = np.zeros(n_img, np.float32)
+    assert lib.pysdr_k1chan_debug_plan(up, down, lp, n_rx, g.ctypes.data, lp_pad, n0, n_in, m0, n_out, x_addr, 1, out.ctypes.data,
+                                       img.ctypes.data, n_img) == n_img
+    used, q_a, out_lo, out_hi, n_steps, ngroups, nch, N, ncls, S = (int(v) for v in out[:10])
+    assert used == 1 and N == 2 * nch and N % 16 == 0 and ngroups * nch >= n_rx and n_steps % 4 == 0 and 4 * n_steps >= lp + 1
+    assert ncls == up * S and S == (2 if down % 2 else 1)
+    K = 8 * n_steps
+    img = img.reshape(up * 2, ngroups, n_steps, 2, 2, N // 8, 8, 4)          # [image][group][step][hi/lo][k chunk][n/8][n%8][k%4]
+    B = img.sum(axis=3, dtype=np.float64)                                      # hi + lo
+    B = B.transpose(0, 1, 2, 3, 6, 4, 5).reshape(up * 2, ngroups, K, N)       # [image][group][k][n]
+    xf = x.view(np.float32).astype(np.float64)
+    seen = np.zeros(n_out, np.int32)
+    y_ref = np.zeros((n_rx, n_out), np.complex128)
+    for m in range(n_out):
+        tt = (m0 + m) * down
+        nm, ph = tt // up, tt % up
+        j = np.arange(lp)
+        idx = nm - n0 - j
+        ok = (idx >= 0) & (idx < n_in)
+        if ok.all():
+            y_ref[:, m] = g[:, ph, :lp].astype(np.complex128) @ x[idx].astype(np.complex128)
+        else:
+            y_ref[:, m] = np.nan                                               # needs history / future samples: must be an edge output
+    for c in range(ncls):
+        i, s, o, im, rows, r0 = (int(v) for v in out[16 + 8 * c:16 + 8 * c + 6])
+        assert r0 >= 0 and ((x_addr + 8 * r0) % 16) == 0, "class %d row start not 16-byte aligned" % c
+        assert o == (i * down) // up
+        u = np.arange(rows)
+        q = q_a + s + S * u
+        idx = q * up + i - m0
+        assert (r0 + (rows - 1) * S * down) + K // 2 <= n_in, "last row of class %d reads past the capture" % c
+        starts = 2 * (r0 + u * S * down)
+        A = xf[starts[:, None] + np.arange(K)[None, :]]                          # [rows][K] raw floats, as the TMA boxes deliver them
+        for grp in range(ngroups):
+            D = A @ B[im, grp]                                                 # [rows][N]
+            for cl in range(nch):
+                rx = grp * nch + cl
+                if rx >= n_rx:
+                    assert not B[im, grp][:, 2 * cl:2 * cl + 2].any()
+                    continue
+                y = D[:, 2 * cl] + 1j * D[:, 2 * cl + 1]
+                live = (idx >= 0) & (idx < n_out)
+                ref = y_ref[rx, idx[live]]
+                assert not np.isnan(ref).any(), "a tensor-core row needs samples outside the capture"
+                assert np.max(np.abs(y[live] - ref)) <= 2e-6 * np.max(np.abs(ref)), (c, grp, cl)
+        seen[idx[(idx >= 0) & (idx < n_out)]] += 1
+    assert (seen[out_lo:out_hi] == 1).all() and not seen[:out_lo].any() and not seen[out_hi:].any()
+    assert out_hi - out_lo > 0.5 * n_out

@@ -78,6 +78,9 @@ def main():
     ap.add_argument("--sharded", action="store_true", help="multi-GPU time-sharded run (launch with torchrun)")
     ap.add_argument("--channels", type=int, default=1024)
     ap.add_argument("--block-chunks", type=int, default=188, help="IN_CHUNK_SIZE chunks per streaming block (188 = 4.0 s)")
+    ap.add_argument("--group", type=int, default=128, help="receivers per bank (any-offsets mode): 128 = two column groups of 64 "
+                    "channels per bank on the tensor-core K1, 96 = one group of 96")
+    ap.add_argument("--k1", type=int, default=1, help="0: FP32 tap-stationary K1 (r01/r02-early path), 1: tensor-core K1s where they apply")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     args = ap.parse_args()
@@ -95,7 +98,9 @@ def main():
     modes = [['AM', 'NFM', 'USB', 'CW'][k % 4] for k in range(args.channels)]
     afs = [[5e3, 10e3, 2e3, 500.][k % 4] for k in range(args.channels)]
     x = synth_iq(n, P.SRATE, offs[:4], modes[:4], seed=5, device="cuda")
-    cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=n)
+    cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=n, group=args.group)
+    for b in cb.banks:
+        b.set_k1_mma(args.k1)
     for _ in range(args.warmup):
         cb.process(x)
     torch.cuda.synchronize()
@@ -113,6 +118,16 @@ def main():
     n_out = cb.n_out
     flops = 8.0 * lp * n_out * args.channels
     sec = n / P.SRATE
+    # stage times of the same step (CUDA events inside the library, separate pass: the event records break the PDL chain)
+    for b in cb.banks:
+        b.set_timing(True)
+    for _ in range(2):
+        cb.process(x)
+    tm = [b.get_timing() for b in cb.banks]
+    stages = {"k1_ms": sum(t['k1_ms'] / t['calls'] for t in tm), "af_filter_ms": sum(t['front_rest_ms'] / t['calls'] for t in tm),
+              "agc_back_ms": sum(t['back_ms'] / t['calls'] for t in tm)}
+    cb_k1_last = cb.banks[0].k1_last
+    k1_kernel = {0: "k1_generic", 1: "k1_fast (FP32 tap-stationary)", 2: "k1_mma", 3: "k1_chan (tcgen05 split-TF32, channels as columns)"}[cb.banks[0].k1_last]
     # the same channels' baseband IQ through the raster channelizer (wola.cu): K1 only
     from pysdr_b200.channelizer import RasterChannelizer
     rc = RasterChannelizer(P, offs[0], 9600.0, args.channels)
@@ -152,12 +167,14 @@ def main():
                                                   "realtime_factor": sec / (ms_r / 1e3),
                                                   "one_hour_capture_s_on_1_gpu": 3600.0 / (sec / (ms_r / 1e3))}}))
     del cbr
-    print(json.dumps({"workload": "cfg5 geometry: %d channels, 9.6 kHz raster, 10 MS/s, 3/625, %.2f s blocks (%d chunks), modes AM/NFM/USB/CW"
+    print(json.dumps({"workload": "cfg5 geometry: %d channels (any offsets: one K1 contraction per bank), 10 MS/s, 3/625, %.2f s blocks (%d chunks), modes AM/NFM/USB/CW"
                                   % (args.channels, sec, args.block_chunks),
                       "ms_per_block": ms, "wall_ms_per_block": wall * 1e3, "Msamples_per_s": n / ms / 1e3,
-                      "realtime_factor": sec / (ms / 1e3), "k1_TFLOP_per_s(8 flop/tap)": flops / ms / 1e9,
+                      "realtime_factor": sec / (ms / 1e3), "k1_kernel": k1_kernel, "stage_ms_per_block": stages,
+                      "k1_TFLOP_per_s(8 flop/tap)": flops / stages["k1_ms"] / 1e9,
+                      "k1_tensor_TFLOP_per_s(3 split-TF32 products)": (3 * flops / stages["k1_ms"] / 1e9) if cb_k1_last == 3 else None,
                       "one_hour_capture_s_on_1_gpu": 3600.0 / (sec / (ms / 1e3)),
-                      "gpu_launches_per_block": launches_per_block, "groups": n_groups}))
+                      "gpu_launches_per_block": launches_per_block, "groups": n_groups, "receivers_per_bank": args.group}))
 
 
 if __name__ == "__main__":
