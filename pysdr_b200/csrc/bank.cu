@@ -950,7 +950,8 @@ struct pysdr_bank {
     int back_grid;
     // host-chunk executive (pysdr_bank_process_host): pinned staging + own device buffers, allocated on first use
     float2 *hc_h_in, *hc_d_in, *hc_d_iq;
-    float *hc_d_am, *hc_d_dc;
+    float *hc_d_am, *hc_d_dc;                 // device result rows — or, when the device can address page-locked host memory
+    bool hc_zero_copy;                       // directly, the device view of hc_h_out: the back kernel stores its results there
     char *hc_h_out;                          // pinned: am [n_rx][2 max_out] f32 | iq [n_rx][max_out] c64 | am_dc [n_rx][2 max_out] f32
     // seek() folded into the next process_front / process_back (no launch of its own)
     bool lazy_seek, lazy_reset_agc;
@@ -1053,7 +1054,7 @@ extern "C" int pysdr_bank_create(const pysdr_bank_config *cfg, pysdr_bank **out)
     b->force_unfused = false; b->defer_peaks = false; b->peaks_deferred = false;
     b->bar_count = 0; b->back_grid = 0;
     b->lazy_seek = false; b->lazy_reset_agc = false;
-    b->hc_h_in = nullptr; b->hc_d_in = nullptr; b->hc_d_iq = nullptr; b->hc_d_am = nullptr; b->hc_d_dc = nullptr; b->hc_h_out = nullptr;
+    b->hc_h_in = nullptr; b->hc_d_in = nullptr; b->hc_d_iq = nullptr; b->hc_d_am = nullptr; b->hc_d_dc = nullptr; b->hc_h_out = nullptr; b->hc_zero_copy = false;
     for (int r = 0; r < PYSDR_MAX_RX; ++r) {
         b->inc[r] = 0; b->acc0[r] = 0; b->mode[r] = PYSDR_MODE_IQ; b->af_cplx[r] = 0; b->bfo_inc[r] = 0;
         b->demod_set[r] = false;
@@ -1079,7 +1080,8 @@ extern "C" int pysdr_bank_destroy(pysdr_bank *b) {
     cudaFree(b->d_H);
     if (b->hc_h_in) cudaFreeHost(b->hc_h_in);
     if (b->hc_h_out) cudaFreeHost(b->hc_h_out);
-    cudaFree(b->hc_d_in); cudaFree(b->hc_d_iq); cudaFree(b->hc_d_am); cudaFree(b->hc_d_dc);
+    cudaFree(b->hc_d_in); cudaFree(b->hc_d_iq);
+    if (!b->hc_zero_copy) { cudaFree(b->hc_d_am); cudaFree(b->hc_d_dc); }
     if (!b->c_external) cudaFree(b->d_C);
     k1_mma_plan_destroy(b->mma);
     k1_chan_plan_destroy(b->chan);
@@ -1979,9 +1981,22 @@ extern "C" int pysdr_bank_process_host(pysdr_bank *b, const void *h_iq, int64_t 
         CUDA_TRY(cudaHostAlloc(&b->hc_h_in, sizeof(float2) * (size_t)c.max_in, cudaHostAllocDefault));
         CUDA_TRY(cudaHostAlloc(&b->hc_h_out, 3 * am_bytes, cudaHostAllocDefault));
         CUDA_TRY(cudaMalloc(&b->hc_d_in, sizeof(float2) * (size_t)c.max_in));
-        CUDA_TRY(cudaMalloc(&b->hc_d_am, am_bytes));
-        CUDA_TRY(cudaMalloc(&b->hc_d_dc, am_bytes));
         CUDA_TRY(cudaMalloc(&b->hc_d_iq, am_bytes));
+        // the audio rows are a few KB per receiver and written once, by the last kernel of the step: let it store them
+        // straight into the pinned result block over PCIe instead of paying two more copy operations per chunk
+        int dev = 0, can = 0;
+        void *dp = nullptr;
+        b->hc_zero_copy = !getenv("PYSDR_NO_ZERO_COPY") && cudaGetDevice(&dev) == cudaSuccess &&
+                          cudaDeviceGetAttribute(&can, cudaDevAttrCanUseHostPointerForRegisteredMem, dev) == cudaSuccess && can &&
+                          cudaHostGetDevicePointer(&dp, b->hc_h_out, 0) == cudaSuccess && dp;
+        cudaGetLastError();
+        if (b->hc_zero_copy) {
+            b->hc_d_am = (float *)dp;
+            b->hc_d_dc = (float *)((char *)dp + 2 * am_bytes);
+        } else {
+            CUDA_TRY(cudaMalloc(&b->hc_d_am, am_bytes));
+            CUDA_TRY(cudaMalloc(&b->hc_d_dc, am_bytes));
+        }
     }
     const void *src = h_iq;
     cudaPointerAttributes pa;
@@ -2001,9 +2016,11 @@ extern "C" int pysdr_bank_process_host(pysdr_bank *b, const void *h_iq, int64_t 
     float2 *o_iq = (float2 *)(b->hc_h_out + am_bytes);
     if (n_out > 0) {
         const size_t w = sizeof(float) * 2 * (size_t)n_out;                      // complex rows use all of it, real rows the first half
-        CUDA_TRY(cudaMemcpy2DAsync(o_am, sizeof(float) * row, b->hc_d_am, sizeof(float) * row, w, c.n_rx, cudaMemcpyDeviceToHost, st));
-        if (want_dc)
-            CUDA_TRY(cudaMemcpy2DAsync(o_dc, sizeof(float) * row, b->hc_d_dc, sizeof(float) * row, w, c.n_rx, cudaMemcpyDeviceToHost, st));
+        if (!b->hc_zero_copy) {
+            CUDA_TRY(cudaMemcpy2DAsync(o_am, sizeof(float) * row, b->hc_d_am, sizeof(float) * row, w, c.n_rx, cudaMemcpyDeviceToHost, st));
+            if (want_dc)
+                CUDA_TRY(cudaMemcpy2DAsync(o_dc, sizeof(float) * row, b->hc_d_dc, sizeof(float) * row, w, c.n_rx, cudaMemcpyDeviceToHost, st));
+        }
         if (want_iq) {
             if (any_sync)
                 CUDA_TRY(cudaMemcpy2DAsync(o_iq, sizeof(float) * row, b->hc_d_iq, sizeof(float2) * (size_t)b->max_out, w, c.n_rx,
