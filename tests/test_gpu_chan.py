@@ -169,3 +169,78 @@ def test_chan_k1_many_tiles_per_cta_is_stable_and_reproducible():
             first = got.clone()
         else:
             assert torch.equal(torch.view_as_real(got), torch.view_as_real(first)), "run %d differs from run 0" % rep
+
+
+def test_chan_k1_retune_mid_stream_rebuilds_the_tap_images():
+    """set_freq between two calls: the folded taps of the retuned channels change, so the host rebuilds the class images
+    (k1_chan_upload_taps behind g_dirty); both calls and every channel equal the FP32 kernel driven the same way (whose retune
+    is checked against the oracle in test_gpu_edges.py::test_retune_and_filter_swap_mid_batch_stream)."""
+    P, _ = make_both(10, [7000], ['IQ'])
+    C, n_ch = P.IN_CHUNK_SIZE, 16
+    offs = _offsets(n_ch, 1.5e6, 77)
+    new = {3: offs[3] + 12345.0, 11: -offs[11]}
+    x = _sig(6 * C, P.SRATE, [offs[3], new[3], offs[11], new[11]], 19)
+    xd = torch.from_numpy(x).cuda()
+    outs = []
+    for mode in (2, 0):
+        cb = _channel_bank(P, offs, 3 * C, mode, 128)
+        b = cb.banks[0]
+        _, iq = cb.process(xd[:3 * C])
+        first = torch.stack(list(iq)).cpu().numpy().copy()
+        for r, f in new.items():
+            b.set_freq(r, f)
+        _, iq = cb.process(xd[3 * C:])
+        assert b.k1_last == (3 if mode else 1)
+        outs.append((first, torch.stack(list(iq)).cpu().numpy().copy()))
+    for c in range(n_ch):
+        for part in (0, 1):
+            assert_parity(outs[0][part][c], outs[1][part][c], "retune, call %d, channel %d: chan vs fp32 K1" % (part, c), rel_tol=2e-5, snr_min=90)
+    # the retune did something: channel 3 moved onto the second test carrier (x holds one at offs[3] + 500 Hz and one at
+    # new[3] + 500 Hz), so its second call still sees a strong in-band tone
+    p1 = np.mean(np.abs(outs[0][1][3]) ** 2)
+    assert p1 > 1e-5, p1
+
+
+def test_chan_k1_time_shards_emulated_on_one_gpu():
+    """Two time shards of a 20-channel bank played one after the other on ONE device (the 2-GPU version is test_gpu_multi.py):
+    each shard's K1 call starts at a non-zero absolute position with its filter history in place in front of x (the edge warp
+    reads it there) and one warm-up chunk; sharded audio through the O(1) AGC carry equals the single-stream FP32 run."""
+    import ctypes
+    from pysdr_b200._lib import check
+    from pysdr_b200.bank import _stream_ptr
+    from pysdr_b200.channelizer import ChannelBank
+    from pysdr_b200.dist import AGC_SUMMARY_LEN, ShardedCapture
+    P, _ = make_both(10, [7000], ['USB'], af_bw_khz=[2])
+    C, n_ch, world, cpr = P.IN_CHUNK_SIZE, 20, 2, 9
+    offs = _offsets(n_ch, 1.0e6, 5)
+    modes = [['AM', 'NFM', 'USB', 'CW', 'LSB'][k % 5] for k in range(n_ch)]
+    afs = [[5e3, 10e3, 2e3, 500., 3e3][k % 5] for k in range(n_ch)]
+    n = world * cpr * C
+    x = _sig(n, P.SRATE, offs[::3], 23)
+    env = np.ones(n, np.float32)
+    env[4 * C:6 * C] = 4.0                                          # a burst in shard 0 whose AGC decay crosses into shard 1
+    xd = torch.from_numpy(x * env).cuda()
+    single = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=n, group=32)
+    single.banks[0].set_k1_mma(0)
+    am, _ = single.process(xd)
+    ref = [a.cpu().numpy().copy() for a in am]
+    shards, all_sum = [], torch.zeros((world, n_ch, AGC_SUMMARY_LEN), dtype=torch.float64, device="cuda")
+    for r in range(world):
+        cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=(cpr + 1) * C, group=32)
+        b = cb.banks[0]
+        b.set_k1_mma(2)
+        sh = ShardedCapture(b, cb.banks[0].P, r, world, cpr)
+        assert sh.o1
+        pl = sh.plan
+        sh.front(xd[pl['first_sample']:pl['start'] + pl['n']], copy_own=False)
+        assert b.k1_last == 3
+        check(b.lib.pysdr_bank_agc_summary(b.h, pl['warm_chunks'], ctypes.c_void_p(all_sum[r].data_ptr()), _stream_ptr()))
+        shards.append(sh)
+    for r in range(world):
+        sh, b = shards[r], shards[r].bank
+        got, _, _ = b.process_back_carry(all_sum, r, want_dc=False, skip_blocks=sh.plan['warm_chunks'])
+        m0 = odsp.n_out_total(r * cpr * C, P.UP, P.DOWN)
+        for k in range(n_ch):
+            g = got[k][sh.skip_out:].cpu().numpy()
+            # tensor-core K1 on the sharded side, FP32 K1 on the single stream: the north-star gate (same-kernel runs agree to 2e-5)
+            assert_parity(g, ref[k][m0:m0 + len(g)], "shard %d channel %d (%s) vs single stream" % (r, k, modes[k]))
