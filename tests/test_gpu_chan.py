@@ -69,12 +69,15 @@ def test_chan_k1_cfg5_geometry_matches_oracle_and_fp32_kernel(n_ch, shift):
         assert_parity(got[c], _oracle_iq(Po, offs[c], x), "chan K1 vs oracle, channel %d" % c)
 
 
-def test_chan_k1_even_down_geometry():
-    """8 MS/s -> 48 kHz (3/500: DOWN even, one parity, three classes), 32 channels, 5 chunks."""
-    P, Po = make_both(8, [7000], ['IQ'])
-    assert (P.UP, P.DOWN) == (3, 500)
+@pytest.mark.parametrize("srate_mhz,updown,span_hz", [(8, (3, 500), 1.5e6), (2.048, (3, 128), 0.4e6)])
+def test_chan_k1_even_down_geometry(srate_mhz, updown, span_hz):
+    """DOWN even (one parity, three classes), 32 channels, 5 chunks: 8 MS/s -> 48 kHz (3/500), and 2.048 MS/s -> 48 kHz (3/128),
+    where the 334-tap window is longer than two super-periods — k1_mma.cu's row-per-super-period layout does not cover that, a
+    row per output instant does."""
+    P, Po = make_both(srate_mhz, [7000], ['IQ'])
+    assert (P.UP, P.DOWN) == updown
     C, k, n_ch = P.IN_CHUNK_SIZE, 5, 32
-    offs = _offsets(n_ch, 1.5e6, 9)
+    offs = _offsets(n_ch, span_hz, 9)
     x = _sig(k * C, P.SRATE, offs[::5], 17)
     xd = torch.from_numpy(x).cuda()
     cb = _channel_bank(P, offs, k * C, 2, 128)
@@ -84,9 +87,9 @@ def test_chan_k1_even_down_geometry():
     cb0 = _channel_bank(P, offs, k * C, 0, 128)
     _, iq0 = cb0.process(xd)
     for c in range(n_ch):
-        assert_parity(got[c], iq0[c].cpu().numpy(), "chan K1 vs fp32 K1 (3/500), channel %d" % c, rel_tol=2e-5, snr_min=90)
+        assert_parity(got[c], iq0[c].cpu().numpy(), "chan K1 vs fp32 K1 (%d/%d), channel %d" % (updown + (c,)), rel_tol=2e-5, snr_min=90)
     for c in (0, 13, 31):
-        assert_parity(got[c], _oracle_iq(Po, offs[c], x), "chan K1 vs oracle (3/500), channel %d" % c)
+        assert_parity(got[c], _oracle_iq(Po, offs[c], x), "chan K1 vs oracle (%d/%d), channel %d" % (updown + (c,)))
 
 
 def test_chan_k1_streaming_calls_full_chain():

@@ -293,7 +293,7 @@ def test_raster_channelizer_tables_against_the_oracle_resampler():
 
 @pytest.mark.parametrize("up,down,lp,n_rx,n0,n_in,x_odd", [(3, 625, 334, 20, 0, 40000, 0), (3, 625, 334, 20, 213333, 30000, 1),
                                                          (3, 500, 334, 9, 1000, 21000, 0), (2, 7, 5, 3, 14, 700, 1),
-                                                         (4, 9, 12, 100, 9 * 50, 1500, 0)])
+                                                         (4, 9, 12, 100, 9 * 50, 1500, 0), (1, 50, 1001, 16, 0, 60000, 1)])
 def test_many_channel_tensor_core_plan_emulated_in_numpy(up, down, lp, n_rx, n0, n_in, x_odd):
     """k1_chan.cu's host side without a device (pysdr_k1chan_debug_plan): the classes' rows as they lie in the capture, the
     alignment shifts, the hi/lo tap images in the tensor core's canonical K-major layout and the output indexing, emulated as
