@@ -165,30 +165,66 @@ class ShardedChannelBank:
                 iq.extend(q)
             return am, iq
         # O(1) carry: one all-gather of 19 doubles per channel per rank (152 KB per rank at 1024 channels, whatever the shard
-        # length; the peak gather was 691 MB at config-5 scale), then every bank enters from the summaries of the earlier ranks
+        # length; the peak gather was 691 MB at config-5 scale), then every bank enters from the summaries of the earlier ranks.
+        # The banks are driven with prepared ctypes arguments and the per-channel views are built once per output length: the
+        # generic per-bank Python path (parameter re-reads, 3 x 128 tensor views and as many slices per bank) cost ~16 ms per
+        # step for 1024 channels, three times the GPU work.  After changing MODE / AF_BW / BFO call invalidate().
         G = cb.GROUP
-        if getattr(self, '_sum', None) is None:
-            dev = cb.device
-            self._sum = torch.zeros((len(cb.banks), G, AGC_SUMMARY_LEN), dtype=torch.float64, device=dev)
-            self._all = torch.zeros((self.world, len(cb.banks), G, AGC_SUMMARY_LEN), dtype=torch.float64, device=dev)
+        dev = cb.device
         w = self.plan['warm_chunks']
-        for k, sh in enumerate(self.shards):
-            sh.front(xbuf, copy_own=False)
-            check(sh.bank.lib.pysdr_bank_agc_summary(sh.bank.h, w, ctypes.c_void_p(self._sum[k].data_ptr()), _stream_ptr()))
+        p = self.plan
+        C = int(cb.P.IN_CHUNK_SIZE)
+        if getattr(self, '_fast', None) is None:
+            nb = len(cb.banks)
+            self._sum = torch.zeros((nb, G, AGC_SUMMARY_LEN), dtype=torch.float64, device=dev)
+            self._all = torch.zeros((self.world, nb, G, AGC_SUMMARY_LEN), dtype=torch.float64, device=dev)
+            self._per_bank = torch.zeros((nb, self.world, G, AGC_SUMMARY_LEN), dtype=torch.float64, device=dev)
+            self._fast = []
+            for k, sh in enumerate(self.shards):
+                b = sh.bank
+                b.sync_demod()
+                compact = None if b.n_rx == G else torch.zeros((self.world, b.n_rx, AGC_SUMMARY_LEN), dtype=torch.float64, device=dev)
+                self._fast.append((b, b.lib, b.h, b._iq_copy_ptr(), ctypes.c_void_p(sh.peaks_ext.data_ptr()),
+                                   ctypes.c_void_p(self._sum[k].data_ptr()), compact,
+                                   ctypes.c_void_p((compact if compact is not None else self._per_bank[k]).data_ptr()),
+                                   ctypes.c_void_p(b._am.data_ptr()), b.max_out))
+            self._views_for = None
+        st = _stream_ptr()
+        n_out = ctypes.c_int64(0)
+        if w:
+            seek_to, x_ptr, n_in, halo_flag = p['start'] - w * C, xbuf.data_ptr() + 8 * p['halo'], xbuf.numel() - p['halo'], 1 if p['halo'] > 0 else 0
+        else:
+            seek_to, x_ptr, n_in, halo_flag = 0, xbuf.data_ptr() + 8 * p['lead'], xbuf.numel() - p['lead'], 0
+        cb.banks[0]._check_input(xbuf[p['halo'] if w else p['lead']:])     # dtype / device / contiguity / capacity, once per step
+        xp = ctypes.c_void_p(x_ptr)
+        for b, lib, h, iq_p, peaks_p, sum_p, compact, sums_p, am_p, max_out in self._fast:
+            check(lib.pysdr_bank_seek(h, int(seek_to), st))
+            check(lib.pysdr_bank_process_front(h, xp, n_in, halo_flag, iq_p, max_out, peaks_p, ctypes.byref(n_out), st))
+            check(lib.pysdr_bank_agc_summary(h, w, sum_p, st))
         if self.world > 1:
             dist.all_gather_into_tensor(self._all, self._sum)            # the one collective, for every channel
-            per_bank = self._all.permute(1, 0, 2, 3).contiguous()        # [bank][rank][G][19]
+            self._per_bank.copy_(self._all.permute(1, 0, 2, 3))          # [bank][rank][G][19]
         else:
-            per_bank = self._sum.unsqueeze(1)
-        for k, sh in enumerate(self.shards):
-            b = sh.bank
-            # rows of a bank's summary block are its n_rx receivers followed by unused rows: compact to [rank][n_rx][19]
-            sums = per_bank[k][:, :b.n_rx, :].contiguous() if b.n_rx != G else per_bank[k]
-            a, q, _ = b.process_back_carry(sums, self.rank, want_dc=False, skip_blocks=w)
-            ks = sh.skip_out
-            am.extend(v[ks:] for v in a)
-            iq.extend(v[ks:] for v in q)
-        return am, iq
+            self._per_bank.copy_(self._sum.unsqueeze(1))
+        for k, (b, lib, h, iq_p, peaks_p, sum_p, compact, sums_p, am_p, max_out) in enumerate(self._fast):
+            if compact is not None:                                      # a bank with fewer receivers: rows [rank][n_rx][19]
+                compact.copy_(self._per_bank[k][:, :b.n_rx, :])
+            check(lib.pysdr_bank_process_back_carry(h, sums_p if self.rank else None, self.rank, w, am_p, None, max_out, st))
+        if self._views_for != n_out.value:
+            self._views = ([], [])
+            for sh in self.shards:
+                b = sh.bank
+                b.n_out = n_out.value
+                a, q, _ = b.views()
+                ks = sh.skip_out
+                self._views[0].extend(v[ks:] for v in a)
+                self._views[1].extend(v[ks:] for v in q)
+            self._views_for = n_out.value
+        return self._views
+
+    def invalidate(self):
+        """Call after changing MODE / AF_BW / BFO on the banks' parameter objects (see step)."""
+        self._fast = None
 
 
 def raster_tables(P, f0_hz, df_hz, n_ch, nd=3125):

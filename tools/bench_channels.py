@@ -35,26 +35,52 @@ def run_sharded(args):
     offs = raster_offsets(args.channels, 9600.0, 0.0)
     modes = [['AM', 'NFM', 'USB', 'CW'][k % 4] for k in range(args.channels)]
     afs = [[5e3, 10e3, 2e3, 500.][k % 4] for k in range(args.channels)]
-    cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=(cpr + 1) * C, device=dev, raster=(offs[0], 9600.0))
+    cb = ChannelBank(P, offs, modes, af_bw=afs, bfo=700.0, max_in=(cpr + 1) * C, device=dev,
+                     raster=None if args.any_offsets else (offs[0], 9600.0), group=args.group)
     sh = ShardedChannelBank(cb, rank, world, cpr)
     pl = sh.plan
     n_loc = pl['lead'] + pl['n']
     xdev = synth_iq(n_loc, P.SRATE, offs[:4], modes[:4], seed=5, device=dev, n0=pl['first_sample'])
     hx = torch.empty(n_loc, dtype=torch.complex64, pin_memory=True)
     hx.copy_(xdev)
+    # every step's samples come from pinned host memory inside the timed region.  Double-buffered (default): the copy of step
+    # k + 1 runs on a copy stream while step k computes — what a streaming run over an hour-long shard does; --no-overlap: copy,
+    # then compute, on one stream (the r02-early number)
+    xbufs = [xdev, torch.empty_like(xdev)] if args.overlap else [xdev]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ev_copied = [torch.cuda.Event() for _ in xbufs]
+    ev_done = [torch.cuda.Event() for _ in xbufs]
 
-    def step():
-        xdev.copy_(hx, non_blocking=True)                   # this rank's shard (+ warm-up and halo) from pinned host memory
-        am, _ = sh.step(xdev)
+    def issue_copy(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_done[i])              # the step that last read this buffer has finished
+            xbufs[i].copy_(hx, non_blocking=True)           # this rank's shard (+ warm-up and halo) from pinned host memory
+            ev_copied[i].record(copy_stream)
+
+    def run(steps):
+        am = None
+        if args.overlap:
+            issue_copy(0)
+            for k in range(steps):
+                i = k & 1
+                if k + 1 < steps:
+                    issue_copy(i ^ 1)
+                torch.cuda.current_stream(dev).wait_event(ev_copied[i])
+                am, _ = sh.step(xbufs[i])
+                ev_done[i].record(torch.cuda.current_stream(dev))
+        else:
+            for _ in range(steps):
+                xdev.copy_(hx, non_blocking=True)
+                am, _ = sh.step(xdev)
         return am
 
-    for _ in range(args.warmup):
-        step()
+    for e in ev_done:
+        e.record(torch.cuda.current_stream(dev))
+    run(args.warmup)
     dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        am = step()
+    am = run(args.steps)
     e1.record()
     dist.barrier(); torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
@@ -62,10 +88,14 @@ def run_sharded(args):
     ms = float(t.item())
     if rank == 0:
         sec = world * pl['n'] / P.SRATE
-        print(json.dumps({"workload": "cfg5: %d channels on a 9.6 kHz raster, 10 MS/s -> 48 kHz (3/625), %.1f s of signal time-sharded "
+        print(json.dumps({"workload": "cfg5: %d channels %s, 10 MS/s -> 48 kHz (3/625), %.1f s of signal time-sharded "
                                       "over %d GPUs (%.1f s = %d chunks per rank, resident per rank), H2D of every shard inside the "
-                                      "timed region, AGC carry = one all-gather of 19 doubles per channel per rank"
-                                      % (args.channels, sec, world, pl['n'] / P.SRATE, cpr),
+                                      "timed region (%s), AGC carry = one all-gather of 19 doubles per channel per rank"
+                                      % (args.channels, "at any offsets (K1 = k1_chan, tensor cores)" if args.any_offsets else
+                                         "on a 9.6 kHz raster (K1 = wola.cu)", sec, world, pl['n'] / P.SRATE, cpr,
+                                         "double-buffered: the next step's copy runs under this step's kernels" if args.overlap else
+                                         "copy, then compute, on one stream"),
+                          "k1_last": cb.banks[0].k1_last,
                           "n_gpus": world, "ms_per_step": ms, "Msamples_per_s": world * pl['n'] / ms / 1e3,
                           "realtime_factor": sec / (ms / 1e3), "one_hour_capture_s": 3600.0 / (sec / (ms / 1e3)),
                           "h2d_bytes_per_rank_per_step": int(n_loc * 8), "collective_bytes_per_rank": int(args.channels * 19 * 8),
@@ -78,6 +108,8 @@ def main():
     ap.add_argument("--sharded", action="store_true", help="multi-GPU time-sharded run (launch with torchrun)")
     ap.add_argument("--channels", type=int, default=1024)
     ap.add_argument("--block-chunks", type=int, default=188, help="IN_CHUNK_SIZE chunks per streaming block (188 = 4.0 s)")
+    ap.add_argument("--any-offsets", action="store_true", help="sharded mode: no raster, every bank's K1 on the tensor cores (k1_chan)")
+    ap.add_argument("--no-overlap", dest="overlap", action="store_false", help="sharded mode: copy then compute on one stream")
     ap.add_argument("--group", type=int, default=128, help="receivers per bank (any-offsets mode): 128 = two column groups of 64 "
                     "channels per bank on the tensor-core K1, 96 = one group of 96")
     ap.add_argument("--k1", type=int, default=1, help="0: FP32 tap-stationary K1 (r01/r02-early path), 1: tensor-core K1s where they apply")
