@@ -1250,6 +1250,7 @@ extern "C" int pysdr_bank_adopt_c_memory(pysdr_bank *b, void *d_ptr, int64_t row
 
 extern "C" int pysdr_bank_set_k1_external(pysdr_bank *b, int on) {
     if (!b) { pysdr_set_error("null bank"); return PYSDR_ERR_ARG; }
+    if (b->k1_external && !on) b->g_dirty = true;     // back to the bank's own K1: (re)build the tap images on the next call
     b->k1_external = on != 0;
     return PYSDR_OK;
 }
@@ -1421,7 +1422,10 @@ static int upload_folded_taps(pysdr_bank *b, cudaStream_t st) {
     CUDA_TRY(cudaMemcpyAsync(b->d_g, g.data(), sizeof(float2) * g.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));      // g is a stack-owned staging vector
     if (b->mma) { int rc = k1_mma_upload_taps(b->mma, g.data(), b->lp_pad, st); if (rc) return rc; }
-    if (b->chan) { int rc = k1_chan_upload_taps(b->chan, g.data(), b->lp_pad, st); if (rc) return rc; }
+    if (b->chan && !b->k1_external) {        // (a bank fed by the raster channelizer never runs its own K1: no 8 MB tap image for it)
+        int rc = k1_chan_upload_taps(b->chan, g.data(), b->lp_pad, st);
+        if (rc) return rc;
+    }
     b->g_dirty = false;
     return PYSDR_OK;
 }
