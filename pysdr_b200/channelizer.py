@@ -104,7 +104,7 @@ class ChannelBank:
                 self._views[0].extend(a)
                 self._views[1].extend(q)
             self._views_for = self.n_out
-        return self._views
+        return list(self._views[0]), list(self._views[1])      # the cached views, in lists the caller may keep or edit
 
     def _advance(self, x):
         """Raster mode: the channelizer's own stream position and raw history move once all banks have processed the block, so
@@ -220,7 +220,7 @@ class ShardedChannelBank:
                 self._views[0].extend(v[ks:] for v in a)
                 self._views[1].extend(v[ks:] for v in q)
             self._views_for = n_out.value
-        return self._views
+        return list(self._views[0]), list(self._views[1])      # the cached views, in lists the caller may keep or edit
 
     def invalidate(self):
         """Call after changing MODE / AF_BW / BFO on the banks' parameter objects (see step)."""
