@@ -43,6 +43,14 @@ def run_sharded(args):
     xdev = synth_iq(n_loc, P.SRATE, offs[:4], modes[:4], seed=5, device=dev, n0=pl['first_sample'])
     hx = torch.empty(n_loc, dtype=torch.complex64, pin_memory=True)
     hx.copy_(xdev)
+    raw16 = None
+    if args.cs16:                                           # the int16 I/Q stream SDR hardware delivers (reference receiver.py:609-617)
+        import ctypes
+        from pysdr_b200._lib import check, load
+        lib = load()
+        h16 = torch.empty((n_loc, 2), dtype=torch.int16, pin_memory=True)
+        h16.copy_((torch.view_as_real(xdev) * 2048.0).round().clamp_(-32768, 32767).to(torch.int16))
+        raw16 = [torch.empty((n_loc, 2), dtype=torch.int16, device=dev) for _ in range(2 if args.overlap else 1)]
     # every step's samples come from pinned host memory inside the timed region.  Double-buffered (default): the copy of step
     # k + 1 runs on a copy stream while step k computes — what a streaming run over an hour-long shard does; --no-overlap: copy,
     # then compute, on one stream (the r02-early number)
@@ -54,7 +62,12 @@ def run_sharded(args):
     def issue_copy(i):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_done[i])              # the step that last read this buffer has finished
-            xbufs[i].copy_(hx, non_blocking=True)           # this rank's shard (+ warm-up and halo) from pinned host memory
+            if raw16 is not None:                           # 4 bytes per sample over PCIe, scaled to complex64 on the device
+                raw16[i].copy_(h16, non_blocking=True)
+                check(lib.pysdr_cs16_to_cf32(ctypes.c_void_p(raw16[i].data_ptr()), ctypes.c_void_p(xbufs[i].data_ptr()), n_loc,
+                                             1.0 / 2048.0, ctypes.c_void_p(copy_stream.cuda_stream)))
+            else:
+                xbufs[i].copy_(hx, non_blocking=True)       # this rank's shard (+ warm-up and halo) from pinned host memory
             ev_copied[i].record(copy_stream)
 
     def run(steps):
@@ -70,7 +83,12 @@ def run_sharded(args):
                 ev_done[i].record(torch.cuda.current_stream(dev))
         else:
             for _ in range(steps):
-                xdev.copy_(hx, non_blocking=True)
+                if raw16 is not None:
+                    raw16[0].copy_(h16, non_blocking=True)
+                    check(lib.pysdr_cs16_to_cf32(ctypes.c_void_p(raw16[0].data_ptr()), ctypes.c_void_p(xdev.data_ptr()), n_loc,
+                                                 1.0 / 2048.0, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+                else:
+                    xdev.copy_(hx, non_blocking=True)
                 am, _ = sh.step(xdev)
         return am
 
@@ -98,7 +116,8 @@ def run_sharded(args):
                           "k1_last": cb.banks[0].k1_last,
                           "n_gpus": world, "ms_per_step": ms, "Msamples_per_s": world * pl['n'] / ms / 1e3,
                           "realtime_factor": sec / (ms / 1e3), "one_hour_capture_s": 3600.0 / (sec / (ms / 1e3)),
-                          "h2d_bytes_per_rank_per_step": int(n_loc * 8), "collective_bytes_per_rank": int(args.channels * 19 * 8),
+                          "h2d_bytes_per_rank_per_step": int(n_loc * (4 if args.cs16 else 8)),
+                          "capture_format": "cs16 (int16 I/Q, scaled on the device)" if args.cs16 else "complex64", "collective_bytes_per_rank": int(args.channels * 19 * 8),
                           "audio_samples_per_channel_per_rank": int(am[0].numel())}))
     dist.destroy_process_group()
 
@@ -109,6 +128,7 @@ def main():
     ap.add_argument("--channels", type=int, default=1024)
     ap.add_argument("--block-chunks", type=int, default=188, help="IN_CHUNK_SIZE chunks per streaming block (188 = 4.0 s)")
     ap.add_argument("--any-offsets", action="store_true", help="sharded mode: no raster, every bank's K1 on the tensor cores (k1_chan)")
+    ap.add_argument("--cs16", action="store_true", help="sharded mode: the host capture is int16 I/Q (4 bytes per sample over PCIe)")
     ap.add_argument("--no-overlap", dest="overlap", action="store_false", help="sharded mode: copy then compute on one stream")
     ap.add_argument("--group", type=int, default=128, help="receivers per bank (any-offsets mode): 128 = two column groups of 64 "
                     "channels per bank on the tensor-core K1, 96 = one group of 96")
