@@ -391,3 +391,14 @@ def _emulate_k1chan_plan(up, down, lp, n_rx, n0, n_in, x_odd, allow_decline=Fals
     if not allow_decline:
         assert out_hi - out_lo > 0.5 * n_out
     return 1
+
+
+def test_bench_and_tools_compile():
+    """bench.py, __graft_entry__.py and every script under tools/ at least byte-compile (they only run on a GPU box)."""
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] + sorted(glob.glob(os.path.join(root, "tools", "*.py")))
+    assert len(files) >= 8
+    for f in files:
+        with open(f) as fh:
+            compile(fh.read(), f, "exec")
